@@ -1,0 +1,332 @@
+"""ctypes binding of libcasing_b200.so (C ABI in include/casing_b200.h).
+
+PyTorch is used only to own device buffers; every computation happens in the
+hand-written sm_100a kernels behind the C ABI.  There is NO CPU fallback: if
+the shared library is missing or no CUDA device is present, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcasing_b200.so")
+
+KIND_DC, KIND_DC_GROUNDED, KIND_EDGE_H, KIND_EDGE_E, KIND_FACE_J, KIND_FACE_B = range(6)
+INFO_LEN = 16
+INFO_NAMES = ["iters", "relres", "ms_assemble", "ms_factor", "ms_solve", "n_apply", "n_launch", "bytes", "converged"]
+
+_lib = None
+
+
+class CasingB200Error(RuntimeError):
+    pass
+
+
+def build_library(verbose=False):
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import subprocess
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    res = subprocess.run(["bash", script], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise CasingB200Error("nvcc build of libcasing_b200.so failed:\n" + res.stderr[-4000:])
+    return LIB_PATH
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CasingB200Error(
+            "libcasing_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+            "this package has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, dp, ip, ll = c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_int), c.c_longlong
+    sig = {
+        "cs_last_error": (c.c_char_p, []),
+        "cs_launch_count": (ll, []),
+        "cs_ctx_create": (c.c_int, [c.c_int, vp, c.POINTER(vp)]),
+        "cs_ctx_destroy": (c.c_int, [vp]),
+        "cs_ctx_sync": (c.c_int, [vp]),
+        "cs_mesh_set": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, dp, dp, dp, c.c_double, c.c_double, c.c_double]),
+        "cs_mesh_counts": (c.c_int, [vp, c.POINTER(ll)]),
+        "cs_model_paint": (c.c_int, [vp, dp, vp, vp]),
+        "cs_model_set": (c.c_int, [vp, vp, vp]),
+        "cs_face_inner_product": (c.c_int, [vp, vp, c.c_int, c.c_int, vp]),
+        "cs_edge_inner_product": (c.c_int, [vp, vp, c.c_int, c.c_int, vp]),
+        "cs_curl": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_curlT": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_div": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_divT": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_op_get": (c.c_int, [vp, c.c_int, c.POINTER(vp)]),
+        "cs_op_size": (ll, [vp]),
+        "cs_op_apply": (c.c_int, [vp, dp, vp, vp, c.c_int, c.c_int]),
+        "cs_op_factor": (c.c_int, [vp, dp, c.c_int, c.c_int]),
+        "cs_op_solve": (c.c_int, [vp, vp, vp, c.c_int, ip, c.c_int, c.c_double, c.c_int, dp]),
+        "cs_op_clean": (c.c_int, [vp]),
+        "cs_solve_dc": (c.c_int, [vp, vp, vp, c.c_int, c.c_double, c.c_int, dp]),
+        "cs_solve_fdem": (c.c_int, [vp, c.c_int, dp, c.c_int, vp, vp, c.c_double, c.c_int, dp]),
+        "cs_tdem_run": (c.c_int, [vp, c.c_int, dp, c.c_int, vp, vp, c.c_double, c.c_int, dp]),
+        "cs_fields_fdem": (c.c_int, [vp, c.c_int, c.c_int, c.c_double, vp, vp, vp]),
+        "cs_fields_dc": (c.c_int, [vp, c.c_int, vp, vp, c.c_int]),
+        "cs_casing_currents": (c.c_int, [vp, vp, c.c_int, c.c_double, c.c_double, c.c_double, c.c_double, vp, vp]),
+        "cs_casing_charges": (c.c_int, [vp, vp, c.c_double, c.c_double, c.c_double, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_mesh_set",
+    "cs_mesh_counts", "cs_model_paint", "cs_model_set", "cs_face_inner_product", "cs_edge_inner_product",
+    "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_op_get", "cs_op_size", "cs_op_apply", "cs_op_factor",
+    "cs_op_solve", "cs_op_clean", "cs_solve_dc", "cs_solve_fdem", "cs_tdem_run", "cs_fields_fdem",
+    "cs_fields_dc", "cs_casing_currents", "cs_casing_charges",
+]
+
+
+def check(rc):
+    if rc != 0:
+        raise CasingB200Error(load_library().cs_last_error().decode("utf-8", "replace"))
+
+
+def _dptr(a):
+    return np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise CasingB200Error("no CUDA device: casingsimulations_b200 has no CPU fallback")
+    return torch
+
+
+def _tptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Op(object):
+    """One assembled operator (weights + theta-mode band matrices) of a Context."""
+
+    def __init__(self, ctx, kind):
+        self.ctx, self.kind = ctx, kind
+        h = ctypes.c_void_p()
+        check(ctx.lib.cs_op_get(ctx.h, kind, ctypes.byref(h)))
+        self.h = h
+        self.n = int(ctx.lib.cs_op_size(h))
+
+    def apply(self, x, shifts=None):
+        """y = A(s) x; x torch tensor (nvec, n) or (n,), float64 or complex128."""
+        torch = _torch()
+        x2 = x.reshape(-1, self.n).contiguous()
+        nvec = x2.shape[0]
+        y = torch.empty_like(x2)
+        sh = np.zeros(2 * nvec)
+        if shifts is not None:
+            s = np.atleast_1d(np.asarray(shifts, dtype=complex))
+            s = np.broadcast_to(s, (nvec,))
+            sh[0::2], sh[1::2] = s.real, s.imag
+        check(self.ctx.lib.cs_op_apply(self.h, _dptr(sh), _tptr(x2), _tptr(y), nvec, int(x2.is_complex())))
+        return y.reshape(x.shape)
+
+    def factor(self, shifts=(0.0,)):
+        s = np.atleast_1d(np.asarray(shifts, dtype=complex))
+        sh = np.zeros(2 * len(s))
+        sh[0::2], sh[1::2] = s.real, s.imag
+        cplx = int(np.any(s.imag != 0))
+        check(self.ctx.lib.cs_op_factor(self.h, _dptr(sh), len(s), cplx))
+        self._complex_shift = bool(cplx)
+
+    def solve(self, rhs, shift_of_vec=None, rtol=1e-10, maxit=50):
+        torch = _torch()
+        r2 = rhs.reshape(-1, self.n).contiguous()
+        nvec = r2.shape[0]
+        x = torch.empty_like(r2)
+        info = np.zeros(INFO_LEN)
+        sov = None
+        if shift_of_vec is not None:
+            sov = np.ascontiguousarray(shift_of_vec, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+        rc = self.ctx.lib.cs_op_solve(self.h, _tptr(r2), _tptr(x), nvec, sov, int(r2.is_complex()), rtol, maxit,
+                                      info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self.info = dict(zip(INFO_NAMES, info))
+        check(rc)
+        return x.reshape(rhs.shape)
+
+    def clean(self):
+        check(self.ctx.lib.cs_op_clean(self.h))
+
+
+class Context(object):
+    """A solver context bound to one CUDA device (mirrors cs_ctx)."""
+
+    def __init__(self, device=0):
+        torch = _torch()
+        self.lib = load_library()
+        self.device = torch.device("cuda", device)
+        h = ctypes.c_void_p()
+        check(self.lib.cs_ctx_create(device, None, ctypes.byref(h)))
+        self.h = h
+        self.info = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cs_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.cs_ctx_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.cs_launch_count())
+
+    # -- mesh / model -------------------------------------------------------
+    def set_mesh(self, hx, hy, hz, z0, axis_weight_edge=1.0, axis_weight_face=0.5):
+        hx, hy, hz = [np.ascontiguousarray(np.atleast_1d(h), dtype=np.float64) for h in (hx, hy, hz)]
+        self.nx, self.nth, self.nz = len(hx), len(hy), len(hz)
+        check(self.lib.cs_mesh_set(self.h, self.nx, self.nth, self.nz, _dptr(hx), _dptr(hy), _dptr(hz), float(z0),
+                                   float(axis_weight_edge), float(axis_weight_face)))
+        cnt = (ctypes.c_longlong * 7)()
+        check(self.lib.cs_mesh_counts(self.h, cnt))
+        self.nC, self.nFx, self.nFy, self.nFz, self.nEx, self.nEy, self.nEz = [int(v) for v in cnt]
+        self.nF, self.nE = self.nFx + self.nFy + self.nFz, self.nEx + self.nEy + self.nEz
+
+    def empty(self, n, complex_=False, cols=None):
+        torch = _torch()
+        shape = (n,) if cols is None else (cols, n)
+        return torch.empty(shape, dtype=torch.complex128 if complex_ else torch.float64, device=self.device)
+
+    def to_device(self, a, complex_=None):
+        torch = _torch()
+        a = np.asarray(a)
+        if complex_ is None:
+            complex_ = np.iscomplexobj(a)
+        a = np.ascontiguousarray(a, dtype=np.complex128 if complex_ else np.float64)
+        return torch.from_numpy(a).to(self.device)
+
+    def paint(self, params):
+        """params: the 18 doubles of k_paint.  Returns (sigma, mu) device tensors."""
+        sigma, mu = self.empty(self.nC), self.empty(self.nC)
+        check(self.lib.cs_model_paint(self.h, _dptr(np.asarray(params, dtype=np.float64)), _tptr(sigma), _tptr(mu)))
+        return sigma, mu
+
+    def set_model(self, sigma, mu):
+        sigma = sigma if hasattr(sigma, "data_ptr") else self.to_device(sigma, False)
+        mu = mu if hasattr(mu, "data_ptr") else self.to_device(mu, False)
+        assert sigma.numel() == self.nC and mu.numel() == self.nC
+        check(self.lib.cs_model_set(self.h, _tptr(sigma), _tptr(mu)))
+
+    # -- building blocks ----------------------------------------------------
+    def face_inner_product(self, prop=None, invProp=False, invMat=False):
+        out = self.empty(self.nF)
+        p = ctypes.c_void_p(0) if prop is None else _tptr(prop)
+        check(self.lib.cs_face_inner_product(self.h, p, int(invProp), int(invMat), _tptr(out)))
+        return out
+
+    def edge_inner_product(self, prop=None, invProp=False, invMat=False):
+        out = self.empty(self.nE)
+        p = ctypes.c_void_p(0) if prop is None else _tptr(prop)
+        check(self.lib.cs_edge_inner_product(self.h, p, int(invProp), int(invMat), _tptr(out)))
+        return out
+
+    def _unary(self, fn, x, nin, nout):
+        assert x.numel() == nin
+        y = self.empty(nout, x.is_complex())
+        check(fn(self.h, _tptr(x.contiguous()), _tptr(y), int(x.is_complex())))
+        return y
+
+    def curl(self, xE):
+        return self._unary(self.lib.cs_curl, xE, self.nE, self.nF)
+
+    def curlT(self, xF):
+        return self._unary(self.lib.cs_curlT, xF, self.nF, self.nE)
+
+    def div(self, xF):
+        return self._unary(self.lib.cs_div, xF, self.nF, self.nC)
+
+    def divT(self, xC):
+        return self._unary(self.lib.cs_divT, xC, self.nC, self.nF)
+
+    def op(self, kind):
+        return Op(self, kind)
+
+    # -- physics-level drivers ----------------------------------------------
+    def _info(self, info):
+        self.info = dict(zip(INFO_NAMES, info))
+
+    def solve_dc(self, q, rtol=1e-10, maxit=50):
+        """q: (nrhs, nC) device tensor -> phi (nrhs, nC)."""
+        torch = _torch()
+        q2 = q.reshape(-1, self.nC).contiguous()
+        phi = torch.empty_like(q2)
+        info = np.zeros(INFO_LEN)
+        rc = self.lib.cs_solve_dc(self.h, _tptr(q2), _tptr(phi), q2.shape[0], rtol, maxit,
+                                  info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self._info(info)
+        check(rc)
+        return phi.reshape(q.shape)
+
+    def solve_fdem(self, form, freqs, s_e, rtol=1e-10, maxit=50):
+        """s_e: real face vector (device); returns (nfreq, n) complex solutions."""
+        freqs = np.ascontiguousarray(np.atleast_1d(freqs), dtype=np.float64)
+        n = self.nE if form == "h" else self.nF
+        u = self.empty(n, True, cols=len(freqs))
+        info = np.zeros(INFO_LEN)
+        rc = self.lib.cs_solve_fdem(self.h, ord(form), _dptr(freqs), len(freqs), _tptr(s_e.contiguous()), _tptr(u),
+                                    rtol, maxit, info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self._info(info)
+        check(rc)
+        return u
+
+    def tdem_run(self, form, dts, s_e, rtol=1e-10, maxit=50):
+        dts = np.ascontiguousarray(dts, dtype=np.float64)
+        out = self.empty(self.nF, False, cols=len(dts) + 1)
+        info = np.zeros(INFO_LEN)
+        rc = self.lib.cs_tdem_run(self.h, ord(form), _dptr(dts), len(dts), _tptr(s_e.contiguous()), _tptr(out),
+                                  rtol, maxit, info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self._info(info)
+        check(rc)
+        return out
+
+    def fields_fdem(self, form, which, freq, u, s_e):
+        n = self.nF if which in ("j", "e") else self.nE
+        out = self.empty(n, True)
+        check(self.lib.cs_fields_fdem(self.h, ord(form), ord(which), float(freq), _tptr(u.contiguous()),
+                                      _tptr(s_e.contiguous()), _tptr(out)))
+        return out
+
+    def fields_dc(self, which, phi):
+        phi2 = phi.reshape(-1, self.nC).contiguous()
+        n = self.nC if which == "charge" else self.nF
+        out = self.empty(n, False, cols=phi2.shape[0])
+        code = {"j": "j", "e": "e", "charge": "c"}[which]
+        check(self.lib.cs_fields_dc(self.h, ord(code), _tptr(phi2), _tptr(out), phi2.shape[0]))
+        return out
+
+    def casing_currents(self, j, casing_a, casing_b, casing_z):
+        j = j.contiguous()
+        ix = self.empty(self.nz, j.is_complex())
+        iz = self.empty(self.nz + 1, j.is_complex())
+        check(self.lib.cs_casing_currents(self.h, _tptr(j), int(j.is_complex()), casing_a, casing_b,
+                                          float(casing_z[0]), float(casing_z[1]), _tptr(ix), _tptr(iz)))
+        return ix, iz
+
+    def casing_charges(self, charge, casing_b, casing_z):
+        out = self.empty(self.nz)
+        check(self.lib.cs_casing_charges(self.h, _tptr(charge.contiguous()), casing_b, float(casing_z[0]),
+                                         float(casing_z[1]), _tptr(out)))
+        return out

@@ -1,0 +1,946 @@
+// C ABI of libcasing_b200 (see include/casing_b200.h): context, operator objects,
+// batched preconditioned BiCGStab, and the physics-level DC / FDEM / TDEM drivers.
+#include "../../include/casing_b200.h"
+#include "cs_internal.h"
+#include <complex>
+#include <map>
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace cs {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+static long long g_launches = 0;
+}  // namespace cs
+
+using namespace cs;
+typedef std::complex<double> zc;
+
+// ------------------------------------------------------------------ structs --
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return CS_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        CS_CUDA(cudaMalloc(&p, need));
+        bytes = need;
+        return CS_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct cs_op {
+    cs_ctx* ctx = nullptr;
+    int kind = 0, family = 0;        // family: 0 cell, 1 edge, 2 face
+    long long n = 0;                 // vector length
+    double *w1 = nullptr, *w2 = nullptr, *mass = nullptr;
+    double shift0 = 0.0;
+    BandPlan bp;
+    DevBuf LU, wts;               // wts: [nshift][n] = 1/|diag A(s)|, the norm of the convergence tests
+    bool lu_cplx = false;
+    std::vector<zc> shifts;
+    double ms_assemble = 0.0, ms_factor = 0.0;
+};
+
+struct cs_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    MeshD m;
+    bool has_mesh = false, has_model = false;
+    std::vector<double> hx, hth, hz, rn, zn;
+    double* tables = nullptr;      // hx | rn | ring | hth | hz | zn
+    double* zn_d = nullptr;
+    double *sigma = nullptr, *mu = nullptr;
+    std::map<int, cs_op*> ops;
+    DevBuf work, scal, modes, tmp1, tmp2;
+    double* pin = nullptr;         // pinned host scratch
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static void op_free(cs_op* op) {
+    if (!op) return;
+    cudaFree(op->w1); cudaFree(op->w2);
+    if (op->family == 2) cudaFree(op->mass);   // edge family: mass aliases w2
+    cudaFree(op->bp.map3d); cudaFree(op->bp.jstr); cudaFree(op->bp.mdiag); cudaFree(op->bp.Kband);
+    op->LU.release(); op->wts.release();
+    delete op;
+}
+static void ctx_drop_ops(cs_ctx* c) {
+    for (auto& kv : c->ops) op_free(kv.second);
+    c->ops.clear();
+}
+
+// ------------------------------------------------------------- small kernels --
+__global__ void k_gather_diag(const long long* __restrict__ map3d, const double* __restrict__ mass, long long n2, double* __restrict__ out) {
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= n2) return;
+    long long b = map3d[q];
+    out[q] = (b >= 0 && mass) ? mass[b] : 0.0;
+}
+// y = a*x (+ b*y) with immediate real scalars, real or complex vectors viewed as doubles
+__global__ void k_scale_add(double* __restrict__ y, const double* __restrict__ x, long long n, double a, double b) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) y[t] = (b == 0.0) ? a * x[t] : a * x[t] + b * y[t];
+}
+__global__ void k_sub_real_from_cplx(cplx* __restrict__ y, const double* __restrict__ s, long long n) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) y[t].x -= s[t];
+}
+// rhs_j[f][i] = alpha[i] * (-i w_f) * s_e[i]
+__global__ void k_rhs_fdem_j(const double* __restrict__ alpha, const double* __restrict__ se, long long n, const double* __restrict__ w, cplx* __restrict__ out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int f = blockIdx.y;
+    out[f * n + t] = mk(0.0, -w[f] * alpha[t] * se[t]);
+}
+// K9: masked area-weighted sums over (r, theta) per z level (physics.py:29-57)
+template <typename T>
+__global__ void k_casing_currents(MeshD m, const double* __restrict__ zn, const T* __restrict__ j, double a, double b, double z0, double z1,
+                                  T* __restrict__ ix, T* __restrict__ iz) {
+    int k = blockIdx.x;   // 0..nz
+    __shared__ double sx[2][32], sz[2][32];
+    double axr = 0, axi = 0, azr = 0, azi = 0;
+    bool zin_n = (zn[k] <= z1) && (zn[k] >= z0);
+    bool zin_c = false;
+    if (k < m.nz) { double zcc = 0.5 * (zn[k] + zn[k + 1]); zin_c = (zcc <= z1) && (zcc >= z0); }
+    const T* jx = j;
+    const T* jz = j + m.nFx + m.nFy;
+    for (long long t = threadIdx.x; t < m.nxy; t += blockDim.x) {
+        int i = (int)(t % m.nx), jj = (int)(t / m.nx);
+        double rf = m.rn[i + 1], rc = 0.5 * (m.rn[i] + m.rn[i + 1]);
+        if (zin_c && rf >= a && rf <= b) {
+            T v = m.aFx(i, jj, k) * jx[m.cidx(i, jj, k)];
+            axr += Sc<T>::re(v); axi += Sc<T>::im(v);
+        }
+        if (zin_n && rc >= a && rc <= b) {
+            T v = m.aFz(i, jj) * jz[m.cidx(i, jj, k)];
+            azr += Sc<T>::re(v); azi += Sc<T>::im(v);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        axr += __shfl_down_sync(0xffffffffu, axr, o); axi += __shfl_down_sync(0xffffffffu, axi, o);
+        azr += __shfl_down_sync(0xffffffffu, azr, o); azi += __shfl_down_sync(0xffffffffu, azi, o);
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sx[0][w] = axr; sx[1][w] = axi; sz[0][w] = azr; sz[1][w] = azi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { r0 += sx[0][q]; r1 += sx[1][q]; r2 += sz[0][q]; r3 += sz[1][q]; }
+        if (k < m.nz) ix[k] = Sc<T>::from(r0, r1);
+        iz[k] = Sc<T>::from(r2, r3);
+    }
+}
+__global__ void k_casing_charges(MeshD m, const double* __restrict__ zn, const double* __restrict__ ch, double rlim, double z0, double z1, double* __restrict__ out) {
+    int k = blockIdx.x;
+    __shared__ double s[32];
+    double zcc = 0.5 * (zn[k] + zn[k + 1]);
+    bool zin = (zcc < z1) && (zcc > z0);
+    double acc = 0;
+    for (long long t = threadIdx.x; t < m.nxy; t += blockDim.x) {
+        int i = (int)(t % m.nx), jj = (int)(t / m.nx);
+        double rc = 0.5 * (m.rn[i] + m.rn[i + 1]);
+        if (zin && rc <= rlim) acc += ch[m.cidx(i, jj, k)];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) s[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double r = 0; for (int q = 0; q < (int)(blockDim.x >> 5); ++q) r += s[q]; out[k] = r; }
+}
+
+static inline size_t esz(bool c) { return c ? sizeof(cplx) : sizeof(double); }
+
+// --------------------------------------------------------------- operator -----
+static int op_apply_dev(cs_op* op, const double* s_d, const void* x, void* y, int nvec, bool cplx_vec) {
+    cs_ctx* c = op->ctx;
+    g_launches += 1;
+    if (op->family == 0) return launch_dc_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st);
+    if (op->family == 1) return launch_edge_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st);
+    return launch_face_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st);
+}
+static double op_bytes_per_apply(cs_op* op, bool cplx_vec) {
+    const MeshD& m = op->ctx->m;
+    double v = cplx_vec ? 16.0 : 8.0;
+    if (op->family == 0) return (double)m.nC * (2 * v + (m.sym ? 16.0 : 24.0));
+    if (m.sym) return (double)m.nC * (op->family == 1 ? (2 * v + 16.0 + 8.0) : (4 * v + 16.0 + 8.0));
+    return (double)m.nC * (6 * v + 24.0 + 24.0);
+}
+
+static int build_plan(cs_op* op) {
+    cs_ctx* c = op->ctx;
+    const MeshD& m = c->m;
+    BandPlan& bp = op->bp;
+    int nx = m.nx, nth = m.nth, nz = m.nz;
+    std::vector<long long> map;
+    std::vector<int> js;
+    long long L;
+    if (op->family == 0) {
+        L = nx; bp.n2 = (long long)nx * nz; bp.p = nx;
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) map[k * L + i] = i + (long long)nx * nth * k;
+    } else if (op->family == 1 && m.sym) {
+        L = nx; bp.n2 = (long long)nx * (nz + 1); bp.p = nx;
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        for (int k = 0; k <= nz; ++k) for (int i = 0; i < nx; ++i) map[k * L + i] = i + (long long)nx * k;
+    } else if (op->family == 1) {
+        L = 3LL * nx + 1; bp.n2 = L * (nz + 1); bp.p = (int)L + 2;
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        for (int k = 0; k <= nz; ++k) {
+            for (int i = 0; i < nx; ++i) {
+                long long q = k * L + 3 * i;
+                map[q] = i + m.nxy * k;
+                map[q + 1] = m.nEx + i + m.nxy * k;
+                if (k < nz) map[q + 2] = m.nEx + m.nEy + m.ez(i, 0, k);
+            }
+            if (k < nz) { long long q = k * L + 3 * nx; map[q] = m.nEx + m.nEy + m.ezaxis(k); js[q] = 0; }
+        }
+    } else if (m.sym) {
+        L = 2LL * nx; bp.n2 = L * (nz + 1); bp.p = (int)L + 2;
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        for (int k = 0; k <= nz; ++k) for (int i = 0; i < nx; ++i) {
+            long long q = k * L + 2 * i;
+            map[q] = m.nFx + i + (long long)nx * k;           // Fz(i,k)
+            if (k < nz) map[q + 1] = i + (long long)nx * k;   // Fx(i,k)
+        }
+    } else {
+        L = 3LL * nx; bp.n2 = L * (nz + 1); bp.p = (int)L + 3;
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        for (int k = 0; k <= nz; ++k) for (int i = 0; i < nx; ++i) {
+            long long q = k * L + 3 * i;
+            map[q] = m.nFx + m.nFy + i + m.nxy * k;           // Fz
+            if (k < nz) { map[q + 1] = i + m.nxy * k; map[q + 2] = m.nFx + i + m.nxy * k; }
+        }
+    }
+    if (bp.p > bp.n2 - 1) bp.p = (int)std::max(1LL, bp.n2 - 1);
+    bp.nb = 16;
+    bp.pw = bp.p + bp.nb;
+    bp.ldab = 2 * bp.pw + 1;
+    bp.nmodes = nth;
+    bp.cplx_band = (nth > 1);
+    CS_CUDA(cudaMalloc(&bp.map3d, bp.n2 * sizeof(long long)));
+    CS_CUDA(cudaMalloc(&bp.jstr, bp.n2 * sizeof(int)));
+    CS_CUDA(cudaMalloc(&bp.mdiag, bp.n2 * sizeof(double)));
+    CS_CUDA(cudaMemcpyAsync(bp.map3d, map.data(), bp.n2 * sizeof(long long), cudaMemcpyHostToDevice, c->st));
+    CS_CUDA(cudaMemcpyAsync(bp.jstr, js.data(), bp.n2 * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    k_gather_diag<<<cdiv(bp.n2, 256), 256, 0, c->st>>>(bp.map3d, op->mass, bp.n2, bp.mdiag);
+    CS_CUDA(cudaGetLastError());
+    size_t kb = (size_t)bp.nmodes * bp.band_elems() * esz(bp.cplx_band);
+    CS_CUDA(cudaMalloc(&bp.Kband, kb));
+    CS_CUDA(cudaMemsetAsync(bp.Kband, 0, kb, c->st));
+    return CS_OK;
+}
+
+// probe the s-independent part of the operator into the per-mode band matrices
+static int probe_plan(cs_op* op) {
+    cs_ctx* c = op->ctx;
+    BandPlan& bp = op->bp;
+    bool cv = bp.cplx_band;
+    CS_TRY(c->tmp1.ensure((size_t)op->n * esz(cv)));
+    CS_TRY(c->tmp2.ensure((size_t)op->n * esz(cv)));
+    CS_TRY(c->modes.ensure((size_t)bp.nmodes * bp.n2 * esz(cv)));
+    CS_TRY(c->scal.ensure(4096));
+    CS_CUDA(cudaMemsetAsync(c->scal.p, 0, 4096, c->st));     // shift 0
+    int ncol = 2 * bp.p + 1;
+    double sh0 = op->shift0;
+    for (int col = 0; col < ncol; ++col) {
+        CS_TRY(band_probe_fill(bp, col, c->tmp1.p, op->n, cv, c->st));
+        CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, 1, cv));
+        CS_TRY(band_dft_gather(bp, c->tmp2.p, cv, c->modes.p, cv, bp.nmodes, op->n, 1, c->st));
+        CS_TRY(band_probe_store(bp, col, c->modes.p, c->st));
+        g_launches += 4;
+    }
+    (void)sh0;
+    return CS_OK;
+}
+
+extern "C" int cs_op_get(cs_ctx* c, int kind, cs_op** out) {
+    CS_CHECK(c && c->has_mesh && c->has_model, "mesh and model must be set first");
+    auto it = c->ops.find(kind);
+    if (it != c->ops.end()) { *out = it->second; return CS_OK; }
+    CS_CUDA(cudaSetDevice(c->device));
+    const MeshD& m = c->m;
+    cs_op* op = new cs_op();
+    op->ctx = c; op->kind = kind;
+    CS_CUDA(cudaEventRecord(c->ev0, c->st));
+    CS_TRY(c->tmp1.ensure((size_t)std::max(m.nF, m.nE) * sizeof(double)));
+    double* t1 = (double*)c->tmp1.p;
+    int rc = CS_OK;
+    auto fail = [&](int r) { op_free(op); return r; };
+    if (kind == CS_KIND_DC || kind == CS_KIND_DC_GROUNDED) {
+        op->family = 0; op->n = m.nC; op->shift0 = (kind == CS_KIND_DC_GROUNDED) ? 1.0 : 0.0;
+        if (cudaMalloc(&op->w1, m.nF * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(CS_ERR); }
+        rc = launch_face_ip(m, c->sigma, 1, 0, t1, c->st); if (rc) return fail(rc);       // MfRho
+        rc = launch_face_scale(m, t1, op->w1, 0, c->st); if (rc) return fail(rc);         // area^2 / MfRho
+    } else if (kind == CS_KIND_EDGE_H || kind == CS_KIND_EDGE_E) {
+        op->family = 1; op->n = m.nE;
+        if (cudaMalloc(&op->w1, m.nF * sizeof(double)) != cudaSuccess || cudaMalloc(&op->w2, m.nE * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(CS_ERR); }
+        const double* pa = (kind == CS_KIND_EDGE_H) ? c->sigma : c->mu;     // alpha = Mf(1/prop)
+        const double* pb = (kind == CS_KIND_EDGE_H) ? c->mu : c->sigma;     // beta  = Me(prop)
+        rc = launch_face_ip(m, pa, 1, 0, t1, c->st); if (rc) return fail(rc);
+        rc = launch_face_scale(m, t1, op->w1, 1, c->st); if (rc) return fail(rc);         // alpha / area^2
+        rc = launch_edge_ip(m, pb, 0, 0, op->w2, c->st); if (rc) return fail(rc);
+        op->mass = op->w2;
+    } else if (kind == CS_KIND_FACE_J || kind == CS_KIND_FACE_B) {
+        op->family = 2; op->n = m.nF;
+        if (cudaMalloc(&op->w1, m.nF * sizeof(double)) != cudaSuccess || cudaMalloc(&op->w2, m.nE * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&op->mass, m.nF * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(CS_ERR); }
+        const double* pa = (kind == CS_KIND_FACE_J) ? c->sigma : c->mu;     // alpha = Mf(1/prop)
+        const double* pg = (kind == CS_KIND_FACE_J) ? c->mu : c->sigma;     // gamma = 1/Me(prop)
+        rc = launch_face_ip(m, pa, 1, 0, op->mass, c->st); if (rc) return fail(rc);       // alpha
+        rc = launch_face_scale(m, op->mass, op->w1, 2, c->st); if (rc) return fail(rc);   // alpha / area
+        rc = launch_edge_ip(m, pg, 0, 1, t1, c->st); if (rc) return fail(rc);             // 1/Me(prop)
+        rc = launch_edge_scale(m, t1, op->w2, 0, c->st); if (rc) return fail(rc);         // len^2 * gamma
+    } else {
+        set_error("unknown operator kind");
+        return fail(CS_ERR);
+    }
+    g_launches += 4;
+    rc = build_plan(op); if (rc) return fail(rc);
+    rc = probe_plan(op); if (rc) return fail(rc);
+    cudaEventRecord(c->ev1, c->st);
+    if (cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("sync failed in cs_op_get"); return fail(CS_ERR); }
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    op->ms_assemble = ms;
+    c->ops[kind] = op;
+    *out = op;
+    return CS_OK;
+}
+
+extern "C" long long cs_op_size(cs_op* op) { return op ? op->n : -1; }
+
+extern "C" int cs_op_apply(cs_op* op, const double* shifts_h, const void* x_d, void* y_d, int nvec, int is_complex) {
+    CS_CHECK(op, "null op");
+    cs_ctx* c = op->ctx;
+    CS_CUDA(cudaSetDevice(c->device));
+    CS_TRY(c->scal.ensure(std::max<size_t>(4096, 2 * nvec * sizeof(double))));
+    if (shifts_h) CS_CUDA(cudaMemcpyAsync(c->scal.p, shifts_h, 2 * nvec * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    else CS_CUDA(cudaMemsetAsync(c->scal.p, 0, 2 * nvec * sizeof(double), c->st));
+    return op_apply_dev(op, (const double*)c->scal.p, x_d, y_d, nvec, is_complex != 0);
+}
+
+extern "C" int cs_op_clean(cs_op* op) {
+    CS_CHECK(op, "null op");
+    op->LU.release();
+    op->shifts.clear();
+    return CS_OK;
+}
+
+extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int complex_shift) {
+    CS_CHECK(op && nshift >= 1, "bad arguments");
+    cs_ctx* c = op->ctx;
+    CS_CUDA(cudaSetDevice(c->device));
+    BandPlan& bp = op->bp;
+    bool lc = bp.cplx_band || complex_shift != 0;
+    size_t need = (size_t)nshift * bp.nmodes * bp.band_elems() * esz(lc);
+    CS_TRY(op->LU.ensure(need));
+    op->lu_cplx = lc;
+    op->shifts.resize(nshift);
+    for (int f = 0; f < nshift; ++f) op->shifts[f] = zc(shifts_h[2 * f], shifts_h[2 * f + 1]);
+    CS_TRY(c->scal.ensure(std::max<size_t>(4096, 2 * nshift * sizeof(double))));
+    CS_CUDA(cudaEventRecord(c->ev0, c->st));
+    CS_CUDA(cudaMemcpyAsync(c->scal.p, shifts_h, 2 * nshift * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CS_TRY(op->wts.ensure((size_t)nshift * op->n * sizeof(double)));
+    CS_TRY(band_diag_weights(bp, (const double*)c->scal.p, nshift, op->n, (double*)op->wts.p, c->st));
+    CS_TRY(band_form_shifted(bp, (const double*)c->scal.p, nshift, op->LU.p, lc, c->st));
+    CS_TRY(band_factor(bp, op->LU.p, lc, nshift * bp.nmodes, c->st));
+    g_launches += 1 + 2 * ((bp.n2 + bp.nb - 1) / bp.nb);
+    CS_CUDA(cudaEventRecord(c->ev1, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    op->ms_factor = ms;
+    return CS_OK;
+}
+
+// ------------------------------------------------------- batched BiCGStab -----
+struct Krylov {
+    cs_op* op; cs_ctx* c; int nvec; bool cv; long long n; size_t vb;
+    char* base; double *s_d, *a_d, *b_d, *dots_d; int* sov_d;
+    std::vector<zc> sh;
+    long long n_apply = 0;
+    void* vec(int i) { return base + (size_t)i * vb; }
+    int dots(const void* a, const void* b, bool conj, std::vector<zc>& out, bool scaled = false) {
+        CS_TRY(launch_dot(a, b, n, nvec, cv, conj, dots_d, c->st, scaled ? (const double*)op->wts.p : nullptr, scaled ? sov_d : nullptr));
+        CS_CUDA(cudaMemcpyAsync(c->pin, dots_d, 2 * nvec * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CS_CUDA(cudaStreamSynchronize(c->st));
+        out.resize(nvec);
+        for (int v = 0; v < nvec; ++v) out[v] = zc(c->pin[2 * v], c->pin[2 * v + 1]);
+        g_launches += 2;
+        return CS_OK;
+    }
+    int axpby(void* y, const void* x, const std::vector<zc>& a, const std::vector<zc>& b) {
+        // scalars go through pinned memory; each call uses its own slot to stay async-safe
+        static const int SL = 64;
+        slot = (slot + 1) % SL;
+        double* ph = c->pin + 4096 + (size_t)slot * 4 * nvec;
+        for (int v = 0; v < nvec; ++v) { ph[2 * v] = a[v].real(); ph[2 * v + 1] = a[v].imag(); ph[2 * nvec + 2 * v] = b[v].real(); ph[2 * nvec + 2 * v + 1] = b[v].imag(); }
+        double* pd = a_d + (size_t)slot * 4 * nvec;
+        CS_CUDA(cudaMemcpyAsync(pd, ph, 4 * nvec * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        g_launches += 1;
+        return launch_axpby(y, x, n, nvec, cv, pd, pd + 2 * nvec, c->st);
+    }
+    int slot = 0;
+    int apply(const void* x, void* y) { n_apply++; return op_apply_dev(op, s_d, x, y, nvec, cv); }
+    int precond(const void* x, void* y) {
+        BandPlan& bp = op->bp;
+        CS_TRY(band_dft_gather(bp, x, cv, c->modes.p, op->lu_cplx, bp.nmodes, n, nvec, c->st));
+        CS_TRY(band_solve(bp, op->LU.p, op->lu_cplx, c->modes.p, op->lu_cplx, nvec, sov_d, c->st));
+        CS_TRY(band_dft_scatter(bp, c->modes.p, op->lu_cplx, y, cv, bp.nmodes, n, nvec, c->st));
+        g_launches += 3;
+        return CS_OK;
+    }
+};
+
+static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int* sov_h, bool cv,
+                        double rtol, int maxit, double* info) {
+    cs_ctx* c = op->ctx;
+    CS_CHECK(op->LU.p && !op->shifts.empty(), "cs_op_factor must be called before cs_op_solve");
+    CS_CHECK(cv || !(op->lu_cplx && !op->bp.cplx_band), "complex shift needs complex vectors");
+    CS_CHECK(nvec >= 1 && nvec <= 1024, "nvec out of range");
+    long long n = op->n;
+    Krylov K;
+    K.op = op; K.c = c; K.nvec = nvec; K.cv = cv; K.n = n; K.vb = (size_t)nvec * n * esz(cv);
+    K.vb = (K.vb + 255) & ~(size_t)255;
+    const int NV = 8;
+    CS_TRY(c->work.ensure(NV * K.vb));
+    K.base = (char*)c->work.p;
+    size_t scal_need = (2 * nvec + 64 * 4 * nvec + 2 * nvec * 260) * sizeof(double) + nvec * sizeof(int) + 1024;
+    CS_TRY(c->scal.ensure(std::max<size_t>(4096, scal_need)));
+    K.s_d = (double*)c->scal.p;
+    K.a_d = K.s_d + 2 * nvec;
+    K.dots_d = K.a_d + 64 * 4 * nvec;
+    K.sov_d = (int*)(K.dots_d + 2 * nvec * 260);
+    CS_TRY(c->modes.ensure((size_t)nvec * op->bp.nmodes * op->bp.n2 * esz(op->lu_cplx)));
+    // per-vector shifts
+    std::vector<int> sov(nvec, 0);
+    for (int v = 0; v < nvec; ++v) { sov[v] = sov_h ? sov_h[v] : 0; CS_CHECK(sov[v] >= 0 && sov[v] < (int)op->shifts.size(), "shift index out of range"); }
+    for (int v = 0; v < nvec; ++v) { c->pin[2 * v] = op->shifts[sov[v]].real(); c->pin[2 * v + 1] = op->shifts[sov[v]].imag(); }
+    CS_CUDA(cudaMemcpyAsync(K.s_d, c->pin, 2 * nvec * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CS_CUDA(cudaMemcpyAsync(K.sov_d, sov.data(), nvec * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+
+    void *r = K.vec(0), *rh = K.vec(1), *p = K.vec(2), *v_ = K.vec(3), *ph = K.vec(4), *sh = K.vec(5), *t = K.vec(6), *dx = K.vec(7);
+    size_t xb = (size_t)nvec * n * esz(cv);
+    std::vector<zc> one(nvec, zc(1, 0)), zero(nvec, zc(0, 0)), d1, d2, bn2;
+    CS_TRY(K.dots(rhs, rhs, true, bn2, true));
+    std::vector<double> bnorm(nvec);
+    for (int v = 0; v < nvec; ++v) bnorm[v] = std::sqrt(std::max(bn2[v].real(), 0.0));
+    CS_CUDA(cudaMemsetAsync(x, 0, xb, c->st));
+    CS_CUDA(cudaMemcpyAsync(r, rhs, xb, cudaMemcpyDeviceToDevice, c->st));
+    int total_it = 0;
+    double worst = 0.0;
+    bool all_ok = false;
+    for (int round = 0; round < 4 && !all_ok; ++round) {
+        // solve A dx = r by BiCGStab (right preconditioned), dx starts at 0
+        CS_CUDA(cudaMemsetAsync(dx, 0, xb, c->st));
+        CS_CUDA(cudaMemcpyAsync(rh, r, xb, cudaMemcpyDeviceToDevice, c->st));
+        CS_CUDA(cudaMemsetAsync(p, 0, xb, c->st));
+        CS_CUDA(cudaMemsetAsync(v_, 0, xb, c->st));
+        std::vector<zc> rho_old(nvec, 1), alpha(nvec, 1), omega(nvec, 1), rho, beta(nvec), tmp(nvec), tmp2(nvec);
+        std::vector<char> done(nvec, 0);
+        std::vector<double> rn(nvec);
+        CS_TRY(K.dots(r, r, true, d1, true));
+        for (int v = 0; v < nvec; ++v) { rn[v] = std::sqrt(std::max(d1[v].real(), 0.0)); if (bnorm[v] == 0.0 || rn[v] <= rtol * bnorm[v]) done[v] = 1; }
+        for (int it = 0; it < maxit; ++it) {
+            bool any = false;
+            for (int v = 0; v < nvec; ++v) any |= !done[v];
+            if (!any) break;
+            total_it++;
+            CS_TRY(K.dots(rh, r, true, rho));
+            for (int v = 0; v < nvec; ++v) {
+                if (done[v] || std::abs(rho[v]) == 0.0 || !std::isfinite(std::abs(rho[v]))) { done[v] = 1; beta[v] = 0; tmp[v] = 0; continue; }
+                beta[v] = (rho[v] / rho_old[v]) * (alpha[v] / omega[v]);
+                tmp[v] = -beta[v] * omega[v];
+            }
+            // p = r + beta (p - omega v)
+            CS_TRY(K.axpby(p, v_, tmp, beta));     // p = -beta*omega*v + beta*p
+            CS_TRY(K.axpby(p, r, one, one));       // p += r
+            CS_TRY(K.precond(p, ph));
+            CS_TRY(K.apply(ph, v_));
+            CS_TRY(K.dots(rh, v_, true, d1));
+            for (int v = 0; v < nvec; ++v) {
+                if (done[v]) { alpha[v] = 0; tmp[v] = 0; continue; }
+                alpha[v] = rho[v] / d1[v];
+                if (!std::isfinite(std::abs(alpha[v]))) { alpha[v] = 0; done[v] = 1; }
+                tmp[v] = -alpha[v];
+            }
+            CS_TRY(K.axpby(r, v_, tmp, one));      // s = r - alpha v   (stored in r)
+            CS_TRY(K.axpby(dx, ph, alpha, one));   // dx += alpha ph
+            CS_TRY(K.dots(r, r, true, d1, true));
+            std::vector<char> half(nvec, 0);
+            for (int v = 0; v < nvec; ++v) {
+                rn[v] = std::sqrt(std::max(d1[v].real(), 0.0));
+                if (!done[v] && rn[v] <= rtol * bnorm[v]) { half[v] = 1; }
+            }
+            bool all_half = true;
+            for (int v = 0; v < nvec; ++v) all_half &= (done[v] || half[v]);
+            if (all_half) { for (int v = 0; v < nvec; ++v) done[v] = 1; break; }
+            CS_TRY(K.precond(r, sh));
+            CS_TRY(K.apply(sh, t));
+            CS_TRY(K.dots(t, r, true, d1));
+            CS_TRY(K.dots(t, t, true, d2));
+            for (int v = 0; v < nvec; ++v) {
+                if (done[v] || half[v]) { omega[v] = done[v] ? omega[v] : zc(0, 0); tmp[v] = 0; tmp2[v] = 0; if (half[v]) done[v] = 1; continue; }
+                omega[v] = d1[v] / d2[v];
+                if (!std::isfinite(std::abs(omega[v])) || std::abs(omega[v]) == 0.0) { omega[v] = 0; done[v] = 1; }
+                tmp[v] = omega[v]; tmp2[v] = -omega[v];
+                rho_old[v] = rho[v];
+            }
+            CS_TRY(K.axpby(dx, sh, tmp, one));     // dx += omega sh
+            CS_TRY(K.axpby(r, t, tmp2, one));      // r = s - omega t
+            CS_TRY(K.dots(r, r, true, d1, true));
+            for (int v = 0; v < nvec; ++v) {
+                if (done[v]) continue;
+                rn[v] = std::sqrt(std::max(d1[v].real(), 0.0));
+                if (rn[v] <= rtol * bnorm[v]) done[v] = 1;
+            }
+        }
+        // x += dx ; true residual r = b - A x
+        CS_TRY(K.axpby(x, dx, one, one));
+        CS_TRY(K.apply(x, t));
+        CS_CUDA(cudaMemcpyAsync(r, rhs, xb, cudaMemcpyDeviceToDevice, c->st));
+        std::vector<zc> mone(nvec, zc(-1, 0));
+        CS_TRY(K.axpby(r, t, mone, one));
+        CS_TRY(K.dots(r, r, true, d1, true));
+        all_ok = true; worst = 0.0;
+        for (int v = 0; v < nvec; ++v) {
+            double rel = bnorm[v] > 0 ? std::sqrt(std::max(d1[v].real(), 0.0)) / bnorm[v] : 0.0;
+            if (!(rel <= rtol)) all_ok = false;
+            if (!(rel <= worst)) worst = rel;   // also catches NaN
+        }
+    }
+    if (info) {
+        info[CS_INFO_ITERS] = total_it;
+        info[CS_INFO_RELRES] = worst;
+        info[CS_INFO_N_APPLY] += (double)K.n_apply;
+        info[CS_INFO_BYTES] += (double)K.n_apply * nvec * op_bytes_per_apply(op, cv);
+        info[CS_INFO_CONVERGED] = all_ok ? 1.0 : 0.0;
+    }
+    if (!all_ok) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "Krylov solve did not reach rtol=%.1e: relative residual %.3e after %d iterations (no CPU fallback by design)", rtol, worst, total_it);
+        set_error(buf);
+        return CS_ERR;
+    }
+    return CS_OK;
+}
+
+extern "C" int cs_op_solve(cs_op* op, const void* rhs_d, void* x_d, int nvec, const int* shift_of_vec_h,
+                           int is_complex, double rtol, int maxit, double* info_h) {
+    CS_CHECK(op, "null op");
+    cs_ctx* c = op->ctx;
+    CS_CUDA(cudaSetDevice(c->device));
+    long long l0 = g_launches;
+    if (info_h) memset(info_h, 0, CS_INFO_LEN * sizeof(double));
+    CS_CUDA(cudaEventRecord(c->ev0, c->st));
+    int rc = krylov_solve(op, rhs_d, x_d, nvec, shift_of_vec_h, is_complex != 0, rtol, maxit, info_h);
+    cudaEventRecord(c->ev1, c->st);
+    cudaStreamSynchronize(c->st);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    if (info_h) {
+        info_h[CS_INFO_MS_SOLVE] = ms; info_h[CS_INFO_MS_FACTOR] = op->ms_factor; info_h[CS_INFO_MS_ASSEMBLE] = op->ms_assemble;
+        info_h[CS_INFO_N_LAUNCH] = (double)(g_launches - l0);
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------ ctx / mesh ------
+extern "C" const char* cs_last_error(void) { return cs::g_err.c_str(); }
+extern "C" long long cs_launch_count(void) { return cs::g_launches; }
+
+extern "C" int cs_ctx_create(int device, void* stream, cs_ctx** out) {
+    CS_CHECK(out, "null out");
+    int ndev = 0;
+    CS_CUDA(cudaGetDeviceCount(&ndev));
+    CS_CHECK(device >= 0 && device < ndev, "no such CUDA device (this library has no CPU fallback)");
+    CS_CUDA(cudaSetDevice(device));
+    cs_ctx* c = new cs_ctx();
+    c->device = device;
+    if (stream) { c->st = (cudaStream_t)stream; c->own_stream = false; }
+    else { CS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)); c->own_stream = true; }
+    CS_CUDA(cudaMallocHost((void**)&c->pin, (4096 + 64 * 4 * 1024 + 4096) * sizeof(double)));
+    CS_CUDA(cudaEventCreate(&c->ev0));
+    CS_CUDA(cudaEventCreate(&c->ev1));
+    memset(&c->m, 0, sizeof(MeshD));
+    *out = c;
+    return CS_OK;
+}
+
+extern "C" int cs_ctx_destroy(cs_ctx* c) {
+    if (!c) return CS_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    ctx_drop_ops(c);
+    cudaFree(c->tables); cudaFree(c->sigma); cudaFree(c->mu);
+    c->work.release(); c->scal.release(); c->modes.release(); c->tmp1.release(); c->tmp2.release();
+    cudaFreeHost(c->pin);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->st);
+    delete c;
+    return CS_OK;
+}
+extern "C" int cs_ctx_sync(cs_ctx* c) { CS_CHECK(c, "null ctx"); CS_CUDA(cudaStreamSynchronize(c->st)); return CS_OK; }
+
+extern "C" int cs_mesh_set(cs_ctx* c, int nx, int nth, int nz, const double* hx, const double* hth, const double* hz,
+                           double z0, double w_edge, double w_face) {
+    CS_CHECK(c && nx >= 1 && nth >= 1 && nz >= 1, "bad mesh sizes");
+    CS_CUDA(cudaSetDevice(c->device));
+    double sth = 0; for (int j = 0; j < nth; ++j) sth += hth[j];
+    CS_CHECK(std::fabs(sth - 2 * M_PI) < 1e-6, "hy must sum to 2*pi (mesh.py:408-411)");
+    ctx_drop_ops(c);
+    cudaFree(c->tables); cudaFree(c->sigma); cudaFree(c->mu);
+    c->tables = c->sigma = c->mu = nullptr; c->has_model = false;
+    c->hx.assign(hx, hx + nx); c->hth.assign(hth, hth + nth); c->hz.assign(hz, hz + nz);
+    c->rn.assign(nx + 1, 0.0); c->zn.assign(nz + 1, z0);
+    for (int i = 0; i < nx; ++i) c->rn[i + 1] = c->rn[i] + hx[i];
+    { double a = 0; for (int k = 0; k < nz; ++k) { a += hz[k]; c->zn[k + 1] = z0 + a; } }
+    std::vector<double> ring(nx);
+    for (int i = 0; i < nx; ++i) ring[i] = 0.5 * (c->rn[i + 1] * c->rn[i + 1] - c->rn[i] * c->rn[i]);
+    size_t tot = nx + (nx + 1) + nx + nth + nz + (nz + 1);
+    std::vector<double> h(tot);
+    size_t o = 0;
+    memcpy(&h[o], hx, nx * 8); size_t o_hx = o; o += nx;
+    memcpy(&h[o], c->rn.data(), (nx + 1) * 8); size_t o_rn = o; o += nx + 1;
+    memcpy(&h[o], ring.data(), nx * 8); size_t o_ring = o; o += nx;
+    memcpy(&h[o], hth, nth * 8); size_t o_hth = o; o += nth;
+    memcpy(&h[o], hz, nz * 8); size_t o_hz = o; o += nz;
+    memcpy(&h[o], c->zn.data(), (nz + 1) * 8); size_t o_zn = o; o += nz + 1;
+    CS_CUDA(cudaMalloc(&c->tables, tot * 8));
+    CS_CUDA(cudaMemcpy(c->tables, h.data(), tot * 8, cudaMemcpyHostToDevice));
+    MeshD& m = c->m;
+    m.nx = nx; m.nth = nth; m.nz = nz; m.sym = (nth == 1);
+    m.hx = c->tables + o_hx; m.rn = c->tables + o_rn; m.ring = c->tables + o_ring; m.hth = c->tables + o_hth; m.hz = c->tables + o_hz;
+    c->zn_d = c->tables + o_zn;
+    m.w_axis_edge = w_edge; m.w_axis_face = w_face;
+    m.nxy = (long long)nx * nth; m.ezp = m.nxy + 1;
+    m.nC = m.nxy * nz;
+    m.nFx = m.nC; m.nFy = m.sym ? 0 : m.nC; m.nFz = m.nxy * (nz + 1);
+    m.nEx = m.sym ? 0 : m.nxy * (nz + 1); m.nEy = m.nxy * (nz + 1); m.nEz = m.sym ? 0 : (long long)nz * m.ezp;
+    m.nF = m.nFx + m.nFy + m.nFz; m.nE = m.nEx + m.nEy + m.nEz;
+    CS_CUDA(cudaMalloc(&c->sigma, m.nC * 8));
+    CS_CUDA(cudaMalloc(&c->mu, m.nC * 8));
+    c->has_mesh = true;
+    return CS_OK;
+}
+
+extern "C" int cs_mesh_counts(cs_ctx* c, long long* o) {
+    CS_CHECK(c && c->has_mesh, "mesh not set");
+    const MeshD& m = c->m;
+    o[0] = m.nC; o[1] = m.nFx; o[2] = m.nFy; o[3] = m.nFz; o[4] = m.nEx; o[5] = m.nEy; o[6] = m.nEz;
+    return CS_OK;
+}
+
+extern "C" int cs_model_paint(cs_ctx* c, const double* par_h, double* sigma_d, double* mu_d) {
+    CS_CHECK(c && c->has_mesh, "mesh not set");
+    CS_CUDA(cudaSetDevice(c->device));
+    ctx_drop_ops(c);
+    CS_TRY(c->scal.ensure(4096));
+    CS_CUDA(cudaMemcpyAsync(c->scal.p, par_h, 18 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CS_TRY(launch_paint(c->m, c->zn_d, (const double*)c->scal.p, c->sigma, c->mu, c->st));
+    g_launches += 1;
+    if (sigma_d) CS_CUDA(cudaMemcpyAsync(sigma_d, c->sigma, c->m.nC * 8, cudaMemcpyDeviceToDevice, c->st));
+    if (mu_d) CS_CUDA(cudaMemcpyAsync(mu_d, c->mu, c->m.nC * 8, cudaMemcpyDeviceToDevice, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    c->has_model = true;
+    return CS_OK;
+}
+
+extern "C" int cs_model_set(cs_ctx* c, const double* sigma_d, const double* mu_d) {
+    CS_CHECK(c && c->has_mesh && sigma_d && mu_d, "mesh not set or null model");
+    CS_CUDA(cudaSetDevice(c->device));
+    ctx_drop_ops(c);
+    CS_CUDA(cudaMemcpyAsync(c->sigma, sigma_d, c->m.nC * 8, cudaMemcpyDeviceToDevice, c->st));
+    CS_CUDA(cudaMemcpyAsync(c->mu, mu_d, c->m.nC * 8, cudaMemcpyDeviceToDevice, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    c->has_model = true;
+    return CS_OK;
+}
+
+extern "C" int cs_face_inner_product(cs_ctx* c, const double* prop_d, int invProp, int invMat, double* out_d) {
+    CS_CHECK(c && c->has_mesh, "mesh not set");
+    CS_CUDA(cudaSetDevice(c->device));
+    g_launches += 1;
+    return launch_face_ip(c->m, prop_d, invProp, invMat, out_d, c->st);
+}
+extern "C" int cs_edge_inner_product(cs_ctx* c, const double* prop_d, int invProp, int invMat, double* out_d) {
+    CS_CHECK(c && c->has_mesh, "mesh not set");
+    CS_CUDA(cudaSetDevice(c->device));
+    g_launches += 1;
+    return launch_edge_ip(c->m, prop_d, invProp, invMat, out_d, c->st);
+}
+extern "C" int cs_curl(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_curl(c->m, x, y, ic != 0, c->st); }
+extern "C" int cs_curlT(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_curlT(c->m, x, y, ic != 0, c->st); }
+extern "C" int cs_div(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_div(c->m, x, y, ic != 0, c->st); }
+extern "C" int cs_divT(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_divT(c->m, x, y, ic != 0, c->st); }
+
+// ------------------------------------------------------- physics drivers ------
+static void info_begin(double* info) { if (info) memset(info, 0, CS_INFO_LEN * sizeof(double)); }
+
+extern "C" int cs_solve_dc(cs_ctx* c, const double* q_d, double* phi_d, int nrhs, double rtol, int maxit, double* info) {
+    CS_CHECK(c && c->has_model, "model not set");
+    long long l0 = g_launches;
+    info_begin(info);
+    cs_op* op = nullptr;
+    CS_TRY(cs_op_get(c, CS_KIND_DC, &op));
+    if (op->shifts.empty()) { double z[2] = {0, 0}; CS_TRY(cs_op_factor(op, z, 1, 0)); }
+    CS_CUDA(cudaEventRecord(c->ev0, c->st));
+    int rc = krylov_solve(op, q_d, phi_d, nrhs, nullptr, false, rtol, maxit, info);
+    cudaEventRecord(c->ev1, c->st); cudaStreamSynchronize(c->st);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    if (info) { info[CS_INFO_MS_SOLVE] = ms; info[CS_INFO_MS_FACTOR] = op->ms_factor; info[CS_INFO_MS_ASSEMBLE] = op->ms_assemble; info[CS_INFO_N_LAUNCH] = (double)(g_launches - l0); }
+    return rc;
+}
+
+extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfreq, const double* s_e_d,
+                             void* u_d, double rtol, int maxit, double* info) {
+    CS_CHECK(c && c->has_model, "model not set");
+    CS_CHECK(form == 'h' || form == 'j', "cs_solve_fdem supports the face-source formulations 'h' and 'j'");
+    CS_CHECK(nfreq >= 1, "no frequencies");
+    long long l0 = g_launches;
+    info_begin(info);
+    const MeshD& m = c->m;
+    cs_op* op = nullptr;
+    CS_TRY(cs_op_get(c, form == 'h' ? CS_KIND_EDGE_H : CS_KIND_FACE_J, &op));
+    long long n = op->n;
+    // how many frequencies fit at once
+    size_t per = (size_t)op->bp.nmodes * op->bp.band_elems() * sizeof(cplx);
+    size_t fr = 0, tot = 0;
+    CS_CUDA(cudaMemGetInfo(&fr, &tot));
+    fr += op->LU.bytes;
+    size_t vecs = (size_t)(8 + 2) * n * sizeof(cplx) + (size_t)op->bp.nmodes * op->bp.n2 * sizeof(cplx);
+    long long chunk = (long long)((0.8 * (double)fr) / (double)(per + vecs));
+    CS_CHECK(chunk >= 1, "not enough device memory for one frequency");
+    if (chunk > nfreq) chunk = nfreq;
+    if (chunk > 256) chunk = 256;
+    DevBuf rhs;
+    CS_TRY(rhs.ensure((size_t)chunk * n * sizeof(cplx)));
+    double ms_fac = 0, ms_sol = 0, worst = 0, iters = 0;
+    int rc = CS_OK;
+    for (long long f0 = 0; f0 < nfreq && rc == CS_OK; f0 += chunk) {
+        int nf = (int)std::min<long long>(chunk, nfreq - f0);
+        std::vector<double> sh(2 * nf), w(nf);
+        std::vector<int> sov(nf);
+        for (int f = 0; f < nf; ++f) { w[f] = 2 * M_PI * freqs_h[f0 + f]; sh[2 * f] = 0; sh[2 * f + 1] = w[f]; sov[f] = f; }
+        // right-hand sides
+        if (form == 'h') {
+            // rhs = C^T (MfRho .* s_e), identical for every frequency
+            CS_TRY(c->tmp1.ensure((size_t)m.nF * 8)); CS_TRY(c->tmp2.ensure((size_t)m.nE * 8));
+            cs_op* dummy = nullptr; (void)dummy;
+            double* a = (double*)c->tmp1.p;
+            CS_TRY(launch_face_scale(m, op->w1, a, 3, c->st));          // alpha/area
+            CS_TRY(launch_face_scale(m, a, a, 3, c->st));               // alpha
+            CS_TRY(launch_mul_real(a, s_e_d, a, m.nF, 1, false, 0, c->st));
+            CS_TRY(launch_curlT(m, a, c->tmp2.p, false, c->st));
+            for (int f = 0; f < nf; ++f) CS_TRY(launch_real_to_cplx((const double*)c->tmp2.p, (cplx*)rhs.p + (size_t)f * n, n, c->st));
+            g_launches += 4 + nf;
+        } else {
+            CS_TRY(c->scal.ensure(std::max<size_t>(4096, nf * 8)));
+            CS_CUDA(cudaMemcpyAsync(c->scal.p, w.data(), nf * 8, cudaMemcpyHostToDevice, c->st));
+            dim3 g((unsigned)cdiv(n, 256), nf);
+            k_rhs_fdem_j<<<g, 256, 0, c->st>>>(op->mass, s_e_d, n, (const double*)c->scal.p, (cplx*)rhs.p);
+            CS_CUDA(cudaGetLastError());
+            CS_CUDA(cudaStreamSynchronize(c->st));
+            g_launches += 1;
+        }
+        rc = cs_op_factor(op, sh.data(), nf, 1);
+        if (rc) break;
+        ms_fac += op->ms_factor;
+        CS_CUDA(cudaEventRecord(c->ev0, c->st));
+        double inf2[CS_INFO_LEN]; memset(inf2, 0, sizeof inf2);
+        rc = krylov_solve(op, rhs.p, (cplx*)u_d + (size_t)f0 * n, nf, sov.data(), true, rtol, maxit, inf2);
+        cudaEventRecord(c->ev1, c->st); cudaStreamSynchronize(c->st);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        ms_sol += ms;
+        worst = std::max(worst, inf2[CS_INFO_RELRES]); iters = std::max(iters, inf2[CS_INFO_ITERS]);
+        if (info) { info[CS_INFO_N_APPLY] += inf2[CS_INFO_N_APPLY]; info[CS_INFO_BYTES] += inf2[CS_INFO_BYTES]; }
+    }
+    rhs.release();
+    if (info) {
+        info[CS_INFO_ITERS] = iters; info[CS_INFO_RELRES] = worst; info[CS_INFO_MS_FACTOR] = ms_fac; info[CS_INFO_MS_SOLVE] = ms_sol;
+        info[CS_INFO_MS_ASSEMBLE] = op->ms_assemble; info[CS_INFO_N_LAUNCH] = (double)(g_launches - l0); info[CS_INFO_CONVERGED] = rc == CS_OK;
+    }
+    return rc;
+}
+
+extern "C" int cs_tdem_run(cs_ctx* c, int form, const double* dts_h, int nsteps, const double* s_e_d,
+                           double* out_d, double rtol, int maxit, double* info) {
+    CS_CHECK(c && c->has_model, "model not set");
+    CS_CHECK(form == 'j', "cs_tdem_run implements the (default) j formulation");
+    long long l0 = g_launches;
+    info_begin(info);
+    const MeshD& m = c->m;
+    long long nF = m.nF, nC = m.nC;
+    cs_op *dc = nullptr, *op = nullptr;
+    CS_TRY(cs_op_get(c, CS_KIND_DC_GROUNDED, &dc));
+    CS_TRY(cs_op_get(c, CS_KIND_FACE_J, &op));
+    double inf2[CS_INFO_LEN];
+    DevBuf b1, b2, b3;
+    CS_TRY(b1.ensure((size_t)nC * 8)); CS_TRY(b2.ensure((size_t)nC * 8)); CS_TRY(b3.ensure((size_t)nF * 8));
+    double ms_fac = 0, ms_sol = 0, worst = 0;
+    // initial DC state: phi = Adc^-1 (Dt s_e); j0 = -MfRhoI Dt^T phi     (A.7)
+    { double z[2] = {0, 0}; CS_TRY(cs_op_factor(dc, z, 1, 0)); ms_fac += dc->ms_factor; }
+    CS_TRY(launch_div(m, s_e_d, b1.p, false, c->st));
+    memset(inf2, 0, sizeof inf2);
+    int rc = krylov_solve(dc, b1.p, b2.p, 1, nullptr, false, rtol, maxit, inf2);
+    if (rc) { b1.release(); b2.release(); b3.release(); return rc; }
+    worst = std::max(worst, inf2[CS_INFO_RELRES]);
+    CS_TRY(launch_divT(m, b2.p, b3.p, false, c->st));
+    CS_TRY(launch_mul_real(b3.p, b3.p, op->mass, nF, 1, false, 1, c->st));      // / MfRho
+    k_scale_add<<<cdiv(nF, 256), 256, 0, c->st>>>(out_d, (const double*)b3.p, nF, -1.0, 0.0);
+    CS_CUDA(cudaGetLastError());
+    g_launches += 4;
+    cs_op_clean(dc);
+    double dt_prev = -1.0;
+    CS_CUDA(cudaEventRecord(c->ev0, c->st));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int t = 0; t < nsteps && rc == CS_OK; ++t) {
+        double dt = dts_h[t];
+        if (dt_prev < 0 || std::fabs(dt - dt_prev) > 1e-8) {      // SimPEG dt_threshold: refactor only when dt changes
+            double sh[2] = {1.0 / dt, 0.0};
+            rc = cs_op_factor(op, sh, 1, 0);
+            if (rc) break;
+            ms_fac += op->ms_factor;
+            dt_prev = dt;
+        }
+        // rhs = MfRho .* (j^n + [t == 0] s_e) / dt
+        const double* jn = out_d + (size_t)t * nF;
+        double* rhs = (double*)b3.p;
+        cudaEventRecord(e0, c->st);
+        k_scale_add<<<cdiv(nF, 256), 256, 0, c->st>>>(rhs, jn, nF, 1.0 / dt_prev, 0.0);
+        if (t == 0) k_scale_add<<<cdiv(nF, 256), 256, 0, c->st>>>(rhs, s_e_d, nF, 1.0 / dt_prev, 1.0);
+        CS_TRY(launch_mul_real(rhs, rhs, op->mass, nF, 1, false, 0, c->st));
+        g_launches += 3;
+        memset(inf2, 0, sizeof inf2);
+        rc = krylov_solve(op, rhs, out_d + (size_t)(t + 1) * nF, 1, nullptr, false, rtol, maxit, inf2);
+        cudaEventRecord(e1, c->st); cudaStreamSynchronize(c->st);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms_sol += ms;
+        worst = std::max(worst, inf2[CS_INFO_RELRES]);
+        if (info) { info[CS_INFO_N_APPLY] += inf2[CS_INFO_N_APPLY]; info[CS_INFO_BYTES] += inf2[CS_INFO_BYTES]; info[CS_INFO_ITERS] += inf2[CS_INFO_ITERS]; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    b1.release(); b2.release(); b3.release();
+    if (info) {
+        info[CS_INFO_RELRES] = worst; info[CS_INFO_MS_FACTOR] = ms_fac; info[CS_INFO_MS_SOLVE] = ms_sol;
+        info[CS_INFO_MS_ASSEMBLE] = op->ms_assemble + dc->ms_assemble; info[CS_INFO_N_LAUNCH] = (double)(g_launches - l0); info[CS_INFO_CONVERGED] = rc == CS_OK;
+    }
+    return rc;
+}
+
+// derived fields (SURVEY A.5 / A.6 last columns) --------------------------------
+__global__ void k_cscale(cplx* __restrict__ y, long long n, double re, double im) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) y[t] = mk(re, im) * y[t];
+}
+// out = (Mnum ./ Mden) .* out, both diagonal inner products of the given kind
+static int ratio_scale(cs_ctx* c, bool face, const double* prop_num, int inv_num, void* out, bool cplx_vec) {
+    const MeshD& m = c->m;
+    long long n = face ? m.nF : m.nE;
+    CS_TRY(c->tmp1.ensure((size_t)n * 8));
+    double* t1 = (double*)c->tmp1.p;
+    if (face) CS_TRY(launch_face_ip(m, prop_num, inv_num, 0, t1, c->st)); else CS_TRY(launch_edge_ip(m, prop_num, inv_num, 0, t1, c->st));
+    CS_TRY(launch_mul_real(out, out, t1, n, 1, cplx_vec, 0, c->st));
+    if (face) CS_TRY(launch_face_ip(m, nullptr, 0, 0, t1, c->st)); else CS_TRY(launch_edge_ip(m, nullptr, 0, 0, t1, c->st));
+    CS_TRY(launch_mul_real(out, out, t1, n, 1, cplx_vec, 1, c->st));
+    g_launches += 4;
+    return CS_OK;
+}
+
+extern "C" int cs_fields_fdem(cs_ctx* c, int form, int which, double freq, const void* u_d, const double* s_e_d, void* out_d) {
+    CS_CHECK(c && c->has_model, "model not set");
+    CS_CHECK(form == 'h' || form == 'j', "fields implemented for the formulations h and j");
+    CS_CUDA(cudaSetDevice(c->device));
+    const MeshD& m = c->m;
+    double w = 2 * M_PI * freq;
+    cplx* out = (cplx*)out_d;
+    if (form == 'h') {
+        if (which == 'h' || which == 'b') {
+            CS_CUDA(cudaMemcpyAsync(out, u_d, m.nE * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
+            if (which == 'b') CS_TRY(ratio_scale(c, false, c->mu, 0, out, true));      // Me^-1 MeMu h
+            return CS_OK;
+        }
+        CS_CHECK(which == 'j' || which == 'e', "which must be one of j, e, h, b");
+        CS_TRY(launch_curl(m, u_d, out, true, c->st));                                 // j = C h - s_e
+        k_sub_real_from_cplx<<<cdiv(m.nF, 256), 256, 0, c->st>>>(out, s_e_d, m.nF);
+        CS_CUDA(cudaGetLastError());
+        g_launches += 2;
+        if (which == 'e') CS_TRY(ratio_scale(c, true, c->sigma, 1, out, true));        // Mf^-1 MfRho j
+        return CS_OK;
+    }
+    // form j
+    if (which == 'j' || which == 'e') {
+        CS_CUDA(cudaMemcpyAsync(out, u_d, m.nF * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
+        if (which == 'e') CS_TRY(ratio_scale(c, true, c->sigma, 1, out, true));
+        return CS_OK;
+    }
+    CS_CHECK(which == 'h' || which == 'b', "which must be one of j, e, h, b");
+    // h = MeMuI (s_m - C^T MfRho j) / (i w), s_m = 0 ; b = Me^-1 MeMu h
+    CS_TRY(c->tmp2.ensure((size_t)m.nF * sizeof(cplx)));
+    CS_TRY(c->tmp1.ensure((size_t)std::max(m.nF, m.nE) * 8));
+    CS_TRY(launch_face_ip(m, c->sigma, 1, 0, (double*)c->tmp1.p, c->st));
+    CS_TRY(launch_mul_real(c->tmp2.p, u_d, (double*)c->tmp1.p, m.nF, 1, true, 0, c->st));
+    CS_TRY(launch_curlT(m, c->tmp2.p, out, true, c->st));
+    const double* none = nullptr;
+    CS_TRY(launch_edge_ip(m, which == 'h' ? c->mu : none, 0, 1, (double*)c->tmp1.p, c->st));   // MeMuI or Me^-1
+    CS_TRY(launch_mul_real(out, out, (double*)c->tmp1.p, m.nE, 1, true, 0, c->st));
+    // multiply by -1/(i w) = i / w
+    k_cscale<<<cdiv(m.nE, 256), 256, 0, c->st>>>(out, m.nE, 0.0, 1.0 / w);
+    CS_CUDA(cudaGetLastError());
+    g_launches += 6;
+    return CS_OK;
+}
+
+#define EPS_0 8.8541878128e-12
+extern "C" int cs_fields_dc(cs_ctx* c, int which, const double* phi_d, double* out_d, int nrhs) {
+    CS_CHECK(c && c->has_model, "model not set");
+    CS_CHECK(which == 'j' || which == 'e' || which == 'c', "which must be j, e or c (charge)");
+    CS_CUDA(cudaSetDevice(c->device));
+    const MeshD& m = c->m;
+    CS_TRY(c->tmp2.ensure((size_t)m.nF * 8));
+    CS_TRY(c->tmp1.ensure((size_t)m.nF * 8));
+    for (int s = 0; s < nrhs; ++s) {
+        const double* phi = phi_d + (size_t)s * m.nC;
+        double* dst = (which == 'c') ? (double*)c->tmp2.p : out_d + (size_t)s * m.nF;
+        CS_TRY(launch_divT(m, phi, dst, false, c->st));
+        // j = MfRhoI Dt^T phi ; e = Mf^-1 MfRho j = Mf^-1 Dt^T phi
+        const double* none = nullptr;
+        CS_TRY(launch_face_ip(m, which == 'j' ? c->sigma : none, which == 'j' ? 1 : 0, 1, (double*)c->tmp1.p, c->st));
+        CS_TRY(launch_mul_real(dst, dst, (double*)c->tmp1.p, m.nF, 1, false, 0, c->st));
+        g_launches += 3;
+        if (which == 'c') {   // charge = eps0 * vol .* (faceDiv e) = eps0 * Dt e
+            double* o = out_d + (size_t)s * m.nC;
+            CS_TRY(launch_div(m, dst, o, false, c->st));
+            k_scale_add<<<cdiv(m.nC, 256), 256, 0, c->st>>>(o, o, m.nC, EPS_0, 0.0);
+            CS_CUDA(cudaGetLastError());
+            g_launches += 2;
+        }
+    }
+    return CS_OK;
+}
+
+extern "C" int cs_casing_currents(cs_ctx* c, const void* j_d, int is_complex, double a, double b, double z0, double z1, void* ix_d, void* iz_d) {
+    CS_CHECK(c && c->has_mesh, "mesh not set");
+    CS_CUDA(cudaSetDevice(c->device));
+    const MeshD& m = c->m;
+    if (is_complex) k_casing_currents<cplx><<<m.nz + 1, 256, 0, c->st>>>(m, c->zn_d, (const cplx*)j_d, a, b, z0, z1, (cplx*)ix_d, (cplx*)iz_d);
+    else k_casing_currents<double><<<m.nz + 1, 256, 0, c->st>>>(m, c->zn_d, (const double*)j_d, a, b, z0, z1, (double*)ix_d, (double*)iz_d);
+    CS_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return CS_OK;
+}
+extern "C" int cs_casing_charges(cs_ctx* c, const double* ch, double casing_b, double z0, double z1, double* out_d) {
+    CS_CHECK(c && c->has_mesh, "mesh not set");
+    CS_CUDA(cudaSetDevice(c->device));
+    const MeshD& m = c->m;
+    double hxmin = c->hx[0];
+    for (double v : c->hx) hxmin = std::min(hxmin, v);
+    k_casing_charges<<<m.nz, 256, 0, c->st>>>(m, c->zn_d, ch, casing_b + hxmin, z0, z1, out_d);
+    CS_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return CS_OK;
+}

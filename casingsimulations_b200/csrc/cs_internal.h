@@ -1,0 +1,75 @@
+// Internal host-side interfaces between the translation units of libcasing_b200.
+#pragma once
+#include "cs_common.cuh"
+#include <vector>
+
+namespace cs {
+
+// -------- cs_kernels.cu : assembly + stencil applies ---------------------------
+// K1: paint sigma / mu from CasingInHalfspace-style parameters (model.py:190-260, 507-580)
+int launch_paint(const MeshD& m, const double* zn_d, const double* par_d, double* sigma, double* mu, cudaStream_t st);
+// K2: diagonal inner products (discretize getFaceInnerProduct / getEdgeInnerProduct)
+int launch_face_ip(const MeshD& m, const double* prop, int invProp, int invMat, double* out, cudaStream_t st);
+int launch_edge_ip(const MeshD& m, const double* prop, int invProp, int invMat, double* out, cudaStream_t st);
+// elementwise geometric rescalings: mode 0: area^2/in, 1: in/area^2, 2: in/area, 3: in*area
+int launch_face_scale(const MeshD& m, const double* in, double* out, int mode, cudaStream_t st);
+// mode 0: len^2*in, 1: len^2/in
+int launch_edge_scale(const MeshD& m, const double* in, double* out, int mode, cudaStream_t st);
+
+// K3: y = Dt diag(g) Dt^T x (+ shift0 * x[0] on row 0), Dt = vol*faceDiv; nsys vectors of length nC
+int launch_dc_apply(const MeshD& m, const double* g, double shift0, const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
+// Dt x_F -> cells ; Dt^T x_C -> faces
+int launch_div(const MeshD& m, const void* xF, void* yC, bool cplx_vec, cudaStream_t st);
+int launch_divT(const MeshD& m, const void* xC, void* yF, bool cplx_vec, cudaStream_t st);
+// y_F = edgeCurl x_E ; y_E = edgeCurl^T x_F
+int launch_curl(const MeshD& m, const void* xE, void* yF, bool cplx_vec, cudaStream_t st);
+int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaStream_t st);
+// K4 edge form: y = C^T diag(alpha) C x + s[sys] * beta .* x, wF = alpha/area^2
+int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const double* s_d /*2 doubles per sys*/,
+                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
+// K4 face form: y = alpha .* (C diag(gamma) C^T (alpha .* x) + s[sys] x), uF = alpha/area, gE = len^2 gamma
+int launch_face_op(const MeshD& m, const double* uF, const double* gE, const double* s_d,
+                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
+
+// -------- cs_vec.cu : BLAS-1 style kernels ------------------------------------------
+// out[sys] = sum conj?(a) * b over n entries; results to dots_d[2*sys..]
+// optional weights w[wsel[sys]*n + t] (real, >= 0) give the diagonally scaled norms used by the convergence tests
+int launch_dot(const void* a, const void* b, long long n, int nsys, bool cplx_vec, bool conj_a, double* dots_d, cudaStream_t st,
+               const double* w = nullptr, const int* wsel = nullptr);
+// y = a*x + b*y with per-system complex scalars (host arrays of 2 doubles per system)
+int launch_axpby(void* y, const void* x, long long n, int nsys, bool cplx_vec, const double* a_d, const double* b_d, cudaStream_t st);
+// z = x .* w (w real, shared by all systems), optionally reciprocal
+int launch_mul_real(void* z, const void* x, const double* w, long long n, int nsys, bool cplx_vec, int recip, cudaStream_t st);
+int launch_real_to_cplx(const double* x, cplx* z, long long n, cudaStream_t st);
+
+// -------- cs_band.cu : theta-DFT + banded direct solves (preconditioner) -----------
+struct BandPlan {
+    // per-mode 2-D unknown ordering ("band ordering")
+    long long n2 = 0;          // unknowns per mode system (incl. dummies)
+    int p = 0;                 // half bandwidth of the true couplings
+    int nb = 16;               // block size of the blocked LU
+    int pw = 0;                // stored half bandwidth = p + nb
+    int ldab = 0;              // 2*pw + 1
+    int nmodes = 1;            // nth
+    bool cplx_band = false;    // storage scalar type of K band / LU
+    long long* map3d = nullptr;  // [n2] index into the 3-D vector at j = 0, -1 = dummy
+    int* jstr = nullptr;         // [n2] stride per theta step (0 = axis unknown)
+    double* mdiag = nullptr;     // [n2] diagonal "mass" part multiplied by the shift s
+    void* Kband = nullptr;       // [nmodes][n2*ldab] band of the s-independent part
+    size_t band_elems() const { return (size_t)n2 * ldab; }
+};
+
+int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm /*[nvec][nmodes][n2]*/, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
+int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
+int band_probe_fill(const BandPlan& bp, int color, void* x3d, long long n3d, bool x_cplx, cudaStream_t st);
+int band_probe_store(const BandPlan& bp, int color, const void* ym /*[nmodes][n2]*/, cudaStream_t st);
+// w[f][3-D index] = 1 / |diag(A(s_f))| recovered from the mode matrices (mean over modes of K_m[q,q]) + s_f * mass
+int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long long n3d, double* w, cudaStream_t st);
+// LU[f][mode] = Kband[mode] + s[f] * diag(mdiag)   (f = 0..nshift-1)
+int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shift*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
+// in-place blocked LU without pivoting of nsys_tot = nshift*nmodes band matrices
+int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st);
+// solve: rhs/solution xm [nvec][nmodes][n2]; vector v uses factor shift_of_vec[v]
+int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st);
+
+}  // namespace cs

@@ -1,0 +1,448 @@
+// K1-K4, K8: model painting, inner-product assembly, and matrix-free stencil
+// applies on the (r, theta, z) mesh.  All arithmetic fp64 / complex128; every
+// kernel is HBM-bound (DESIGN.md gives bytes per cell) and uses one thread per
+// (i, j, k) slot with i fastest => fully coalesced streams of the big arrays,
+// neighbour values come from L1/L2 (a z-plane is nx*nth*16 B <= 223 KB).
+#include "cs_internal.h"
+#include "cs_stencil.cuh"
+
+namespace cs {
+
+static const int TPB = 256;
+static inline dim3 grid1(long long n, int nsys = 1) { return dim3((unsigned)cdiv(n, TPB), (unsigned)nsys, 1); }
+#define MU_0 1.25663706143591729539e-06
+
+// ============================ K1: paint ========================================
+// params (doubles): 0 sigma_back 1 has_air 2 sigma_air 3 surface_z 4 has_casing
+// 5 sigma_casing 6 sigma_inside 7 casing_a 8 casing_b 9 casing_z0 10 casing_z1
+// 11 mur_back 12 mur_casing 13 mur_inside 14 has_layer 15 sigma_layer
+// 16 layer_z0 17 layer_z1.  Predicates are the strict inequalities of
+// model.py:249 (air), :290-293 (layer), :514-529, :538 (casing / inside);
+// paint order background -> air -> layer -> casing -> inside (model.py:258-260,
+// 301-303, 566-567).
+__global__ void k_paint(MeshD m, const double* __restrict__ zn, const double* __restrict__ par,
+                        double* __restrict__ sigma, double* __restrict__ mu) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz, s)) return;
+    double rc = 0.5 * (m.rn[s.i + 1] + m.rn[s.i]);
+    double zc = 0.5 * (zn[s.k + 1] + zn[s.k]);
+    double sg = par[0], mr = par[11];
+    if (par[1] != 0.0 && zc > par[3]) sg = par[2];
+    if (par[14] != 0.0 && zc < par[17] && zc > par[16]) sg = par[15];
+    if (par[4] != 0.0) {
+        bool inz = (zc > par[9]) && (zc < par[10]);
+        if (inz && rc > par[7] && rc < par[8]) { sg = par[5]; mr = par[12]; }
+        if (inz && rc < par[7]) { sg = par[6]; mr = par[13]; }
+    }
+    sigma[t] = sg;
+    mu[t] = MU_0 * mr;
+}
+
+int launch_paint(const MeshD& m, const double* zn_d, const double* par_d, double* sigma, double* mu, cudaStream_t st) {
+    k_paint<<<grid1(m.nC), TPB, 0, st>>>(m, zn_d, par_d, sigma, mu);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// ============================ K2: inner products ================================
+// Mf(p)_f = sum over the (<=2) cells touching f of w * vol_c p_c, w = 1/2 except
+// the innermost cell's share of the face at r_1 (w_axis_face); Me(p)_e likewise
+// with 4 cells and w = 1/4 (radial factor of the Ey edge at r_1: w_axis_edge);
+// the shared axis Ez edge collects 1/2 vol p from every innermost cell.
+__device__ __forceinline__ double vp(const MeshD& m, const double* __restrict__ p, int inv, int i, int j, int k) {
+    double v = p ? p[m.cidx(i, j, k)] : 1.0;     // p == nullptr: unit property (Mf, Me)
+    return m.vol(i, j, k) * (inv ? 1.0 / v : v);
+}
+
+__global__ void k_face_ip(MeshD m, const double* __restrict__ p, int invProp, int invMat, double* __restrict__ out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    if (k < m.nz) {
+        double a = (i == 0 ? m.w_axis_face : 0.5) * vp(m, p, invProp, i, j, k);
+        if (i + 1 < m.nx) a += 0.5 * vp(m, p, invProp, i + 1, j, k);
+        out[m.cidx(i, j, k)] = invMat ? 1.0 / a : a;
+        if (!m.sym) {
+            double b = 0.5 * (vp(m, p, invProp, i, m.jm(j), k) + vp(m, p, invProp, i, j, k));
+            out[m.nFx + m.cidx(i, j, k)] = invMat ? 1.0 / b : b;
+        }
+    }
+    double c = 0.0;
+    if (k > 0) c += 0.5 * vp(m, p, invProp, i, j, k - 1);
+    if (k < m.nz) c += 0.5 * vp(m, p, invProp, i, j, k);
+    out[m.nFx + m.nFy + m.cidx(i, j, k)] = invMat ? 1.0 / c : c;
+}
+
+__global__ void k_edge_ip(MeshD m, const double* __restrict__ p, int invProp, int invMat, double* __restrict__ out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    double wr = (i == 0) ? m.w_axis_edge : 0.5;
+    // Ey (r_{i+1}, cell j, node k): cells (i | i+1, j, k-1 | k)
+    double ey = 0.0;
+    for (int kk = k - 1; kk <= k; ++kk) {
+        if (kk < 0 || kk >= m.nz) continue;
+        ey += 0.5 * wr * vp(m, p, invProp, i, j, kk);
+        if (i + 1 < m.nx) ey += 0.25 * vp(m, p, invProp, i + 1, j, kk);
+    }
+    out[m.nEx + m.cidx(i, j, k)] = invMat ? 1.0 / ey : ey;
+    if (m.sym) return;
+    // Ex (cell i, node j, node k): cells (i, j-1 | j, k-1 | k)
+    double ex = 0.0;
+    for (int kk = k - 1; kk <= k; ++kk) {
+        if (kk < 0 || kk >= m.nz) continue;
+        ex += 0.25 * (vp(m, p, invProp, i, m.jm(j), kk) + vp(m, p, invProp, i, j, kk));
+    }
+    out[m.cidx(i, j, k)] = invMat ? 1.0 / ex : ex;
+    if (k < m.nz) {
+        // Ez (r_{i+1}, node j, cell k): cells (i | i+1, j-1 | j, k)
+        double ez = 0.25 * (vp(m, p, invProp, i, m.jm(j), k) + vp(m, p, invProp, i, j, k));
+        if (i + 1 < m.nx) ez += 0.25 * (vp(m, p, invProp, i + 1, m.jm(j), k) + vp(m, p, invProp, i + 1, j, k));
+        out[m.nEx + m.nEy + m.ez(i, j, k)] = invMat ? 1.0 / ez : ez;
+        if (i == 0 && j == 0) {
+            double ax = 0.0;
+            for (int jj = 0; jj < m.nth; ++jj) ax += 0.5 * vp(m, p, invProp, 0, jj, k);
+            out[m.nEx + m.nEy + m.ezaxis(k)] = invMat ? 1.0 / ax : ax;
+        }
+    }
+}
+
+int launch_face_ip(const MeshD& m, const double* prop, int invProp, int invMat, double* out, cudaStream_t st) {
+    k_face_ip<<<grid1(m.nxy * (m.nz + 1)), TPB, 0, st>>>(m, prop, invProp, invMat, out);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+int launch_edge_ip(const MeshD& m, const double* prop, int invProp, int invMat, double* out, cudaStream_t st) {
+    k_edge_ip<<<grid1(m.nxy * (m.nz + 1)), TPB, 0, st>>>(m, prop, invProp, invMat, out);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+__global__ void k_face_scale(MeshD m, const double* __restrict__ in, double* __restrict__ out, int mode) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    auto f = [&](double v, double a) -> double {
+        switch (mode) {
+            case 0: return a * a / v;
+            case 1: return v / (a * a);
+            case 2: return v / a;
+            default: return v * a;
+        }
+    };
+    if (k < m.nz) {
+        long long c = m.cidx(i, j, k);
+        out[c] = f(in[c], m.aFx(i, j, k));
+        if (!m.sym) out[m.nFx + c] = f(in[m.nFx + c], m.aFy(i, k));
+    }
+    long long c = m.nFx + m.nFy + m.cidx(i, j, k);
+    out[c] = f(in[c], m.aFz(i, j));
+}
+__global__ void k_edge_scale(MeshD m, const double* __restrict__ in, double* __restrict__ out, int mode) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    auto f = [&](double v, double l) -> double { return mode == 0 ? l * l * v : l * l / v; };
+    long long c = m.cidx(i, j, k);
+    out[m.nEx + c] = f(in[m.nEx + c], m.lEy(i, j));
+    if (m.sym) return;
+    out[c] = f(in[c], m.lEx(i));
+    if (k < m.nz) {
+        long long e = m.nEx + m.nEy + m.ez(i, j, k);
+        out[e] = f(in[e], m.lEz(k));
+        if (i == 0 && j == 0) {
+            long long a = m.nEx + m.nEy + m.ezaxis(k);
+            out[a] = f(in[a], m.lEz(k));
+        }
+    }
+}
+int launch_face_scale(const MeshD& m, const double* in, double* out, int mode, cudaStream_t st) {
+    k_face_scale<<<grid1(m.nxy * (m.nz + 1)), TPB, 0, st>>>(m, in, out, mode);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+int launch_edge_scale(const MeshD& m, const double* in, double* out, int mode, cudaStream_t st) {
+    k_edge_scale<<<grid1(m.nxy * (m.nz + 1)), TPB, 0, st>>>(m, in, out, mode);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// ============================ K3: DC apply =======================================
+// y_c = sum_f g_f (x_c - x_nbr(f)); faces on the outer r / bottom / top boundary
+// have no neighbour (Dirichlet phi = 0 outside; SimPEG Problem3D_CC, run.py:339-344)
+// g = area^2 / MfRho laid out like a face vector.  40 B/cell (3-D), 32 B/cell (2-D).
+template <typename T>
+__global__ void k_dc_apply(MeshD m, const double* __restrict__ g, double shift0,
+                           const T* __restrict__ x, T* __restrict__ y) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz, s)) return;
+    x += blockIdx.y * m.nC;
+    y += blockIdx.y * m.nC;
+    int i = s.i, j = s.j, k = s.k;
+    const double* gx = g;
+    const double* gy = g + m.nFx;
+    const double* gz = g + m.nFx + m.nFy;
+    T xc = x[t];
+    T acc = gx[t] * ((i + 1 < m.nx) ? (xc - x[t + 1]) : xc);
+    if (i > 0) acc += gx[t - 1] * (xc - x[t - 1]);
+    if (!m.sym) {
+        long long cm = m.cidx(i, m.jm(j), k), cp = m.cidx(i, m.jp(j), k);
+        acc += gy[t] * (xc - x[cm]) + gy[cp] * (xc - x[cp]);
+    }
+    acc += gz[t] * ((k > 0) ? (xc - x[t - m.nxy]) : xc);
+    acc += gz[t + m.nxy] * ((k + 1 < m.nz) ? (xc - x[t + m.nxy]) : xc);
+    if (t == 0) acc += shift0 * xc;
+    y[t] = acc;
+}
+
+int launch_dc_apply(const MeshD& m, const double* g, double shift0, const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st) {
+    if (cplx_vec) k_dc_apply<cplx><<<grid1(m.nC, nsys), TPB, 0, st>>>(m, g, shift0, (const cplx*)x, (cplx*)y);
+    else k_dc_apply<double><<<grid1(m.nC, nsys), TPB, 0, st>>>(m, g, shift0, (const double*)x, (double*)y);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// Dt = vol*faceDiv = D_topo diag(area): faces -> cells, and its transpose
+template <typename T>
+__global__ void k_div(MeshD m, const T* __restrict__ xF, T* __restrict__ yC) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    FaceV<T> f(m, xF);
+    T acc = m.aFx(i, j, k) * f.x[t];
+    if (i > 0) acc -= m.aFx(i - 1, j, k) * f.x[t - 1];
+    if (!m.sym) acc += m.aFy(i, k) * (f.y[m.cidx(i, m.jp(j), k)] - f.y[t]);
+    acc += m.aFz(i, j) * (f.z[t + m.nxy] - f.z[t]);
+    yC[t] = acc;
+}
+template <typename T>
+__global__ void k_divT(MeshD m, const T* __restrict__ xC, T* __restrict__ yF) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    long long c = m.cidx(i, j, k);
+    if (k < m.nz) {
+        T xc = xC[c];
+        yF[c] = m.aFx(i, j, k) * ((i + 1 < m.nx) ? (xc - xC[c + 1]) : xc);
+        if (!m.sym) yF[m.nFx + c] = m.aFy(i, k) * (xC[m.cidx(i, m.jm(j), k)] - xc);
+    }
+    T lo = (k > 0) ? xC[c - m.nxy] : Sc<T>::zero();
+    T hi = (k < m.nz) ? xC[c] : Sc<T>::zero();
+    yF[m.nFx + m.nFy + c] = m.aFz(i, j) * (lo - hi);
+}
+int launch_div(const MeshD& m, const void* xF, void* yC, bool cplx_vec, cudaStream_t st) {
+    if (cplx_vec) k_div<cplx><<<grid1(m.nC), TPB, 0, st>>>(m, (const cplx*)xF, (cplx*)yC);
+    else k_div<double><<<grid1(m.nC), TPB, 0, st>>>(m, (const double*)xF, (double*)yC);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+int launch_divT(const MeshD& m, const void* xC, void* yF, bool cplx_vec, cudaStream_t st) {
+    long long n = m.nxy * (m.nz + 1);
+    if (cplx_vec) k_divT<cplx><<<grid1(n), TPB, 0, st>>>(m, (const cplx*)xC, (cplx*)yF);
+    else k_divT<double><<<grid1(n), TPB, 0, st>>>(m, (const double*)xC, (double*)yF);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// ============================ curl / curl^T ======================================
+template <typename T>
+__global__ void k_curl(MeshD m, const T* __restrict__ xE, T* __restrict__ yF) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    EdgeV<T> e(m, xE);
+    long long c = m.cidx(i, j, k);
+    if (k < m.nz) {
+        yF[c] = (1.0 / m.aFx(i, j, k)) * circFx(m, e, i, j, k);
+        if (!m.sym) yF[m.nFx + c] = (1.0 / m.aFy(i, k)) * circFy(m, e, i, j, k);
+    }
+    yF[m.nFx + m.nFy + c] = (1.0 / m.aFz(i, j)) * circFz(m, e, i, j, k);
+}
+
+template <typename T> struct PlainFace {
+    const MeshD& m; FaceV<T> f;
+    __device__ PlainFace(const MeshD& m_, const T* v) : m(m_), f(m_, v) {}
+    // value / area of face (kind, i, j, k)
+    __device__ __forceinline__ T operator()(int kind, int i, int j, int k) const {
+        long long c = m.cidx(i, j, k);
+        if (kind == 0) return (1.0 / m.aFx(i, j, k)) * f.x[c];
+        if (kind == 1) return (1.0 / m.aFy(i, k)) * f.y[c];
+        return (1.0 / m.aFz(i, j)) * f.z[c];
+    }
+};
+
+template <typename T>
+__global__ void k_curlT(MeshD m, const T* __restrict__ xF, T* __restrict__ yE) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    int i = s.i, j = s.j, k = s.k;
+    PlainFace<T> f(m, xF);
+    long long c = m.cidx(i, j, k);
+    yE[m.nEx + c] = m.lEy(i, j) * gathEy<T>(m, f, i, j, k);
+    if (m.sym) return;
+    yE[c] = m.lEx(i) * gathEx<T>(m, f, i, j, k);
+    if (k < m.nz) {
+        yE[m.nEx + m.nEy + m.ez(i, j, k)] = m.lEz(k) * gathEz<T>(m, f, i, j, k);
+        if (i == 0 && j == 0) yE[m.nEx + m.nEy + m.ezaxis(k)] = m.lEz(k) * gathEzAxis<T>(m, f, k);
+    }
+}
+int launch_curl(const MeshD& m, const void* xE, void* yF, bool cplx_vec, cudaStream_t st) {
+    long long n = m.nxy * (m.nz + 1);
+    if (cplx_vec) k_curl<cplx><<<grid1(n), TPB, 0, st>>>(m, (const cplx*)xE, (cplx*)yF);
+    else k_curl<double><<<grid1(n), TPB, 0, st>>>(m, (const double*)xE, (double*)yF);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaStream_t st) {
+    long long n = m.nxy * (m.nz + 1);
+    if (cplx_vec) k_curlT<cplx><<<grid1(n), TPB, 0, st>>>(m, (const cplx*)xF, (cplx*)yE);
+    else k_curlT<double><<<grid1(n), TPB, 0, st>>>(m, (const double*)xF, (double*)yE);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// ============================ K4: fused edge-form operator =======================
+// y = C^T diag(alpha) C x + s * beta .* x  with C = diag(1/area) C_topo diag(len):
+//   y_e = len_e * sum_{f around e} +-[ wF_f * circ_f(len .* x) ] + s beta_e x_e,
+// wF = alpha / area^2.  Serves FDEM-h (alpha = MfRho, beta = MeMu, s = i w),
+// FDEM-e / TDEM-e (alpha = MfMui, beta = MeSigma, s = i w | 1/dt).  3-D complex:
+// x 48 + y 48 + wF 24 + beta 24 = 144 B/cell; 2-D symmetric: 56 B/cell.
+template <typename T> struct WCirc {
+    const MeshD& m; EdgeV<T> e; const double *wx, *wy, *wz;
+    __device__ WCirc(const MeshD& m_, const T* v, const double* w) : m(m_), e(m_, v) {
+        wx = w; wy = w + m_.nFx; wz = w + m_.nFx + m_.nFy;
+    }
+    __device__ __forceinline__ T operator()(int kind, int i, int j, int k) const {
+        long long c = m.cidx(i, j, k);
+        if (kind == 0) return wx[c] * circFx(m, e, i, j, k);
+        if (kind == 1) return wy[c] * circFy(m, e, i, j, k);
+        return wz[c] * circFz(m, e, i, j, k);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TPB)
+k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ beta,
+          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot sl;
+    if (!slot_of(m, t, m.nz + 1, sl)) return;
+    int sys = blockIdx.y;
+    x += sys * m.nE;
+    y += sys * m.nE;
+    T s = Sc<T>::from(s_d[2 * sys], s_d[2 * sys + 1]);
+    int i = sl.i, j = sl.j, k = sl.k;
+    WCirc<T> f(m, x, wF);
+    long long c = m.cidx(i, j, k);
+    {
+        long long e = m.nEx + c;
+        y[e] = m.lEy(i, j) * gathEy<T>(m, f, i, j, k) + s * (beta[e] * x[e]);
+    }
+    if (m.sym) return;
+    y[c] = m.lEx(i) * gathEx<T>(m, f, i, j, k) + s * (beta[c] * x[c]);
+    if (k < m.nz) {
+        long long e = m.nEx + m.nEy + m.ez(i, j, k);
+        y[e] = m.lEz(k) * gathEz<T>(m, f, i, j, k) + s * (beta[e] * x[e]);
+        if (i == 0 && j == 0) {
+            long long a = m.nEx + m.nEy + m.ezaxis(k);
+            y[a] = m.lEz(k) * gathEzAxis<T>(m, f, k) + s * (beta[a] * x[a]);
+        }
+    }
+}
+
+int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const double* s_d,
+                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st) {
+    long long n = m.nxy * (m.nz + 1);
+    if (cplx_vec) k_edge_op<cplx><<<grid1(n, nsys), TPB, 0, st>>>(m, wF, beta, s_d, (const cplx*)x, (cplx*)y);
+    else k_edge_op<double><<<grid1(n, nsys), TPB, 0, st>>>(m, wF, beta, s_d, (const double*)x, (double*)y);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// ============================ K4': fused face-form operator ======================
+// y = alpha .* ( C diag(gamma) C^T (alpha .* x) + s x ),
+//   y_f = uF_f * circ_f( gE .* d ) + s * uF_f * area_f * x_f,
+//   d_e = sum_{f' around e} +- uF_f' x_f',  uF = alpha/area, gE = len^2 * gamma.
+// Serves FDEM-j / TDEM-j (alpha = MfRho, gamma = MeMuI) and the b forms
+// (alpha = MfMui, gamma = MeSigmaI).
+template <typename T> struct UFace {
+    const MeshD& m; FaceV<T> f; const double *ux, *uy, *uz;
+    __device__ UFace(const MeshD& m_, const T* v, const double* u) : m(m_), f(m_, v) {
+        ux = u; uy = u + m_.nFx; uz = u + m_.nFx + m_.nFy;
+    }
+    __device__ __forceinline__ T operator()(int kind, int i, int j, int k) const {
+        long long c = m.cidx(i, j, k);
+        if (kind == 0) return ux[c] * f.x[c];
+        if (kind == 1) return uy[c] * f.y[c];
+        return uz[c] * f.z[c];
+    }
+};
+// gE_e * d_e for each edge kind, evaluated on the fly
+template <typename T> struct GD {
+    const MeshD& m; UFace<T> u; const double *gx, *gy, *gz;
+    __device__ GD(const MeshD& m_, const T* v, const double* uF, const double* gE) : m(m_), u(m_, v, uF) {
+        gx = gE; gy = gE + m_.nEx; gz = gE + m_.nEx + m_.nEy;
+    }
+    __device__ __forceinline__ T ex(int i, int j, int k) const { return gx[m.cidx(i, j, k)] * gathEx<T>(m, u, i, j, k); }
+    __device__ __forceinline__ T ey(int i, int j, int k) const { return gy[m.cidx(i, j, k)] * gathEy<T>(m, u, i, j, k); }
+    __device__ __forceinline__ T ez(int i, int j, int k) const { return gz[m.ez(i, j, k)] * gathEz<T>(m, u, i, j, k); }
+    __device__ __forceinline__ T ezax(int k) const { return gz[m.ezaxis(k)] * gathEzAxis<T>(m, u, k); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TPB)
+k_face_op(MeshD m, const double* __restrict__ uF, const double* __restrict__ gE,
+          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot sl;
+    if (!slot_of(m, t, m.nz + 1, sl)) return;
+    int sys = blockIdx.y;
+    x += sys * m.nF;
+    y += sys * m.nF;
+    T s = Sc<T>::from(s_d[2 * sys], s_d[2 * sys + 1]);
+    int i = sl.i, j = sl.j, k = sl.k;
+    GD<T> d(m, x, uF, gE);
+    long long c = m.cidx(i, j, k);
+    if (k < m.nz) {
+        // Fx: + Ez(j+1) - Ez(j) - Ey(k+1) + Ey(k)
+        T r = d.ey(i, j, k) - d.ey(i, j, k + 1);
+        if (!m.sym) r += d.ez(i, m.jp(j), k) - d.ez(i, j, k);
+        double u = uF[c];
+        y[c] = u * r + s * ((u * m.aFx(i, j, k)) * x[c]);
+        if (!m.sym) {
+            // Fy: + Ex(k+1) - Ex(k) - Ez(i) + Ez(i-1 | axis)
+            T zin = (i > 0) ? d.ez(i - 1, j, k) : d.ezax(k);
+            T r2 = d.ex(i, j, k + 1) - d.ex(i, j, k) - d.ez(i, j, k) + zin;
+            double u2 = uF[m.nFx + c];
+            y[m.nFx + c] = u2 * r2 + s * ((u2 * m.aFy(i, k)) * x[m.nFx + c]);
+        }
+    }
+    // Fz: + Ey(i) - Ey(i-1) - Ex(j+1) + Ex(j)
+    T r3 = d.ey(i, j, k);
+    if (i > 0) r3 -= d.ey(i - 1, j, k);
+    if (!m.sym) r3 -= d.ex(i, m.jp(j), k) - d.ex(i, j, k);
+    long long fz = m.nFx + m.nFy + c;
+    double u3 = uF[fz];
+    y[fz] = u3 * r3 + s * ((u3 * m.aFz(i, j)) * x[fz]);
+}
+
+int launch_face_op(const MeshD& m, const double* uF, const double* gE, const double* s_d,
+                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st) {
+    long long n = m.nxy * (m.nz + 1);
+    if (cplx_vec) k_face_op<cplx><<<grid1(n, nsys), TPB, 0, st>>>(m, uF, gE, s_d, (const cplx*)x, (cplx*)y);
+    else k_face_op<double><<<grid1(n, nsys), TPB, 0, st>>>(m, uF, gE, s_d, (const double*)x, (double*)y);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+}  // namespace cs

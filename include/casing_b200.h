@@ -1,0 +1,115 @@
+/* casing_b200 -- C ABI of the B200-native cylindrical-mesh EM solver.
+ *
+ * Drop-in boundary for the hot path casingSimulations hands to SimPEG + a sparse
+ * direct solver.  Every entry point replaces a call that the reference makes
+ * into un-vendored third-party code; the reference call site is cited.
+ *
+ * Conventions: every function returns 0 on success; on failure a message is
+ * available from cs_last_error().  Pointers suffixed _h are host pointers,
+ * _d device pointers (owned by the caller, e.g. torch tensors).  Vectors use
+ * the reference layout (casingSimulations/utils.py:41-47, 63-67): Fortran order,
+ * i = r fastest, [Fx|Fy|Fz] / [Ex|Ey|Ez]; complex128 = interleaved doubles.
+ * A cs_ctx is bound to one device and one stream; it is not thread safe,
+ * independent contexts are.
+ */
+#ifndef CASING_B200_H
+#define CASING_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cs_ctx cs_ctx;
+typedef struct cs_op cs_op;
+
+/* operator kinds (cs_op_create) */
+#define CS_KIND_DC 0          /* D~ MfRhoI D~^T            Problem3D_CC, run.py:339-344            */
+#define CS_KIND_DC_GROUNDED 1 /* same + 1 at [0,0]          SimPEG tdem getAdc, via run.py:287-296  */
+#define CS_KIND_EDGE_H 2      /* C^T MfRho C + s MeMu       Problem3D_h, run.py:240-248             */
+#define CS_KIND_EDGE_E 3      /* C^T MfMui C + s MeSigma    Problem3D_e                             */
+#define CS_KIND_FACE_J 4      /* MfRho (C MeMuI C^T MfRho + s)   Problem3D_j, run.py:287-296        */
+#define CS_KIND_FACE_B 5      /* MfMui (C MeSigmaI C^T MfMui + s) Problem3D_b                       */
+
+/* info_h layout (doubles) returned by the solve calls */
+#define CS_INFO_ITERS 0      /* Krylov iterations (max over systems)          */
+#define CS_INFO_RELRES 1     /* max over systems of ||b - A x|| / ||b||       */
+#define CS_INFO_MS_ASSEMBLE 2
+#define CS_INFO_MS_FACTOR 3
+#define CS_INFO_MS_SOLVE 4
+#define CS_INFO_N_APPLY 5    /* stencil applies (per system)                  */
+#define CS_INFO_N_LAUNCH 6   /* kernels launched by this call                 */
+#define CS_INFO_BYTES 7      /* algorithmic bytes moved by the stencil applies */
+#define CS_INFO_CONVERGED 8
+#define CS_INFO_LEN 16
+
+const char* cs_last_error(void);
+long long cs_launch_count(void);
+
+/* lifetime; stream may be NULL (a private stream is created) */
+int cs_ctx_create(int device, void* stream, cs_ctx** out);
+int cs_ctx_destroy(cs_ctx* ctx);
+int cs_ctx_sync(cs_ctx* ctx);
+
+/* discretize.CylMesh([hx, hy, hz], x0)            mesh.py:87-99, 518, 563 */
+int cs_mesh_set(cs_ctx* ctx, int nx, int nth, int nz, const double* hx_h, const double* hth_h,
+                const double* hz_h, double z0, double axis_weight_edge, double axis_weight_face);
+/* counts: nC nFx nFy nFz nEx nEy nEz */
+int cs_mesh_counts(cs_ctx* ctx, long long* out7_h);
+
+/* CasingInHalfspace.sigma / .mur                   model.py:190-260, 507-580, 699-717
+ * params_h: 18 doubles, see cs_kernels.cu k_paint.  Writes the context's model
+ * and, when non-NULL, the caller's sigma_d / mu_d (nC doubles each).          */
+int cs_model_paint(cs_ctx* ctx, const double* params_h, double* sigma_d, double* mu_d);
+/* PhysicalProperties.model = [sigma; mu]           model.py:848-868 */
+int cs_model_set(cs_ctx* ctx, const double* sigma_d, const double* mu_d);
+
+/* mesh.getFaceInnerProduct / getEdgeInnerProduct diagonals  (SimPEG MfRho, MeMu, ...) */
+int cs_face_inner_product(cs_ctx* ctx, const double* prop_d, int invProp, int invMat, double* out_d);
+int cs_edge_inner_product(cs_ctx* ctx, const double* prop_d, int invProp, int invMat, double* out_d);
+
+/* mesh.edgeCurl, its transpose, vol*faceDiv and its transpose (is_complex: 0/1) */
+int cs_curl(cs_ctx* ctx, const void* xE_d, void* yF_d, int is_complex);
+int cs_curlT(cs_ctx* ctx, const void* xF_d, void* yE_d, int is_complex);
+int cs_div(cs_ctx* ctx, const void* xF_d, void* yC_d, int is_complex);
+int cs_divT(cs_ctx* ctx, const void* xC_d, void* yF_d, int is_complex);
+
+/* operator objects: weights (K2) + band plan + probed theta-mode band matrices.
+ * Cached per kind inside the context; invalidated by cs_model_* / cs_mesh_set. */
+int cs_op_get(cs_ctx* ctx, int kind, cs_op** out);
+long long cs_op_size(cs_op* op);
+/* y = A(s) x for nvec vectors, shifts_h: 2 doubles (re, im) per vector.  K3 / K4. */
+int cs_op_apply(cs_op* op, const double* shifts_h, const void* x_d, void* y_d, int nvec, int is_complex);
+/* Solver(A)  : factor A(s_f) for nshift shifts      run.py:246, 294, 343 */
+int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int complex_shift);
+/* Ainv * rhs : preconditioned Krylov to rtol; vector v uses shift shift_of_vec_h[v] */
+int cs_op_solve(cs_op* op, const void* rhs_d, void* x_d, int nvec, const int* shift_of_vec_h,
+                int is_complex, double rtol, int maxit, double* info_h);
+/* Ainv.clean() */
+int cs_op_clean(cs_op* op);
+
+/* Problem3D_CC.fields: phi = A^-1 q, q (nC x nrhs) column-major    run.py:205, 339-352 */
+int cs_solve_dc(cs_ctx* ctx, const double* q_d, double* phi_d, int nrhs, double rtol, int maxit, double* info_h);
+/* Problem3D_{h,j}.fields: one solve per frequency (form 'h' or 'j'); s_e_d real face
+ * vector (sources.py:119-123); u_d complex, nfreq columns of nE (h) or nF (j)   run.py:205, 237-257 */
+int cs_solve_fdem(cs_ctx* ctx, int form, const double* freqs_h, int nfreq, const double* s_e_d,
+                  void* u_d, double rtol, int maxit, double* info_h);
+/* Problem3D_j.fields (backward Euler, step-off RawVec_Grounded): out_d is
+ * (nF x (nsteps+1)) column-major                                     run.py:205, 284-301 */
+int cs_tdem_run(cs_ctx* ctx, int form, const double* dts_h, int nsteps, const double* s_e_d,
+                double* out_d, double rtol, int maxit, double* info_h);
+
+/* Fields derived quantities (tests/test_cyl2D3D.py:212,266; run.py:211)
+ * which: 'j','e','h','b' ; kind: the formulation the solution u came from */
+int cs_fields_fdem(cs_ctx* ctx, int form, int which, double freq, const void* u_d, const double* s_e_d, void* out_d);
+int cs_fields_dc(cs_ctx* ctx, int which, const double* phi_d, double* out_d, int nrhs);
+
+/* physics.casing_currents / casing_charges            physics.py:10-83
+ * ix_d: nz doubles (per z cell), iz_d: nz+1 doubles (per z node); j real or complex */
+int cs_casing_currents(cs_ctx* ctx, const void* j_d, int is_complex, double casing_a, double casing_b,
+                       double casing_z0, double casing_z1, void* ix_d, void* iz_d);
+int cs_casing_charges(cs_ctx* ctx, const double* charge_d, double casing_b, double casing_z0,
+                      double casing_z1, double* out_d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,198 @@
+"""GPU parity tests: every CUDA kernel / driver behind the C ABI against the CPU
+oracle (oracle/cyl_oracle.py) on the same seeded inputs.  Tolerances: fp64 stencil
+applies 1e-12 relative (sum-order differences only); solves: Krylov relres <= 1e-10
+and solution rel-L2 vs the oracle's SuperLU solve <= 1e-6 (BASELINE.json north_star)
+wherever the system's conditioning allows the oracle itself that accuracy."""
+import numpy as np
+import pytest
+
+from conftest import CASING, paint_params, small_casing_mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def setup(ctx, nth, halfspace=True):
+    from oracle.cyl_oracle import OracleCylMesh, paint_casing_in_halfspace
+    hx, hy, hz, z0 = small_casing_mesh(nth)
+    om = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    ctx.set_mesh(hx, hy, hz, z0)
+    sig, mu = paint_casing_in_halfspace(om, halfspace=halfspace, **CASING)
+    s_d, m_d = ctx.paint(paint_params(CASING, halfspace))
+    return om, sig, mu, s_d, m_d
+
+
+def rnd(n, cplx, seed=0):
+    x = np.random.default_rng(seed).standard_normal(n)
+    if cplx:
+        x = x + 1j * np.random.default_rng(seed + 1).standard_normal(n)
+    return x
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_counts_and_paint(gpu_ctx, nth):
+    om, sig, mu, s_d, m_d = setup(gpu_ctx, nth)
+    assert (gpu_ctx.nC, gpu_ctx.nF, gpu_ctx.nE) == (om.nC, om.nF, om.nE)
+    assert np.array_equal(s_d.cpu().numpy(), sig)          # bit exact
+    assert np.array_equal(m_d.cpu().numpy(), mu)
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_inner_products(gpu_ctx, nth):
+    om, sig, mu, s_d, m_d = setup(gpu_ctx, nth)
+    for invP in (False, True):
+        for invM in (False, True):
+            f = gpu_ctx.face_inner_product(s_d, invP, invM).cpu().numpy()
+            e = gpu_ctx.edge_inner_product(m_d, invP, invM).cpu().numpy()
+            assert rel(f, om.getFaceInnerProduct(sig, invP, invM).diagonal()) < 1e-14
+            assert rel(e, om.getEdgeInnerProduct(mu, invP, invM).diagonal()) < 1e-14
+    assert rel(gpu_ctx.face_inner_product().cpu().numpy(), om.getFaceInnerProduct().diagonal()) < 1e-14
+    assert rel(gpu_ctx.edge_inner_product().cpu().numpy(), om.getEdgeInnerProduct().diagonal()) < 1e-14
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_diff_operators(gpu_ctx, nth, cplx):
+    from oracle.cyl_oracle import _sdiag
+    om, *_ = setup(gpu_ctx, nth)
+    xe, xf, xc = rnd(om.nE, cplx), rnd(om.nF, cplx, 2), rnd(om.nC, cplx, 4)
+    C = om.edgeCurl
+    Dt = om._Dtopo() @ _sdiag(om.area)
+    assert rel(gpu_ctx.curl(gpu_ctx.to_device(xe)).cpu().numpy(), C @ xe) < 1e-13
+    assert rel(gpu_ctx.curlT(gpu_ctx.to_device(xf)).cpu().numpy(), C.T @ xf) < 1e-13
+    assert rel(gpu_ctx.div(gpu_ctx.to_device(xf)).cpu().numpy(), Dt @ xf) < 1e-13
+    assert rel(gpu_ctx.divT(gpu_ctx.to_device(xc)).cpu().numpy(), Dt.T @ xc) < 1e-13
+
+
+def oracle_matrix(om, sig, mu, kind, s):
+    import scipy.sparse as sp
+    from oracle.cyl_oracle import OracleDC, OracleFDEM
+    P = OracleFDEM(om, sig, mu)
+    C = P.C
+    if kind == "dc":
+        return OracleDC(om, sig).getA()
+    if kind == "edge_h":
+        return C.T @ P.MfRho @ C + s * P.MeMu
+    if kind == "edge_e":
+        return C.T @ P.MfMui @ C + s * P.MeSigma
+    if kind == "face_j":
+        return P.MfRho @ (C @ P.MeMuI @ C.T @ P.MfRho + s * sp.identity(om.nF))
+    if kind == "face_b":
+        return P.MfMui @ (C @ P.MeSigmaI @ C.T @ P.MfMui + s * sp.identity(om.nF))
+
+
+KINDS = {"dc": 0, "edge_h": 2, "edge_e": 3, "face_j": 4, "face_b": 5}
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+@pytest.mark.parametrize("kind", ["dc", "edge_h", "edge_e", "face_j", "face_b"])
+def test_operator_apply(gpu_ctx, nth, kind):
+    om, sig, mu, *_ = setup(gpu_ctx, nth)
+    op = gpu_ctx.op(KINDS[kind])
+    for cplx, s in ((False, 3.0), (True, 2j * np.pi * 7.0)):
+        if kind == "dc":
+            s = 0.0
+        A = oracle_matrix(om, sig, mu, kind, s)
+        x = np.stack([rnd(op.n, cplx, 10), rnd(op.n, cplx, 20)])
+        y = op.apply(gpu_ctx.to_device(x), shifts=s).cpu().numpy()
+        for v in range(2):
+            assert rel(y[v], A @ x[v]) < 1e-12, (kind, nth, cplx, rel(y[v], A @ x[v]))
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_dc_solve(gpu_ctx, nth):
+    from oracle.cyl_oracle import OracleDC
+    om, sig, mu, *_ = setup(gpu_ctx, nth)
+    P = OracleDC(om, sig)
+    a = np.array([[0.03, np.pi / 4 if nth > 1 else 0.0, -0.25], [0.03, 0.0, -1.2]])
+    b = np.array([[2.0, 5 * np.pi / 4 if nth > 1 else 0.0, -0.25], [1.0, 0.0, -0.25]])
+    q = P.getRHS(a, b)
+    phi_ref = P.fields(a, b)
+    phi = gpu_ctx.solve_dc(gpu_ctx.to_device(q.T.copy())).cpu().numpy().T
+    print("dc info", gpu_ctx.info)
+    assert gpu_ctx.info["relres"] <= 1e-10
+    assert rel(phi, phi_ref) < 1e-6, rel(phi, phi_ref)
+    j = gpu_ctx.fields_dc("j", gpu_ctx.to_device(phi.T.copy())).cpu().numpy().T
+    assert rel(j, P.j(phi)) < 1e-12
+    e = gpu_ctx.fields_dc("e", gpu_ctx.to_device(phi.T.copy())).cpu().numpy().T
+    assert rel(e, P.e(phi)) < 1e-12
+    ch = gpu_ctx.fields_dc("charge", gpu_ctx.to_device(phi.T.copy())).cpu().numpy().T
+    assert rel(ch, P.charge(phi)) < 1e-10
+
+
+def source_wire(om):
+    """vertical wire down the innermost cells + return, as tests/test_cyl2D3D.py:22-40"""
+    g = om.gridFz
+    w = np.zeros(om.nFz)
+    sel = (g[:, 0] < om.hx.min()) & (g[:, 2] > -2.6) & (g[:, 2] < 0.1)
+    if not om.isSymmetric:
+        sel &= g[:, 1] < om.hy[0]
+    w[sel] = 1.0
+    return np.r_[np.zeros(om.nFx + om.nFy), w] / om.area
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+@pytest.mark.parametrize("form", ["h", "j"])
+def test_fdem_solve(gpu_ctx, nth, form):
+    from oracle.cyl_oracle import OracleFDEM
+    om, sig, mu, *_ = setup(gpu_ctx, nth)
+    se = source_wire(om)
+    freqs = np.r_[1.0, 100.0, 1e4]
+    P = OracleFDEM(om, sig, mu, form)
+    u = gpu_ctx.solve_fdem(form, freqs, gpu_ctx.to_device(se)).cpu().numpy()
+    print("fdem info", form, nth, gpu_ctx.info)
+    assert gpu_ctx.info["relres"] <= 1e-10
+    for f, freq in enumerate(freqs):
+        A, rhs = P.getA(freq), P.getRHS(freq, se)
+        assert np.linalg.norm(A @ u[f] - rhs) <= 1e-10 * np.linalg.norm(rhs)
+        uref = P.solve(freq, se)
+        jref, jg = P.j_from(freq, uref, se), P.j_from(freq, u[f], se)
+        print("  f", freq, "u rel", rel(u[f], uref), "j rel", rel(jg, jref))
+        jd = gpu_ctx.fields_fdem(form, "j", freq, gpu_ctx.to_device(u[f]), gpu_ctx.to_device(se)).cpu().numpy()
+        assert rel(jd, jg) < 1e-12
+        ed = gpu_ctx.fields_fdem(form, "e", freq, gpu_ctx.to_device(u[f]), gpu_ctx.to_device(se)).cpu().numpy()
+        assert rel(ed, P.e_from(freq, u[f], se)) < 1e-12
+        hd = gpu_ctx.fields_fdem(form, "h", freq, gpu_ctx.to_device(u[f]), gpu_ctx.to_device(se)).cpu().numpy()
+        assert rel(hd, P.h_from(freq, u[f], se)) < 1e-10
+        bd = gpu_ctx.fields_fdem(form, "b", freq, gpu_ctx.to_device(u[f]), gpu_ctx.to_device(se)).cpu().numpy()
+        assert rel(bd, P.b_from(freq, u[f], se)) < 1e-10
+        if nth == 1:
+            assert rel(u[f], uref) < 1e-6, rel(u[f], uref)
+        assert rel(jg, jref) < 1e-6, rel(jg, jref)
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_tdem_run(gpu_ctx, nth):
+    from oracle.cyl_oracle import OracleTDEM
+    om, sig, mu, *_ = setup(gpu_ctx, nth)
+    se = source_wire(om)
+    steps = [(1e-5, 3), (1e-4, 3)]
+    P = OracleTDEM(om, sig, mu, steps)
+    Fref = P.fields(se)
+    F = gpu_ctx.tdem_run("j", P.time_steps, gpu_ctx.to_device(se)).cpu().numpy().T
+    print("tdem info", gpu_ctx.info)
+    for t in range(Fref.shape[1]):
+        print("  step", t, rel(F[:, t], Fref[:, t]))
+    assert rel(F, Fref) < 1e-6
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_casing_currents(gpu_ctx, nth):
+    from oracle.cyl_oracle import casing_currents, casing_charges
+    om, *_ = setup(gpu_ctx, nth)
+    j = rnd(om.nF, True, 5)
+    ref = casing_currents(j, om, CASING["casing_a"], CASING["casing_b"], CASING["casing_z"])
+    ix, iz = gpu_ctx.casing_currents(gpu_ctx.to_device(j), CASING["casing_a"], CASING["casing_b"], CASING["casing_z"])
+    ix, iz = ix.cpu().numpy(), iz.cpu().numpy()
+    cz = CASING["casing_z"]
+    ixs = ix[(om.vectorCCz > cz[0]) & (om.vectorCCz < cz[1])]
+    izs = iz[(om.vectorNz > cz[0]) & (om.vectorNz < cz[1])]
+    assert rel(ixs, ref["x"][1]) < 1e-13 and rel(izs, ref["z"][1]) < 1e-13
+    ch = rnd(om.nC, False, 9)
+    z, cref = casing_charges(ch, om, CASING["casing_b"], cz)
+    cg = gpu_ctx.casing_charges(gpu_ctx.to_device(ch), CASING["casing_b"], cz).cpu().numpy()
+    assert rel(cg[(om.vectorCCz > cz[0]) & (om.vectorCCz < cz[1])], cref) < 1e-13
