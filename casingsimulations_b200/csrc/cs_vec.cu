@@ -10,17 +10,17 @@ static const int DOT_BLOCKS = 256;   // partial sums per system
 
 template <typename T, bool CONJ>
 __global__ void k_dot_partial(const T* __restrict__ a, const T* __restrict__ b, long long n, double* __restrict__ part,
-                              const double* __restrict__ w, const int* __restrict__ wsel) {
+                              const double* __restrict__ wt, const int* __restrict__ wsel) {
     int sys = blockIdx.y;
     a += sys * n;
     b += sys * n;
-    if (w) w += (wsel ? wsel[sys] : 0) * n;
+    if (wt) wt += (wsel ? wsel[sys] : 0) * n;
     double re = 0.0, im = 0.0;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         T av = a[t], bv = b[t];
         if (CONJ) av = Sc<T>::conj(av);
         T pr = av * bv;
-        double ww = w ? w[t] : 1.0;
+        double ww = wt ? wt[t] : 1.0;
         re += ww * Sc<T>::re(pr);
         im += ww * Sc<T>::im(pr);
     }

@@ -424,6 +424,31 @@ class SolverLU(object):
         self.lu = None
 
 
+def solve_refined(A, b, iters=10, lu=None):
+    """"Truth" for parity tests: SuperLU solution polished by iterative refinement
+    with the residual b - A x accumulated in extended precision (np.longdouble).
+    The casing systems are so ill-conditioned (coefficient contrast 1e13, curl-curl
+    null space) that a plain fp64 direct solve -- the reference's Pardiso / SolverLU
+    included -- carries a relative error of 1e-7 (DC) up to 1e-4 (3-D FDEM j at 1 Hz);
+    returns (x_refined, x_plain_splu)."""
+    A = A.tocsr()
+    A.sort_indices()
+    b = np.asarray(b)
+    cplx = np.iscomplexobj(A.data) or np.iscomplexobj(b)
+    ld = np.clongdouble if cplx else np.longdouble
+    wd = complex if cplx else float
+    if lu is None:
+        lu = spla.splu(A.tocsc().astype(wd))
+    x0 = lu.solve(b.astype(wd))
+    data = A.data.astype(ld)
+    assert np.all(np.diff(A.indptr) > 0)
+    x, bl = x0.astype(ld), b.astype(ld)
+    for _ in range(iters):
+        r = bl - np.add.reduceat(data * x[A.indices], A.indptr[:-1])
+        x = x + lu.solve(r.astype(wd)).astype(ld)
+    return x.astype(wd), x0
+
+
 # --------------------------------------------------------------------------
 # DC  (A.5; Problem3D_CC, Dirichlet; run.py:339-352)
 # --------------------------------------------------------------------------
@@ -446,8 +471,12 @@ class OracleDC(object):
             q[closest_points(cc, src_b[s])[0], s] -= current
         return q
 
-    def fields(self, src_a, src_b):
+    def fields(self, src_a, src_b, refine=False):
         q = self.getRHS(src_a, src_b)
+        if refine:
+            A = self.getA()
+            lu = spla.splu(A.tocsc())
+            return np.stack([solve_refined(A, q[:, s], lu=lu)[0] for s in range(q.shape[1])], axis=1)
         Ainv = SolverLU(self.getA())
         phi = Ainv * q
         return phi
@@ -509,8 +538,10 @@ class OracleFDEM(object):
             return self.MfRho @ (-1j * w * s_e)
         raise NotImplementedError("oracle RHS only for the face-source forms h, j")
 
-    def solve(self, freq, s_e):
+    def solve(self, freq, s_e, refine=False):
         A = self.getA(freq)
+        if refine:
+            return solve_refined(A, self.getRHS(freq, s_e))[0]
         Ainv = SolverLU(A)
         u = Ainv * self.getRHS(freq, s_e)
         Ainv.clean()
@@ -559,33 +590,38 @@ class OracleTDEM(object):
             A[0, 0] = A[0, 0] + 1.0            # [3P-recall] SimPEG tdem getAdc
         return A.tocsr()
 
-    def j_initial(self, s_e):
-        phi = SolverLU(self.getAdc()) * (self.Dt @ s_e)
+    def j_initial(self, s_e, refine=False):
+        if refine:
+            phi = solve_refined(self.getAdc(), self.Dt @ s_e)[0]
+        else:
+            phi = SolverLU(self.getAdc()) * (self.Dt @ s_e)
         return -(self.MfRhoI @ (self.Dt.T @ phi)), phi
 
     def getAdiag(self, dt):
         n = self.mesh.nF
         return (self.MfRho @ (self.C @ self.MeMuI @ self.C.T @ self.MfRho + sp.identity(n) / dt)).tocsr()
 
-    def fields(self, s_e):
+    def fields(self, s_e, refine=False):
         """returns jSolution (nF x (nT+1)); step-off waveform: s_e(t=0) = s_e,
         s_e(t>0) = 0."""
         assert self.form == "j"
         s_e = np.asarray(s_e, dtype=float)
         nT = len(self.time_steps)
         F = np.zeros((self.mesh.nF, nT + 1))
-        F[:, 0], _ = self.j_initial(s_e)
-        Ainv, dt_prev = None, None
+        F[:, 0], _ = self.j_initial(s_e, refine)
+        A, lu, dt_prev = None, None, None
         for t, dt in enumerate(self.time_steps):
-            if Ainv is not None and abs(dt - dt_prev) > self.dt_threshold:
-                Ainv.clean(); Ainv = None
-            if Ainv is None:
-                Ainv = SolverLU(self.getAdiag(dt)); dt_prev = dt
+            if lu is None or abs(dt - dt_prev) > self.dt_threshold:
+                A = self.getAdiag(dt)
+                lu = spla.splu(A.tocsc()); dt_prev = dt
             se_n1 = 0.0 * s_e
             se_n = s_e if t == 0 else 0.0 * s_e
             rhs = self.MfRho @ (-(se_n1 - se_n) / dt)
             Asub_x = -(self.MfRho @ F[:, t]) / dt
-            F[:, t + 1] = Ainv * (rhs - Asub_x)
+            if refine:
+                F[:, t + 1] = solve_refined(A, rhs - Asub_x, lu=lu)[0]
+            else:
+                F[:, t + 1] = lu.solve(rhs - Asub_x)
         return F
 
 
