@@ -64,6 +64,9 @@ def load_library():
         "cs_div": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_divT": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_op_get": (c.c_int, [vp, c.c_int, c.POINTER(vp)]),
+        "cs_op_get_noplan": (c.c_int, [vp, c.c_int, c.POINTER(vp)]),
+        "cs_op_apply_timed": (c.c_int, [vp, dp, vp, vp, c.c_int, c.c_int, c.c_int, dp]),
+        "cs_op_from_csr": (c.c_int, [vp, c.c_int, ll, ll, c.POINTER(ll), ip, vp, c.c_int, c.POINTER(vp)]),
         "cs_op_size": (ll, [vp]),
         "cs_op_apply": (c.c_int, [vp, dp, vp, vp, c.c_int, c.c_int]),
         "cs_op_factor": (c.c_int, [vp, dp, c.c_int, c.c_int]),
@@ -88,7 +91,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_mesh_set",
     "cs_mesh_counts", "cs_model_paint", "cs_model_set", "cs_face_inner_product", "cs_edge_inner_product",
-    "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_op_get", "cs_op_size", "cs_op_apply", "cs_op_factor",
+    "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_op_get", "cs_op_get_noplan", "cs_op_apply_timed", "cs_op_from_csr", "cs_op_size", "cs_op_apply", "cs_op_factor",
     "cs_op_solve", "cs_op_clean", "cs_solve_dc", "cs_solve_fdem", "cs_tdem_run", "cs_fields_fdem",
     "cs_fields_dc", "cs_casing_currents", "cs_casing_charges",
 ]
@@ -117,12 +120,13 @@ def _tptr(t):
 class Op(object):
     """One assembled operator (weights + theta-mode band matrices) of a Context."""
 
-    def __init__(self, ctx, kind):
+    def __init__(self, ctx, kind, handle=None):
         self.ctx, self.kind = ctx, kind
-        h = ctypes.c_void_p()
-        check(ctx.lib.cs_op_get(ctx.h, kind, ctypes.byref(h)))
-        self.h = h
-        self.n = int(ctx.lib.cs_op_size(h))
+        if handle is None:
+            handle = ctypes.c_void_p()
+            check(ctx.lib.cs_op_get(ctx.h, kind, ctypes.byref(handle)))
+        self.h = handle
+        self.n = int(ctx.lib.cs_op_size(handle))
 
     def apply(self, x, shifts=None):
         """y = A(s) x; x torch tensor (nvec, n) or (n,), float64 or complex128."""
@@ -137,6 +141,18 @@ class Op(object):
             sh[0::2], sh[1::2] = s.real, s.imag
         check(self.ctx.lib.cs_op_apply(self.h, _dptr(sh), _tptr(x2), _tptr(y), nvec, int(x2.is_complex())))
         return y.reshape(x.shape)
+
+    def apply_timed(self, x, shift=0.0, reps=20):
+        """average device time (ms) of one apply launch, CUDA events on the library stream"""
+        torch = _torch()
+        x2 = x.reshape(-1, self.n).contiguous()
+        y = torch.empty_like(x2)
+        s = complex(shift)
+        sh = np.tile(np.array([s.real, s.imag]), x2.shape[0])
+        ms = ctypes.c_double(0.0)
+        check(self.ctx.lib.cs_op_apply_timed(self.h, _dptr(sh), _tptr(x2), _tptr(y), x2.shape[0], int(x2.is_complex()),
+                                             int(reps), ctypes.byref(ms)))
+        return ms.value
 
     def factor(self, shifts=(0.0,)):
         s = np.atleast_1d(np.asarray(shifts, dtype=complex))
@@ -168,12 +184,14 @@ class Op(object):
 class Context(object):
     """A solver context bound to one CUDA device (mirrors cs_ctx)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, stream=None):
+        """stream: raw cudaStream_t (int) to run on, e.g. torch.cuda.Stream().cuda_stream;
+        None creates a private non-blocking stream."""
         torch = _torch()
         self.lib = load_library()
         self.device = torch.device("cuda", device)
         h = ctypes.c_void_p()
-        check(self.lib.cs_ctx_create(device, None, ctypes.byref(h)))
+        check(self.lib.cs_ctx_create(device, ctypes.c_void_p(stream) if stream else None, ctypes.byref(h)))
         self.h = h
         self.info = {}
 
@@ -261,8 +279,26 @@ class Context(object):
     def divT(self, xC):
         return self._unary(self.lib.cs_divT, xC, self.nC, self.nF)
 
-    def op(self, kind):
-        return Op(self, kind)
+    def op(self, kind, plan=True):
+        if plan:
+            return Op(self, kind)
+        h = ctypes.c_void_p()
+        check(self.lib.cs_op_get_noplan(self.h, kind, ctypes.byref(h)))
+        return Op(self, kind, handle=h)
+
+    def op_from_csr(self, A, family):
+        """Operator from an assembled scipy.sparse CSR matrix (Solver(A) plugin path)."""
+        A = A.tocsr()
+        cplx = np.iscomplexobj(A.data)
+        indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+        vals = np.ascontiguousarray(A.data, dtype=np.complex128 if cplx else np.float64)
+        h = ctypes.c_void_p()
+        check(self.lib.cs_op_from_csr(self.h, family, A.shape[0], A.nnz,
+                                      indptr.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                      indices.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                      vals.ctypes.data_as(ctypes.c_void_p), int(cplx), ctypes.byref(h)))
+        return Op(self, -1, handle=h)
 
     # -- physics-level drivers ----------------------------------------------
     def _info(self, info):

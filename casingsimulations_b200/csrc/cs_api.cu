@@ -39,6 +39,9 @@ struct cs_op {
     long long n = 0;                 // vector length
     double *w1 = nullptr, *w2 = nullptr, *mass = nullptr;
     double shift0 = 0.0;
+    // assembled-matrix operators (Solver(A) plugin): CSR on the device
+    bool is_csr = false, csr_cplx = false;
+    long long* csr_indptr = nullptr; int* csr_indices = nullptr; void* csr_vals = nullptr; long long csr_nnz = 0;
     BandPlan bp;
     DevBuf LU, wts;               // wts: [nshift][n] = 1/|diag A(s)|, the norm of the convergence tests
     bool lu_cplx = false;
@@ -65,7 +68,8 @@ struct cs_ctx {
 static void op_free(cs_op* op) {
     if (!op) return;
     cudaFree(op->w1); cudaFree(op->w2);
-    if (op->family == 2) cudaFree(op->mass);   // edge family: mass aliases w2
+    cudaFree(op->csr_indptr); cudaFree(op->csr_indices); cudaFree(op->csr_vals);
+    if (op->family == 2 && !op->is_csr) cudaFree(op->mass);   // edge family: mass aliases w2
     cudaFree(op->bp.map3d); cudaFree(op->bp.jstr); cudaFree(op->bp.mdiag); cudaFree(op->bp.Kband);
     op->LU.release(); op->wts.release();
     delete op;
@@ -160,6 +164,7 @@ static inline size_t esz(bool c) { return c ? sizeof(cplx) : sizeof(double); }
 static int op_apply_dev(cs_op* op, const double* s_d, const void* x, void* y, int nvec, bool cplx_vec) {
     cs_ctx* c = op->ctx;
     g_launches += 1;
+    if (op->is_csr) return launch_csr_spmv(op->n, op->csr_indptr, op->csr_indices, op->csr_vals, op->csr_cplx, x, y, nvec, cplx_vec, c->st);
     if (op->family == 0) return launch_dc_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st);
     if (op->family == 1) return launch_edge_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st);
     return launch_face_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st);
@@ -167,6 +172,7 @@ static int op_apply_dev(cs_op* op, const double* s_d, const void* x, void* y, in
 static double op_bytes_per_apply(cs_op* op, bool cplx_vec) {
     const MeshD& m = op->ctx->m;
     double v = cplx_vec ? 16.0 : 8.0;
+    if (op->is_csr) return (double)op->csr_nnz * ((op->csr_cplx ? 16.0 : 8.0) + 4.0) + (double)op->n * (2 * v + 8.0);
     if (op->family == 0) return (double)m.nC * (2 * v + (m.sym ? 16.0 : 24.0));
     if (m.sym) return (double)m.nC * (op->family == 1 ? (2 * v + 16.0 + 8.0) : (4 * v + 16.0 + 8.0));
     return (double)m.nC * (6 * v + 24.0 + 24.0);
@@ -222,7 +228,7 @@ static int build_plan(cs_op* op) {
     bp.pw = bp.p + bp.nb;
     bp.ldab = 2 * bp.pw + 1;
     bp.nmodes = nth;
-    bp.cplx_band = (nth > 1);
+    bp.cplx_band = (nth > 1) || op->csr_cplx;
     CS_CUDA(cudaMalloc(&bp.map3d, bp.n2 * sizeof(long long)));
     CS_CUDA(cudaMalloc(&bp.jstr, bp.n2 * sizeof(int)));
     CS_CUDA(cudaMalloc(&bp.mdiag, bp.n2 * sizeof(double)));
@@ -260,9 +266,16 @@ static int probe_plan(cs_op* op) {
     return CS_OK;
 }
 
-extern "C" int cs_op_get(cs_ctx* c, int kind, cs_op** out) {
+static int op_get(cs_ctx* c, int kind, bool with_plan, cs_op** out);
+extern "C" int cs_op_get(cs_ctx* c, int kind, cs_op** out) { return op_get(c, kind, true, out); }
+// weights only (K2), no theta-mode band matrices: for stencil-apply measurements at
+// sizes whose direct factors would not fit one GPU.  factor / solve on it raise.
+extern "C" int cs_op_get_noplan(cs_ctx* c, int kind, cs_op** out) { return op_get(c, kind, false, out); }
+
+static int op_get(cs_ctx* c, int kind, bool with_plan, cs_op** out) {
     CS_CHECK(c && c->has_mesh && c->has_model, "mesh and model must be set first");
-    auto it = c->ops.find(kind);
+    int key = with_plan ? kind : 1000 + kind;
+    auto it = c->ops.find(key);
     if (it != c->ops.end()) { *out = it->second; return CS_OK; }
     CS_CUDA(cudaSetDevice(c->device));
     const MeshD& m = c->m;
@@ -302,13 +315,44 @@ extern "C" int cs_op_get(cs_ctx* c, int kind, cs_op** out) {
         return fail(CS_ERR);
     }
     g_launches += 4;
-    rc = build_plan(op); if (rc) return fail(rc);
-    rc = probe_plan(op); if (rc) return fail(rc);
+    if (with_plan) {
+        rc = build_plan(op); if (rc) return fail(rc);
+        rc = probe_plan(op); if (rc) return fail(rc);
+    }
     cudaEventRecord(c->ev1, c->st);
     if (cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("sync failed in cs_op_get"); return fail(CS_ERR); }
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     op->ms_assemble = ms;
-    c->ops[kind] = op;
+    c->ops[key] = op;
+    *out = op;
+    return CS_OK;
+}
+
+extern "C" int cs_op_from_csr(cs_ctx* c, int family, long long n, long long nnz, const long long* indptr_h,
+                              const int* indices_h, const void* vals_h, int is_complex, cs_op** out) {
+    CS_CHECK(c && c->has_mesh, "mesh must be set first");
+    CS_CHECK(family >= 0 && family <= 2, "family must be 0 (cells), 1 (edges) or 2 (faces)");
+    const MeshD& m = c->m;
+    long long expect = family == 0 ? m.nC : (family == 1 ? m.nE : m.nF);
+    CS_CHECK(n == expect, "matrix size does not match the mesh for this family");
+    CS_CUDA(cudaSetDevice(c->device));
+    cs_op* op = new cs_op();
+    op->ctx = c; op->kind = -1; op->family = family; op->n = n; op->is_csr = true; op->csr_cplx = is_complex != 0; op->csr_nnz = nnz;
+    size_t vb = (size_t)nnz * (is_complex ? sizeof(cplx) : sizeof(double));
+    if (cudaMalloc(&op->csr_indptr, (n + 1) * sizeof(long long)) != cudaSuccess || cudaMalloc(&op->csr_indices, nnz * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&op->csr_vals, vb) != cudaSuccess) { set_error("cudaMalloc failed for the CSR matrix"); op_free(op); return CS_ERR; }
+    cudaMemcpyAsync(op->csr_indptr, indptr_h, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(op->csr_indices, indices_h, nnz * sizeof(int), cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(op->csr_vals, vals_h, vb, cudaMemcpyHostToDevice, c->st);
+    CS_CUDA(cudaEventRecord(c->ev0, c->st));
+    int rc = build_plan(op); if (rc) { op_free(op); return rc; }
+    rc = probe_plan(op); if (rc) { op_free(op); return rc; }
+    cudaEventRecord(c->ev1, c->st);
+    if (cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("sync failed in cs_op_from_csr"); op_free(op); return CS_ERR; }
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    op->ms_assemble = ms;
+    static int next_key = -1;
+    c->ops[next_key--] = op;
     *out = op;
     return CS_OK;
 }
@@ -325,6 +369,22 @@ extern "C" int cs_op_apply(cs_op* op, const double* shifts_h, const void* x_d, v
     return op_apply_dev(op, (const double*)c->scal.p, x_d, y_d, nvec, is_complex != 0);
 }
 
+// reps back-to-back launches bracketed by CUDA events on the context's stream
+extern "C" int cs_op_apply_timed(cs_op* op, const double* shifts_h, const void* x_d, void* y_d, int nvec, int is_complex,
+                                 int reps, double* ms_per_launch) {
+    CS_CHECK(op && reps >= 1, "bad arguments");
+    cs_ctx* c = op->ctx;
+    CS_TRY(cs_op_apply(op, shifts_h, x_d, y_d, nvec, is_complex));   // uploads the shifts, warms up
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    CS_CUDA(cudaEventRecord(c->ev0, c->st));
+    for (int r = 0; r < reps; ++r) CS_TRY(op_apply_dev(op, (const double*)c->scal.p, x_d, y_d, nvec, is_complex != 0));
+    CS_CUDA(cudaEventRecord(c->ev1, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    *ms_per_launch = (double)ms / reps;
+    return CS_OK;
+}
+
 extern "C" int cs_op_clean(cs_op* op) {
     CS_CHECK(op, "null op");
     op->LU.release();
@@ -334,6 +394,7 @@ extern "C" int cs_op_clean(cs_op* op) {
 
 extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int complex_shift) {
     CS_CHECK(op && nshift >= 1, "bad arguments");
+    CS_CHECK(op->bp.Kband, "operator was created without a band plan (cs_op_get_noplan)");
     cs_ctx* c = op->ctx;
     CS_CUDA(cudaSetDevice(c->device));
     BandPlan& bp = op->bp;

@@ -31,6 +31,9 @@ int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const d
 int launch_face_op(const MeshD& m, const double* uF, const double* gE, const double* s_d,
                    const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
 
+int launch_csr_spmv(long long n, const long long* indptr, const int* indices, const void* vals, bool a_cplx,
+                    const void* x, void* y, int nsys, bool x_cplx, cudaStream_t st);
+
 // -------- cs_vec.cu : BLAS-1 style kernels ------------------------------------------
 // out[sys] = sum conj?(a) * b over n entries; results to dots_d[2*sys..]
 // optional weights w[wsel[sys]*n + t] (real, >= 0) give the diagonally scaled norms used by the convergence tests

@@ -445,4 +445,29 @@ int launch_face_op(const MeshD& m, const double* uF, const double* gE, const dou
     return CS_OK;
 }
 
+// ============================ CSR SpMV (Solver(A) plugin path) =====================
+// y = A x for an assembled matrix handed over through the SimPEG solver protocol
+// (run.py:246, 294, 343).  One thread per row: the systems have <= 33 nonzeros per row.
+template <typename TA, typename TX>
+__global__ void k_csr_spmv(long long n, const long long* __restrict__ indptr, const int* __restrict__ indices,
+                           const TA* __restrict__ vals, const TX* __restrict__ x, TX* __restrict__ y) {
+    long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    x += blockIdx.y * n;
+    y += blockIdx.y * n;
+    TX acc = Sc<TX>::zero();
+    for (long long e = indptr[r]; e < indptr[r + 1]; ++e) acc += vals[e] * x[indices[e]];
+    y[r] = acc;
+}
+int launch_csr_spmv(long long n, const long long* indptr, const int* indices, const void* vals, bool a_cplx,
+                    const void* x, void* y, int nsys, bool x_cplx, cudaStream_t st) {
+    dim3 g((unsigned)cdiv(n, TPB), nsys);
+    if (a_cplx && x_cplx) k_csr_spmv<cplx, cplx><<<g, TPB, 0, st>>>(n, indptr, indices, (const cplx*)vals, (const cplx*)x, (cplx*)y);
+    else if (!a_cplx && x_cplx) k_csr_spmv<double, cplx><<<g, TPB, 0, st>>>(n, indptr, indices, (const double*)vals, (const cplx*)x, (cplx*)y);
+    else if (!a_cplx && !x_cplx) k_csr_spmv<double, double><<<g, TPB, 0, st>>>(n, indptr, indices, (const double*)vals, (const double*)x, (double*)y);
+    else CS_CHECK(false, "complex matrix needs complex vectors");
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
 }  // namespace cs

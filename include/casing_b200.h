@@ -75,6 +75,16 @@ int cs_divT(cs_ctx* ctx, const void* xC_d, void* yF_d, int is_complex);
 /* operator objects: weights (K2) + band plan + probed theta-mode band matrices.
  * Cached per kind inside the context; invalidated by cs_model_* / cs_mesh_set. */
 int cs_op_get(cs_ctx* ctx, int kind, cs_op** out);
+/* weights only, no band matrices: stencil-apply measurements at sizes whose factors do not fit */
+int cs_op_get_noplan(cs_ctx* ctx, int kind, cs_op** out);
+/* reps launches of the apply kernel bracketed by CUDA events on the context's stream */
+int cs_op_apply_timed(cs_op* op, const double* shifts_h, const void* x_d, void* y_d, int nvec, int is_complex,
+                      int reps, double* ms_per_launch_h);
+/* Solver(A, mesh=...) for an ASSEMBLED scipy.sparse system (CSR, host pointers):
+ * pymatsolver.Pardiso(A) / SimPEG.SolverLU(A)        run.py:17-24, 246, 294, 343
+ * family: 0 cell-, 1 edge-, 2 face-based unknowns in the reference layout        */
+int cs_op_from_csr(cs_ctx* ctx, int family, long long n, long long nnz, const long long* indptr_h,
+                   const int* indices_h, const void* vals_h, int is_complex, cs_op** out);
 long long cs_op_size(cs_op* op);
 /* y = A(s) x for nvec vectors, shifts_h: 2 doubles (re, im) per vector.  K3 / K4. */
 int cs_op_apply(cs_op* op, const double* shifts_h, const void* x_d, void* y_d, int nvec, int is_complex);
