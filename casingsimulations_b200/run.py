@@ -35,6 +35,9 @@ class _Survey(object):
     nSrc = property(lambda self: len(self.srcList))
 
 
+Survey = _Survey
+
+
 class DipoleSrc(object):
     """dc.sources.Dipole([], a, b) stand-in (run.py:345-348): +I at the cell centre
     closest to a, -I at the one closest to b."""

@@ -1,0 +1,272 @@
+"""GPU tests through the reference-facing API: run.Simulation*, the SimPEG-style problem /
+survey / fields objects, the Solver(A) plugin, physics.casing_currents -- i.e. the reference's
+own tests (tests/test_cyl2D3D.py, tests/test_SimulationRun.py) re-targeted at the B200 path."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import casingsimulations_b200 as cs
+from casingsimulations_b200 import run, sources
+
+pytestmark = pytest.mark.gpu
+TOL, ZERO = 1e-4, 1e-7                                        # tests/test_cyl2D3D.py:18-19
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def get_src_wire(mesh, mp):
+    wire = np.zeros(mesh.vnF[2])
+    g = mesh.gridFz
+    wire[(g[:, 0] < mesh.hx.min()) & (g[:, 2] > mp.src_a[2]) & (g[:, 2] < mp.src_b[2])] = 1
+    return np.hstack([np.zeros(mesh.nFx), np.zeros(mesh.nFy), wire])
+
+
+@pytest.fixture(scope="module")
+def cyl2d3d():
+    """tests/test_cyl2D3D.py:81-170 verbatim in structure: Wholespace sigma = 0.1, 2-D vs 3-D
+    CylMeshGenerator, a vertical wire on the innermost Fz faces, 3 frequencies, Problem3D_h."""
+    mp = cs.model.Wholespace(src_a=np.r_[0.0, 0.0, -9.0], src_b=np.r_[0.0, 0.0, -1.0], freqs=np.r_[0.1, 1.0, 2.0], sigma_back=1e-1)
+    mesh2D = cs.CylMeshGenerator(modelParameters=mp, npadx=11, npadz=26, csz=2.0)
+    mesh3D = cs.CylMeshGenerator(modelParameters=mp, hy=np.ones(4) * 2 * np.pi / 4.0, csz=2.0, npadx=11, npadz=26)
+    out = {}
+    for tag, mg in (("2D", mesh2D), ("3D", mesh3D)):
+        wire = get_src_wire(mg.mesh, mp)
+        srcList = [sources.RawVec_e([], f, wire) for f in mp.freqs]
+        pp = cs.model.PhysicalProperties(mg, mp)
+        prb = run.Problem3D_h(mg.mesh, sigmaMap=pp.wires.sigma, muMap=pp.wires.mu, Solver=cs.Solver)
+        prb.pair(run.Survey(srcList))
+        out[tag] = (mg, srcList, prb, prb.fields(pp.model))
+        assert prb.info["relres"] <= 1e-10
+    return out
+
+
+def _jslice(mesh, j3D, q=0):
+    return cs.face3DthetaSlice(mesh, j3D, q)
+
+
+def test_cyl2D3D_symmetry_and_agreement(cyl2d3d):
+    mg2, src2, prb2, f2 = cyl2d3d["2D"]
+    mg3, src3, prb3, f3 = cyl2d3d["3D"]
+    m3 = mg3.mesh
+    for s2, s3 in zip(src2, src3):
+        j3, h3 = f3[s3, "j"], f3[s3, "h"]
+        j0, h0 = _jslice(m3, j3), cs.edge3DthetaSlice(m3, h3)
+        for q in range(1, m3.vnC[1]):
+            assert rel(_jslice(m3, j3, q), j0) < TOL                      # :202-231
+            assert rel(cs.edge3DthetaSlice(m3, h3, q), h0) < TOL          # :273-302
+        assert np.all(np.abs(j3[m3.nFx:m3.nFx + m3.nFy]) < ZERO)          # :233-251
+        assert np.all(np.abs(h3[:m3.nEx]) < ZERO) and np.all(np.abs(h3[m3.nEx + m3.nEy:]) < ZERO)   # :253-271
+        assert rel(j0, f2[s2, "j"]) < TOL                                 # :304-330
+        assert rel(h0, f2[s2, "h"][:, 0]) < TOL                           # :332-359
+
+
+def test_cyl2D3D_matches_oracle(cyl2d3d):
+    from oracle.cyl_oracle import MU_0, OracleCylMesh, OracleFDEM
+    mg2, src2, prb2, f2 = cyl2d3d["2D"]
+    m = mg2.mesh
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    P = OracleFDEM(om, 0.1 * np.ones(om.nC), MU_0 * np.ones(om.nC))
+    for s in src2:
+        h = P.solve(s.freq, np.real(s.s_e), refine=True)
+        assert rel(f2[s, "h"][:, 0], h) < 1e-6
+        assert rel(f2[s, "j"][:, 0], P.j_from(s.freq, h, np.real(s.s_e))) < 1e-6
+        assert rel(f2[s, "e"][:, 0], P.e_from(s.freq, h, np.real(s.s_e))) < 1e-6
+        assert rel(f2[s, "b"][:, 0], P.b_from(s.freq, h, np.real(s.s_e))) < 1e-6
+
+
+def _casing_sim(tmp, nth=1, physics="fdem", **mesh_kw):
+    mp = cs.model.CasingInHalfspace(directory=tmp, sigma_back=1e-1, src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0],
+                                    freqs=np.r_[0.5, 50.0], casing_l=100.0,
+                                    timeSteps=[(1e-5, 3), (1e-4, 3)])
+    hy = np.r_[2 * np.pi] if nth == 1 else np.ones(nth) * 2 * np.pi / nth
+    kw = dict(npadx=6, npadz=8, csz=5.0)
+    kw.update(mesh_kw)
+    mg = cs.CasingMeshGenerator(directory=tmp, modelParameters=mp, hy=hy, **kw)
+    if nth > 1:
+        th = mg.mesh.vectorCCy[1]
+        mp.src_a, mp.src_b = np.r_[0.0, th, 0.0], np.r_[1000.0, th, 0.0]
+    return mp, mg
+
+
+def test_simulation_fdem_run_and_save(tmp_path):
+    """tests/test_SimulationRun.py:38-81: run each source, the saved fields.npy equals fields[:, 'h']"""
+    tmp = str(tmp_path / "sim2D")
+    mp, mg = _casing_sim(tmp)
+    from oracle.cyl_oracle import OracleCylMesh, OracleFDEM
+    m = mg.mesh
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    P = OracleFDEM(om, mp.sigma(m), mp.mu(m))
+    for klass, a, b in ((sources.TopCasingSrc, np.r_[0.0, 0.0, 0.0], np.r_[1000.0, 0.0, 0.0]),
+                        (sources.DownHoleCasingSrc, np.r_[0.0, 0.0, -50.0], np.r_[500.0, 0.0, 0.0]),
+                        (sources.DownHoleTerminatingSrc, np.r_[0.0, 0.0, -50.0], np.r_[500.0, 0.0, 0.0])):
+        src = klass(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a.copy(), src_b=b.copy())
+        sim = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src)
+        fields = sim.run()
+        loaded = np.load("/".join([tmp, "fields.npy"]))
+        assert np.all(fields[:, "h"] == loaded)                                        # :51
+        assert os.path.exists(os.path.join(tmp, "simulationParameters.json"))
+        assert sim.prob.info["relres"] <= 1e-10
+        for k, s in enumerate(sim.survey.srcList):
+            h = P.solve(s.freq, np.real(s.s_e), refine=True)
+            assert rel(fields[s, "h"][:, 0], h) < 1e-6, klass.__name__
+        assert sim.fields() is fields
+        sim.prob.clean()
+
+
+def test_simulation_dc_and_casing_currents(tmp_path):
+    tmp = str(tmp_path / "simDC")
+    mp, mg = _casing_sim(tmp)
+    m = mg.mesh
+    a = np.array([[0.05125, 0.0, -2.5]])
+    b = np.array([[1000.0, 0.0, -2.5]])
+    sim = run.SimulationDC(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a, src_b=b)
+    f = sim.run()
+    assert np.array_equal(np.load(os.path.join(tmp, "fieldsDC.npy")), f[:, "phiSolution"])
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, casing_currents
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    P = OracleDC(om, mp.sigma(m))
+    phi = P.fields(a, b, refine=True)
+    assert rel(f[:, "phi"], phi) < 5e-6
+    j = f[:, "j"]
+    assert rel(j, P.j(phi)) < 1e-4
+    cur = cs.casing_currents(j, m, mp)
+    ref = casing_currents(P.j(phi), om, mp.casing_a, mp.casing_b, mp.casing_z)
+    assert np.array_equal(cur["z"][0], ref["z"][0]) and rel(cur["z"][1][:, 0], ref["z"][1]) < 1e-4
+    assert rel(cur["x"][1][:, 0], ref["x"][1]) < 1e-4
+    assert 0.5 < -cur["z"][1][-1, 0] <= 1.0 + 1e-6                     # ~1 A enters the casing top
+    z, q = cs.casing_charges(f[:, "charge"][:, 0], m, mp)
+    assert len(z) == len(q)
+    sim.prob.clean()
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_simulation_tdem(tmp_path, nth):
+    tmp = str(tmp_path / "simT")
+    mp, mg = _casing_sim(tmp, nth, npadx=4, npadz=5, csz=10.0)
+    src = sources.TopCasingSrc(directory=tmp, modelParameters=mp, meshGenerator=mg)
+    sim = run.SimulationTDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src)
+    f = sim.run()
+    jsol = f[:, "jSolution"]
+    assert jsol.shape == (mg.mesh.nF, 7)
+    assert np.array_equal(np.load(os.path.join(tmp, "fields.npy")), jsol)
+    from oracle.cyl_oracle import OracleCylMesh, OracleTDEM
+    m = mg.mesh
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    T = OracleTDEM(om, mp.sigma(m), mp.mu(m), mp.timeSteps)
+    Flu, Fref = T.fields(src.s_e), T.fields(src.s_e, refine=True)
+    tol = max(1e-6, 10 * rel(Flu, Fref))
+    assert rel(jsol, Fref) < tol, (rel(jsol, Fref), tol)
+    assert rel(f[:, "j", 3], Fref[:, 3]) < tol
+    sim.prob.clean()
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_solver_plugin_protocol(nth):
+    """Ainv = Solver(A, **opts); x = Ainv * rhs; Ainv.clean()  (run.py:246,294,343) with assembled matrices"""
+    from conftest import CASING, small_casing_mesh
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, OracleFDEM, paint_casing_in_halfspace, solve_refined
+    hx, hy, hz, z0 = small_casing_mesh(nth)
+    om = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    sig, mu = paint_casing_in_halfspace(om, **CASING)
+    mesh = cs.CylMesh([hx, hy, hz], x0=[0, 0, z0])
+    # real SPD, multi-RHS (DC)
+    Pd = OracleDC(om, sig)
+    A = Pd.getA()
+    q = Pd.getRHS(np.array([[0.03, 0.0, -0.25], [0.03, 0.0, -1.2]]), np.array([[2.0, 0.0, -0.25], [1.0, 0.0, -0.25]]))
+    Ainv = cs.Solver(A, mesh=mesh)
+    x = Ainv * q
+    assert x.shape == q.shape
+    for c in range(2):
+        assert rel(x[:, c], solve_refined(A, q[:, c])[0]) < 5e-6
+    x1 = Ainv * q[:, 0]
+    assert x1.shape == (om.nC,) and rel(x1, x[:, 0]) < 1e-9
+    with pytest.raises(TypeError):
+        Ainv * [1.0, 2.0]
+    Ainv.clean()
+    # complex symmetric (FDEM-h)
+    P = OracleFDEM(om, sig, mu, "h")
+    g = om.gridFz
+    w = np.zeros(om.nFz)
+    sel = (g[:, 0] < om.hx.min()) & (g[:, 2] > -2.6) & (g[:, 2] < 0.1)
+    if nth > 1:
+        sel &= g[:, 1] < om.hy[0]
+    w[sel] = 1.0
+    se = np.r_[np.zeros(om.nFx + om.nFy), w] / om.area
+    Ah, rhs = P.getA(100.0), P.getRHS(100.0, se)
+    Ainv = cs.Solver(Ah, mesh=mesh)
+    h = Ainv.solve(rhs)
+    d = np.sqrt(np.abs(Ah.diagonal()))
+    assert np.linalg.norm((Ah @ h - rhs) / d) <= 1e-10 * np.linalg.norm(rhs / d)
+    jt = P.j_from(100.0, solve_refined(Ah, rhs)[0], se)
+    assert rel(P.j_from(100.0, h, se), jt) < 1e-4
+    Ainv.clean()
+    with pytest.raises(cs._lib.CasingB200Error):
+        import scipy.sparse as sp
+        cs.Solver(sp.identity(7, format="csr"), mesh=mesh)
+
+
+def test_full_size_c1_dc():
+    """BASELINE config 1 at full size: 109 x 1 x 717 (78 153 cells), a on the casing wall top, b at 1 km"""
+    mp = cs.model.CasingInHalfspace(src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0])
+    mg = cs.CasingMeshGenerator(modelParameters=mp, npadx=10, npadz=20, csz=1.5)
+    m = mg.mesh
+    a, b = np.array([[0.05125, 0.0, -0.75]]), np.array([[1000.0, 0.0, -0.75]])
+    sim = run.SimulationDC(directory="/tmp/cs_b200_c1", modelParameters=mp, meshGenerator=mg, src_a=a, src_b=b)
+    f = sim.run(save=False)
+    info = sim.prob.info
+    print("C1 info", info)
+    assert info["relres"] <= 1e-10
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    P = OracleDC(om, mp.sigma(m))
+    phi_lu, phi = P.fields(a, b), P.fields(a, b, refine=True)
+    print("C1 gpu vs truth", rel(f[:, "phi"], phi), "splu vs truth", rel(phi_lu, phi))
+    assert rel(f[:, "phi"], phi) < max(5e-6, 10 * rel(phi_lu, phi))
+    cur = cs.casing_currents(f[:, "j"], m, mp)
+    assert 0.9 < -cur["z"][1][-1, 0] <= 1.0 + 1e-6
+    sim.prob.clean()
+    shutil.rmtree("/tmp/cs_b200_c1", ignore_errors=True)
+
+
+def test_full_size_c3_dc_3d_properties():
+    """BASELINE config 3 at full size (109 x 32 x 1394 = 4.86 M cells): the oracle cannot factor this
+    on the host, so parity goes through size-independent properties: Krylov residual, reciprocity
+    phi_a(b) = phi_b(a) of the symmetric operator, and linearity."""
+    import torch
+    from casingsimulations_b200 import _lib
+    mp = cs.model.CasingInHalfspace(src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0], mur_casing=100.0)
+    mg = cs.CasingMeshGenerator(modelParameters=mp, npadx=10, npadz=25, csz=0.75, hy=np.ones(32) * 2 * np.pi / 32)
+    m = mg.mesh
+    assert m.nC == 4862272
+    ctx = _lib.Context(0)
+    ctx.set_mesh(m.hx, m.hy, m.hz, m.x0[2])
+    ctx.paint(mp.paint_params())
+    from casingsimulations_b200.mesh import closestPoints
+    ia = closestPoints(m, np.r_[0.05125, 33 * np.pi / 32, -0.375])[0]
+    ib = closestPoints(m, np.r_[1000.0, 17 * np.pi / 32, -0.375])[0]
+    q = torch.zeros((2, m.nC), dtype=torch.float64, device=ctx.device)
+    q[0, ia], q[0, ib] = 1.0, -1.0            # the C3 dipole
+    q[1, ib] = 1.0                            # unit source at b
+    phi = ctx.solve_dc(q)
+    print("C3 info", ctx.info)
+    assert ctx.info["relres"] <= 1e-10
+    qa = torch.zeros((1, m.nC), dtype=torch.float64, device=ctx.device)
+    qa[0, ia] = 1.0
+    phia = ctx.solve_dc(qa)
+    # reciprocity: potential at a due to a source at b == potential at b due to a source at a
+    assert abs(float(phi[1, ia]) - float(phia[0, ib])) <= 1e-6 * abs(float(phia[0, ib]))
+    # linearity: dipole = unit(a) - unit(b)
+    lin = phia[0] - phi[1]
+    assert float(torch.linalg.norm(lin - phi[0]) / torch.linalg.norm(phi[0])) < 1e-6
+    ctx.close()

@@ -1,0 +1,161 @@
+"""Pins the CPU oracle (oracle/cyl_oracle.py): the reference ships no golden vectors, so the
+acceptance checks of SURVEY.md section 8c are (i) the reference's own 2-D / 3-D consistency test
+(tests/test_cyl2D3D.py:202-359) re-run on the oracle, (ii) discrete identities, (iii) analytic
+solutions, plus the committed golden fixtures that guard against regressions."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASING, small_casing_mesh
+from oracle.cyl_oracle import (MU_0, OracleCylMesh, OracleDC, OracleFDEM, OracleTDEM, casing_currents, mesh_tensor,
+                               paint_casing_in_halfspace, solve_refined)
+
+TOL, ZERO = 1e-4, 1e-7          # tests/test_cyl2D3D.py:18-19
+
+
+def test_mesh_tensor():
+    assert np.allclose(mesh_tensor([(2.0, 3)]), [2, 2, 2])
+    assert np.allclose(mesh_tensor([(1.0, 2, 2.0)]), [2, 4])
+    assert np.allclose(mesh_tensor([(1.0, 2, -2.0)]), [4, 2])
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_discrete_identities(nth):
+    hx, hy, hz, z0 = small_casing_mesh(nth)
+    m = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    assert len(m.area) == m.nF and len(m.edge) == m.nE and len(m.vol) == m.nC
+    assert abs(m.faceDiv @ m.edgeCurl).max() < 1e-10 * abs(m.edgeCurl).max()       # div curl = 0
+    if nth > 1:
+        assert abs(m.edgeCurl @ m.nodalGrad).max() < 1e-10 * abs(m.edgeCurl).max()  # curl grad = 0
+        assert m.gridEz.shape[0] == m.nEz
+    sig, mu = paint_casing_in_halfspace(m, **CASING)
+    A = OracleDC(m, sig).getA()
+    assert abs(A - A.T).max() < 1e-12 * abs(A).max()
+    Ah = OracleFDEM(m, sig, mu, "h").getA(10.0)
+    assert abs(Ah - Ah.T).max() < 1e-12 * abs(Ah).max()                             # complex symmetric
+    # volumes / areas: total volume and the outer cylinder surface
+    R, H = hx.sum(), hz.sum()
+    assert np.isclose(m.vol.sum(), np.pi * R ** 2 * H)
+    outer = m.area[:m.nFx].reshape(m.vnFx, order="F")[-1].sum()
+    assert np.isclose(outer, 2 * np.pi * R * H)
+
+
+def _ref_test_mesh(nth):
+    """tests/test_cyl2D3D.py:87-105: CylMeshGenerator(csz=2, npadx=11, npadz=26), src z in [-9, -1]"""
+    hx = mesh_tensor([(25.0, int(np.ceil(1000 / 25.0) + 10)), (25.0, 11, 1.5)])
+    ncz = int(np.ceil(8.0 / 2.0)) + 5 + 5
+    hz = mesh_tensor([(2.0, 26, -1.5), (2.0, ncz), (2.0, 26, 1.5)])
+    hy = np.r_[2 * np.pi] if nth == 1 else np.ones(nth) * 2 * np.pi / nth
+    return OracleCylMesh([hx, hy, hz], np.r_[0, 0, -np.sum(hz[:26 + ncz - 5])])
+
+
+def _wire(m):
+    g = m.gridFz
+    w = np.zeros(m.nFz)
+    w[(g[:, 0] < m.hx.min()) & (g[:, 2] > -9.0) & (g[:, 2] < -1.0)] = 1
+    return np.r_[np.zeros(m.nFx + m.nFy), w]
+
+
+def test_reference_cyl2D3D_consistency():
+    """the reference's six assertions, at its own sizes (4 026 / 16 104 cells), one frequency"""
+    m2, m3 = _ref_test_mesh(1), _ref_test_mesh(4)
+    assert (m2.nC, m2.nF, m2.nE) == (4026, 8113, 4087) and (m3.nC, m3.nF, m3.nE) == (16104, 48556, 48866)
+    freq = 1.0
+    P2 = OracleFDEM(m2, 0.1 * np.ones(m2.nC), MU_0 * np.ones(m2.nC))
+    P3 = OracleFDEM(m3, 0.1 * np.ones(m3.nC), MU_0 * np.ones(m3.nC))
+    h2, h3 = P2.solve(freq, _wire(m2)), P3.solve(freq, _wire(m3))
+    j2, j3 = P2.j_from(freq, h2, _wire(m2)), P3.j_from(freq, h3, _wire(m3))
+    h3y = h3[m3.nEx:m3.nEx + m3.nEy].reshape(m3.vnEy, order="F")
+    j3x = j3[:m3.nFx].reshape(m3.vnFx, order="F")
+    j3z = j3[m3.nFx + m3.nFy:].reshape(m3.vnFz, order="F")
+
+    def jslice(q):
+        return np.r_[j3x[:, q, :].ravel(order="F"), j3z[:, q, :].ravel(order="F")]
+    for q in range(1, 4):                                                   # :202-231, :273-302
+        assert np.linalg.norm(jslice(0) - jslice(q)) / np.linalg.norm(jslice(0)) < TOL
+        assert np.linalg.norm(h3y[:, 0] - h3y[:, q]) / np.linalg.norm(h3y[:, 0]) < TOL
+    assert np.all(np.abs(j3[m3.nFx:m3.nFx + m3.nFy]) < ZERO)               # :233-251 (magnitudes)
+    assert np.all(np.abs(h3[:m3.nEx]) < ZERO) and np.all(np.abs(h3[m3.nEx + m3.nEy:]) < ZERO)   # :253-271
+    assert np.linalg.norm(jslice(0) - j2) / np.linalg.norm(j2) < TOL       # :304-330
+    assert np.linalg.norm(h3y[:, 0].ravel(order="F") - h2) / np.linalg.norm(h2) < TOL   # :332-359
+
+
+def test_dc_point_source_analytic():
+    """phi = I / (4 pi sigma) (1/Ra - 1/Rb) away from the electrodes and the boundary"""
+    hx = mesh_tensor([(1.0, 40), (1.0, 18, 1.4)])
+    hz = mesh_tensor([(1.0, 18, -1.4), (1.0, 80), (1.0, 18, 1.4)])
+    m = OracleCylMesh([hx, np.r_[2 * np.pi], hz], [0, 0, -hz.sum() / 2])
+    sigma = 0.1
+    P = OracleDC(m, sigma * np.ones(m.nC))
+    a, b = np.array([[0.0, 0.0, 10.5]]), np.array([[0.0, 0.0, -10.5]])
+    phi = P.fields(a, b)[:, 0]
+    cc = m.gridCC
+    ia, ib = np.argmax(P.getRHS(a, b)[:, 0]), np.argmin(P.getRHS(a, b)[:, 0])
+    Ra = np.sqrt(cc[:, 0] ** 2 + (cc[:, 2] - cc[ia, 2]) ** 2)
+    Rb = np.sqrt(cc[:, 0] ** 2 + (cc[:, 2] - cc[ib, 2]) ** 2)
+    ana = 1.0 / (4 * np.pi * sigma) * (1 / Ra - 1 / Rb)
+    sel = (Ra > 6) & (Rb > 6) & (cc[:, 0] < 30) & (np.abs(cc[:, 2]) < 30)
+    assert np.linalg.norm(phi[sel] - ana[sel]) / np.linalg.norm(ana[sel]) < 0.03
+
+
+def test_tdem_initial_state_and_decay():
+    hx, hy, hz, z0 = small_casing_mesh(1)
+    m = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    sig, mu = paint_casing_in_halfspace(m, **CASING)
+    g = m.gridFz
+    w = np.zeros(m.nFz)
+    w[(g[:, 0] < m.hx.min()) & (g[:, 2] > -2.6) & (g[:, 2] < 0.1)] = 1.0
+    se = np.r_[np.zeros(m.nFx), w] / m.area
+    T = OracleTDEM(m, sig, mu, [(1e-5, 4), (1e-3, 4)], ground_first_cell=False)
+    F = T.fields(se, refine=True)
+    # galvanic DC state: D (j0 + s_e) = 0  
+    div0 = T.Dt @ (F[:, 0] + se)
+    assert np.linalg.norm(div0) < 1e-6 * np.linalg.norm(T.Dt @ se)      # raw 2-norm floor of the 1e13-contrast system
+    en = [float(F[:, t] @ (T.MfRho @ F[:, t])) for t in range(F.shape[1])]
+    assert all(en[t + 1] <= en[t] * (1 + 1e-9) for t in range(1, len(en) - 1))      # ohmic energy decays
+
+
+def test_casing_currents_top_source():
+    """I_z just below a source grounded on the casing top is ~1 A and leaks off monotonically"""
+    hx, hy, hz, z0 = small_casing_mesh(1)
+    m = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    sig, mu = paint_casing_in_halfspace(m, **CASING)
+    P = OracleDC(m, sig)
+    a, b = np.array([[0.03, 0.0, -0.25]]), np.array([[4.0, 0.0, -0.25]])
+    phi = P.fields(a, b, refine=True)
+    j = P.j(phi)
+    cur = casing_currents(j, m, CASING["casing_a"], CASING["casing_b"], CASING["casing_z"])
+    iz = -cur["z"][1]                    # downward current
+    assert 0.5 < iz[-1] <= 1.0 + 1e-9
+    assert np.all(np.diff(iz) >= -1e-9)  # grows towards the top = leaks off downwards
+
+
+def test_refined_solve_beats_plain_lu():
+    hx, hy, hz, z0 = small_casing_mesh(1)
+    m = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    sig, mu = paint_casing_in_halfspace(m, **CASING)
+    P = OracleDC(m, sig)
+    A = P.getA()
+    q = P.getRHS(np.array([[0.03, 0, -0.25]]), np.array([[2.0, 0, -0.25]]))[:, 0]
+    x, x0 = solve_refined(A, q)
+    d = np.sqrt(A.diagonal())
+    r, r0 = (q - A @ x) / d, (q - A @ x0) / d
+    assert np.linalg.norm(r) <= np.linalg.norm(r0) * 1.0001
+
+
+def test_golden_fixture_matches_oracle():
+    p = os.path.join(os.path.dirname(__file__), "golden", "small_casing.npz")
+    g = np.load(p)
+    for nth in (1, 4):
+        hx, hy, hz, z0 = small_casing_mesh(nth)
+        m = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+        sig, mu = paint_casing_in_halfspace(m, **CASING)
+        tag = "n%d_" % nth
+        assert np.array_equal(g[tag + "sigma"], sig) and np.array_equal(g[tag + "mu"], mu)
+        assert np.allclose(g[tag + "MfRho"], m.getFaceInnerProduct(sig, invProp=True).diagonal(), rtol=1e-14)
+        assert np.allclose(g[tag + "MeMu"], m.getEdgeInnerProduct(mu).diagonal(), rtol=1e-14)
+        if nth == 1:
+            P = OracleFDEM(m, sig, mu, "h")
+            h = P.solve(100.0, g[tag + "s_e"], refine=True)
+            assert np.linalg.norm(h - g[tag + "fdem_h_100Hz"]) / np.linalg.norm(h) < 1e-9
