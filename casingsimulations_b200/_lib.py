@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcasing_b200.so")
 
 KIND_DC, KIND_DC_GROUNDED, KIND_EDGE_H, KIND_EDGE_E, KIND_FACE_J, KIND_FACE_B = range(6)
 INFO_LEN = 16
-INFO_NAMES = ["iters", "relres", "ms_assemble", "ms_factor", "ms_solve", "n_apply", "n_launch", "bytes", "converged"]
+INFO_NAMES = ["iters", "relres", "ms_assemble", "ms_factor", "ms_solve", "n_apply", "n_launch", "bytes", "converged", "backward_err"]
 
 _lib = None
 

@@ -38,7 +38,7 @@ int launch_csr_spmv(long long n, const long long* indptr, const int* indices, co
 // out[sys] = sum conj?(a) * b over n entries; results to dots_d[2*sys..]
 // optional weights w[wsel[sys]*n + t] (real, >= 0) give the diagonally scaled norms used by the convergence tests
 int launch_dot(const void* a, const void* b, long long n, int nsys, bool cplx_vec, bool conj_a, double* dots_d, cudaStream_t st,
-               const double* w = nullptr, const int* wsel = nullptr);
+               const double* w = nullptr, const int* wsel = nullptr, int winv = 0);
 // y = a*x + b*y with per-system complex scalars (host arrays of 2 doubles per system)
 int launch_axpby(void* y, const void* x, long long n, int nsys, bool cplx_vec, const double* a_d, const double* b_d, cudaStream_t st);
 // z = x .* w (w real, shared by all systems), optionally reciprocal

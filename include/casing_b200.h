@@ -31,7 +31,7 @@ typedef struct cs_op cs_op;
 
 /* info_h layout (doubles) returned by the solve calls */
 #define CS_INFO_ITERS 0      /* Krylov iterations (max over systems)          */
-#define CS_INFO_RELRES 1     /* max over systems of ||b - A x|| / ||b||       */
+#define CS_INFO_RELRES 1     /* max over systems of ||b - A x|| / ||b|| in the Jacobi-scaled norm (r_i / sqrt|a_ii|) */
 #define CS_INFO_MS_ASSEMBLE 2
 #define CS_INFO_MS_FACTOR 3
 #define CS_INFO_MS_SOLVE 4
@@ -39,6 +39,7 @@ typedef struct cs_op cs_op;
 #define CS_INFO_N_LAUNCH 6   /* kernels launched by this call                 */
 #define CS_INFO_BYTES 7      /* algorithmic bytes moved by the stencil applies */
 #define CS_INFO_CONVERGED 8
+#define CS_INFO_BACKWARD_ERR 9 /* set when relres stalls above rtol at the fp64 floor: ||r~||/(8||x~||+||b~||) <= 1e-14 is accepted */
 #define CS_INFO_LEN 16
 
 const char* cs_last_error(void);

