@@ -124,7 +124,9 @@ class Op(object):
         self.ctx, self.kind = ctx, kind
         if handle is None:
             handle = ctypes.c_void_p()
+            ctx._enter()
             check(ctx.lib.cs_op_get(ctx.h, kind, ctypes.byref(handle)))
+            ctx._exit()
         self.h = handle
         self.n = int(ctx.lib.cs_op_size(handle))
 
@@ -139,7 +141,9 @@ class Op(object):
             s = np.atleast_1d(np.asarray(shifts, dtype=complex))
             s = np.broadcast_to(s, (nvec,))
             sh[0::2], sh[1::2] = s.real, s.imag
+        self.ctx._enter()
         check(self.ctx.lib.cs_op_apply(self.h, _dptr(sh), _tptr(x2), _tptr(y), nvec, int(x2.is_complex())))
+        self.ctx._exit()
         return y.reshape(x.shape)
 
     def apply_timed(self, x, shift=0.0, reps=20):
@@ -150,8 +154,10 @@ class Op(object):
         s = complex(shift)
         sh = np.tile(np.array([s.real, s.imag]), x2.shape[0])
         ms = ctypes.c_double(0.0)
+        self.ctx._enter()
         check(self.ctx.lib.cs_op_apply_timed(self.h, _dptr(sh), _tptr(x2), _tptr(y), x2.shape[0], int(x2.is_complex()),
                                              int(reps), ctypes.byref(ms)))
+        self.ctx._exit()
         return ms.value
 
     def factor(self, shifts=(0.0,)):
@@ -159,7 +165,9 @@ class Op(object):
         sh = np.zeros(2 * len(s))
         sh[0::2], sh[1::2] = s.real, s.imag
         cplx = int(np.any(s.imag != 0))
+        self.ctx._enter()
         check(self.ctx.lib.cs_op_factor(self.h, _dptr(sh), len(s), cplx))
+        self.ctx._exit()
         self._complex_shift = bool(cplx)
 
     def solve(self, rhs, shift_of_vec=None, rtol=1e-10, maxit=50):
@@ -171,14 +179,18 @@ class Op(object):
         sov = None
         if shift_of_vec is not None:
             sov = np.ascontiguousarray(shift_of_vec, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+        self.ctx._enter()
         rc = self.ctx.lib.cs_op_solve(self.h, _tptr(r2), _tptr(x), nvec, sov, int(r2.is_complex()), rtol, maxit,
                                       info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self.ctx._exit()
         self.info = dict(zip(INFO_NAMES, info))
         check(rc)
         return x.reshape(rhs.shape)
 
     def clean(self):
+        self.ctx._enter()
         check(self.ctx.lib.cs_op_clean(self.h))
+        self.ctx._exit()
 
 
 class Context(object):
@@ -190,10 +202,29 @@ class Context(object):
         torch = _torch()
         self.lib = load_library()
         self.device = torch.device("cuda", device)
+        # The library runs on ONE explicit stream.  Torch allocations / copies made by the
+        # caller live on torch's current stream, so every wrapper orders the two streams
+        # (wait_stream in, wait_stream out) -- see _enter / _exit.
+        if stream is None:
+            self.tstream = torch.cuda.Stream(device=self.device)
+        else:
+            self.tstream = torch.cuda.ExternalStream(stream, device=self.device)
         h = ctypes.c_void_p()
-        check(self.lib.cs_ctx_create(device, ctypes.c_void_p(stream) if stream else None, ctypes.byref(h)))
+        check(self.lib.cs_ctx_create(device, ctypes.c_void_p(self.tstream.cuda_stream), ctypes.byref(h)))
         self.h = h
         self.info = {}
+
+    def _enter(self):
+        torch = _torch()
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.tstream.cuda_stream:
+            self.tstream.wait_stream(cur)
+
+    def _exit(self):
+        torch = _torch()
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.tstream.cuda_stream:
+            cur.wait_stream(self.tstream)
 
     def close(self):
         if getattr(self, "h", None):
@@ -207,7 +238,9 @@ class Context(object):
             pass
 
     def sync(self):
+        self._enter()
         check(self.lib.cs_ctx_sync(self.h))
+        self._exit()
 
     def launch_count(self):
         return int(self.lib.cs_launch_count())
@@ -216,8 +249,10 @@ class Context(object):
     def set_mesh(self, hx, hy, hz, z0, axis_weight_edge=1.0, axis_weight_face=0.5):
         hx, hy, hz = [np.ascontiguousarray(np.atleast_1d(h), dtype=np.float64) for h in (hx, hy, hz)]
         self.nx, self.nth, self.nz = len(hx), len(hy), len(hz)
+        self._enter()
         check(self.lib.cs_mesh_set(self.h, self.nx, self.nth, self.nz, _dptr(hx), _dptr(hy), _dptr(hz), float(z0),
                                    float(axis_weight_edge), float(axis_weight_face)))
+        self._exit()
         cnt = (ctypes.c_longlong * 7)()
         check(self.lib.cs_mesh_counts(self.h, cnt))
         self.nC, self.nFx, self.nFy, self.nFz, self.nEx, self.nEy, self.nEz = [int(v) for v in cnt]
@@ -239,26 +274,34 @@ class Context(object):
     def paint(self, params):
         """params: the 18 doubles of k_paint.  Returns (sigma, mu) device tensors."""
         sigma, mu = self.empty(self.nC), self.empty(self.nC)
+        self._enter()
         check(self.lib.cs_model_paint(self.h, _dptr(np.asarray(params, dtype=np.float64)), _tptr(sigma), _tptr(mu)))
+        self._exit()
         return sigma, mu
 
     def set_model(self, sigma, mu):
         sigma = sigma if hasattr(sigma, "data_ptr") else self.to_device(sigma, False)
         mu = mu if hasattr(mu, "data_ptr") else self.to_device(mu, False)
         assert sigma.numel() == self.nC and mu.numel() == self.nC
+        self._enter()
         check(self.lib.cs_model_set(self.h, _tptr(sigma), _tptr(mu)))
+        self._exit()
 
     # -- building blocks ----------------------------------------------------
     def face_inner_product(self, prop=None, invProp=False, invMat=False):
         out = self.empty(self.nF)
         p = ctypes.c_void_p(0) if prop is None else _tptr(prop)
+        self._enter()
         check(self.lib.cs_face_inner_product(self.h, p, int(invProp), int(invMat), _tptr(out)))
+        self._exit()
         return out
 
     def edge_inner_product(self, prop=None, invProp=False, invMat=False):
         out = self.empty(self.nE)
         p = ctypes.c_void_p(0) if prop is None else _tptr(prop)
+        self._enter()
         check(self.lib.cs_edge_inner_product(self.h, p, int(invProp), int(invMat), _tptr(out)))
+        self._exit()
         return out
 
     def _unary(self, fn, x, nin, nout):
@@ -283,7 +326,9 @@ class Context(object):
         if plan:
             return Op(self, kind)
         h = ctypes.c_void_p()
+        self._enter()
         check(self.lib.cs_op_get_noplan(self.h, kind, ctypes.byref(h)))
+        self._exit()
         return Op(self, kind, handle=h)
 
     def op_from_csr(self, A, family):
@@ -294,10 +339,12 @@ class Context(object):
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         vals = np.ascontiguousarray(A.data, dtype=np.complex128 if cplx else np.float64)
         h = ctypes.c_void_p()
+        self._enter()
         check(self.lib.cs_op_from_csr(self.h, family, A.shape[0], A.nnz,
                                       indptr.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
                                       indices.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
                                       vals.ctypes.data_as(ctypes.c_void_p), int(cplx), ctypes.byref(h)))
+        self._exit()
         return Op(self, -1, handle=h)
 
     # -- physics-level drivers ----------------------------------------------
@@ -310,8 +357,10 @@ class Context(object):
         q2 = q.reshape(-1, self.nC).contiguous()
         phi = torch.empty_like(q2)
         info = np.zeros(INFO_LEN)
+        self._enter()
         rc = self.lib.cs_solve_dc(self.h, _tptr(q2), _tptr(phi), q2.shape[0], rtol, maxit,
                                   info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self._exit()
         self._info(info)
         check(rc)
         return phi.reshape(q.shape)
@@ -322,8 +371,10 @@ class Context(object):
         n = self.nE if form == "h" else self.nF
         u = self.empty(n, True, cols=len(freqs))
         info = np.zeros(INFO_LEN)
+        self._enter()
         rc = self.lib.cs_solve_fdem(self.h, ord(form), _dptr(freqs), len(freqs), _tptr(s_e.contiguous()), _tptr(u),
                                     rtol, maxit, info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self._exit()
         self._info(info)
         check(rc)
         return u
@@ -332,8 +383,10 @@ class Context(object):
         dts = np.ascontiguousarray(dts, dtype=np.float64)
         out = self.empty(self.nF, False, cols=len(dts) + 1)
         info = np.zeros(INFO_LEN)
+        self._enter()
         rc = self.lib.cs_tdem_run(self.h, ord(form), _dptr(dts), len(dts), _tptr(s_e.contiguous()), _tptr(out),
                                   rtol, maxit, info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        self._exit()
         self._info(info)
         check(rc)
         return out
@@ -341,8 +394,10 @@ class Context(object):
     def fields_fdem(self, form, which, freq, u, s_e):
         n = self.nF if which in ("j", "e") else self.nE
         out = self.empty(n, True)
+        self._enter()
         check(self.lib.cs_fields_fdem(self.h, ord(form), ord(which), float(freq), _tptr(u.contiguous()),
                                       _tptr(s_e.contiguous()), _tptr(out)))
+        self._exit()
         return out
 
     def fields_dc(self, which, phi):
@@ -350,19 +405,25 @@ class Context(object):
         n = self.nC if which == "charge" else self.nF
         out = self.empty(n, False, cols=phi2.shape[0])
         code = {"j": "j", "e": "e", "charge": "c"}[which]
+        self._enter()
         check(self.lib.cs_fields_dc(self.h, ord(code), _tptr(phi2), _tptr(out), phi2.shape[0]))
+        self._exit()
         return out
 
     def casing_currents(self, j, casing_a, casing_b, casing_z):
         j = j.contiguous()
         ix = self.empty(self.nz, j.is_complex())
         iz = self.empty(self.nz + 1, j.is_complex())
+        self._enter()
         check(self.lib.cs_casing_currents(self.h, _tptr(j), int(j.is_complex()), casing_a, casing_b,
                                           float(casing_z[0]), float(casing_z[1]), _tptr(ix), _tptr(iz)))
+        self._exit()
         return ix, iz
 
     def casing_charges(self, charge, casing_b, casing_z):
         out = self.empty(self.nz)
+        self._enter()
         check(self.lib.cs_casing_charges(self.h, _tptr(charge.contiguous()), casing_b, float(casing_z[0]),
                                          float(casing_z[1]), _tptr(out)))
+        self._exit()
         return out

@@ -19,18 +19,52 @@ using namespace cs;
 typedef std::complex<double> zc;
 
 // ------------------------------------------------------------------ structs --
+// Device-memory pool of a context: the multi-GB factor / band buffers are recycled when an
+// operator is dropped and rebuilt (every fields() call re-assembles, like the reference),
+// instead of paying cudaFree + cudaMalloc of 10+ GB each time.
+struct Pool {
+    std::vector<std::pair<void*, size_t>> free_;
+    void* get(size_t need) {
+        int best = -1;
+        for (int i = 0; i < (int)free_.size(); ++i)
+            if (free_[i].second >= need && free_[i].second <= 2 * need + (1 << 20) && (best < 0 || free_[i].second < free_[best].second)) best = i;
+        if (best >= 0) { void* p = free_[best].first; last_bytes = free_[best].second; free_.erase(free_.begin() + best); return p; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, need) != cudaSuccess) {
+            clear();                                   // release cached blocks and retry once
+            cudaGetLastError();
+            if (cudaMalloc(&p, need) != cudaSuccess) return nullptr;
+        }
+        last_bytes = need;
+        return p;
+    }
+    void put(void* p, size_t bytes) { if (p) free_.push_back({p, bytes}); }
+    void clear() { for (auto& b : free_) cudaFree(b.first); free_.clear(); }
+    size_t total() const { size_t t = 0; for (auto& b : free_) t += b.second; return t; }
+    size_t last_bytes = 0;
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    Pool* pool = nullptr;
     int ensure(size_t need) {
         if (need <= bytes) return CS_OK;
-        if (p) cudaFree(p);
-        p = nullptr; bytes = 0;
+        release();
+        if (pool) {
+            p = pool->get(need);
+            CS_CHECK(p, "out of device memory");
+            bytes = pool->last_bytes;
+            return CS_OK;
+        }
         CS_CUDA(cudaMalloc(&p, need));
         bytes = need;
         return CS_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() {
+        if (p) { if (pool) pool->put(p, bytes); else cudaFree(p); }
+        p = nullptr; bytes = 0;
+    }
 };
 
 struct cs_op {
@@ -43,6 +77,7 @@ struct cs_op {
     bool is_csr = false, csr_cplx = false;
     long long* csr_indptr = nullptr; int* csr_indices = nullptr; void* csr_vals = nullptr; long long csr_nnz = 0;
     BandPlan bp;
+    DevBuf kband;                 // storage behind bp.Kband (pooled)
     DevBuf LU, wts;               // wts: [nshift][n] = 1/|diag A(s)|, the norm of the convergence tests
     bool lu_cplx = false;
     std::vector<zc> shifts;
@@ -61,6 +96,7 @@ struct cs_ctx {
     double *sigma = nullptr, *mu = nullptr;
     std::map<int, cs_op*> ops;
     DevBuf work, scal, modes, tmp1, tmp2;
+    Pool pool;
     double* pin = nullptr;         // pinned host scratch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -70,7 +106,8 @@ static void op_free(cs_op* op) {
     cudaFree(op->w1); cudaFree(op->w2);
     cudaFree(op->csr_indptr); cudaFree(op->csr_indices); cudaFree(op->csr_vals);
     if (op->family == 2 && !op->is_csr) cudaFree(op->mass);   // edge family: mass aliases w2
-    cudaFree(op->bp.map3d); cudaFree(op->bp.jstr); cudaFree(op->bp.mdiag); cudaFree(op->bp.Kband);
+    cudaFree(op->bp.map3d); cudaFree(op->bp.jstr); cudaFree(op->bp.mdiag);
+    op->kband.release(); op->bp.Kband = nullptr;
     op->LU.release(); op->wts.release();
     delete op;
 }
@@ -238,7 +275,9 @@ static int build_plan(cs_op* op) {
     k_gather_diag<<<cdiv(bp.n2, 256), 256, 0, c->st>>>(bp.map3d, op->mass, bp.n2, bp.mdiag);
     CS_CUDA(cudaGetLastError());
     size_t kb = (size_t)bp.nmodes * bp.band_elems() * esz(bp.cplx_band);
-    CS_CUDA(cudaMalloc(&bp.Kband, kb));
+    op->kband.pool = &c->pool; op->LU.pool = &c->pool; op->wts.pool = &c->pool;
+    CS_TRY(op->kband.ensure(kb));
+    bp.Kband = op->kband.p;
     CS_CUDA(cudaMemsetAsync(bp.Kband, 0, kb, c->st));
     return CS_OK;
 }
@@ -666,6 +705,7 @@ extern "C" int cs_ctx_destroy(cs_ctx* c) {
     ctx_drop_ops(c);
     cudaFree(c->tables); cudaFree(c->sigma); cudaFree(c->mu);
     c->work.release(); c->scal.release(); c->modes.release(); c->tmp1.release(); c->tmp2.release();
+    c->pool.clear();
     cudaFreeHost(c->pin);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->st);
@@ -799,7 +839,7 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
     size_t per = (size_t)op->bp.nmodes * op->bp.band_elems() * sizeof(cplx);
     size_t fr = 0, tot = 0;
     CS_CUDA(cudaMemGetInfo(&fr, &tot));
-    fr += op->LU.bytes;
+    fr += op->LU.bytes + c->pool.total();
     size_t vecs = (size_t)(8 + 2) * n * sizeof(cplx) + (size_t)op->bp.nmodes * op->bp.n2 * sizeof(cplx);
     long long chunk = (long long)((0.8 * (double)fr) / (double)(per + vecs));
     CS_CHECK(chunk >= 1, "not enough device memory for one frequency");

@@ -15,8 +15,17 @@
 // ld = ldab - 1 every block inside the band is a plain dense column-major block,
 // which is what the panel / update / solve kernels use.
 #include "cs_internal.h"
+#include <cuda_pipeline.h>
 
 namespace cs {
+
+template <typename T> __device__ __forceinline__ T shfl_t(T v, int src);
+template <> __device__ __forceinline__ double shfl_t<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <> __device__ __forceinline__ cplx shfl_t<cplx>(cplx v, int src) {
+    return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+// broadcast within each half-warp group of 16 lanes (lane r <-> row r of a 16 x 16 block)
+template <typename T> __device__ __forceinline__ T shfl_row(T v, int src) { return shfl_t<T>(v, src); }
 
 static const int TPB = 128;
 #define TWO_PI 6.28318530717958647692
@@ -232,118 +241,165 @@ int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long lo
 // Step t factors block column [t, t+nbe): panel kernel (one CTA per system)
 //   A11 = L11 U11,  L21 = A21 U11^-1 (R x nbe),  U12 = L11^-1 A12 (nbe x R)
 // then the update kernel (32x32 tiles x systems)  A22 -= L21 U12  (R x R).
-static const int NBMAX = 32;
+// NB is a compile-time constant so the per-thread row / column solves live in
+// registers; a short last block is padded with an identity.
+static const int NB = 16;
+static const int NBMAX = NB;
 
+// grid = (chunks, systems), 128 threads: every CTA factors the NB x NB diagonal block
+// itself (one warp, ~1 us, redundant across chunks) and then solves 64 rows of A21 and
+// 64 columns of A12.  A11 is NOT overwritten here (other chunks may still read it):
+// chunk 0 parks the factored block in `scratch`, the update kernel copies it in place.
 template <typename T>
-__global__ void k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, int nb, long long t) {
-    extern __shared__ unsigned char smem_raw[];
-    T* D = reinterpret_cast<T*>(smem_raw);           // [nb][nb], D[r*nb + c]
-    T* A = LU + (size_t)blockIdx.x * nel + pw;       // dense view base
-    int nbe = (int)min((long long)nb, n2 - t);
+__global__ void __launch_bounds__(128)
+k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, T* __restrict__ scratch) {
+    __shared__ T D[NB][NB + 1];                      // D[r][c]
+    T* A = LU + (size_t)blockIdx.y * nel + pw;       // dense view base
+    int nbe = (int)min((long long)NB, n2 - t);
     int R = (int)min((long long)p, n2 - (t + nbe));
     int tid = threadIdx.x;
-    for (int e = tid; e < nbe * nbe; e += blockDim.x) {
-        int r = e % nbe, c = e / nbe;
-        D[r * nb + c] = A[(t + r) + (t + c) * (long long)ld];
+    int idx = blockIdx.x * 64 + (tid & 63);          // row / column handled by this thread
+    bool isrow = (tid < 64) && idx < R, iscol = (tid >= 64) && idx < R;
+    // issue this thread's panel loads first: they overlap the A11 factorization
+    T v[NB];
+    long long row = t + nbe + idx, col = t + nbe + idx;
+    if (isrow) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) v[c] = (c < nbe) ? A[row + (t + c) * (long long)ld] : Sc<T>::zero();
+    } else if (iscol) {
+        const T* cp = A + col * (long long)ld + t;
+#pragma unroll
+        for (int r = 0; r < NB; ++r) v[r] = (r < nbe) ? cp[r] : Sc<T>::zero();
+    }
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
+        int r = e % NB, c = e / NB;
+        T val = (r == c) ? Sc<T>::one() : Sc<T>::zero();
+        if (r < nbe && c < nbe) val = A[(t + r) + (t + c) * (long long)ld];
+        D[r][c] = val;
     }
     __syncthreads();
-    for (int c = 0; c < nbe; ++c) {
-        T piv = Sc<T>::inv(D[c * nb + c]);
-        __syncthreads();
-        if (tid > c && tid < nbe) D[tid * nb + c] = D[tid * nb + c] * piv;
-        __syncthreads();
-        for (int e = tid; e < (nbe - c - 1) * (nbe - c - 1); e += blockDim.x) {
-            int r = c + 1 + e % (nbe - c - 1), cc = c + 1 + e / (nbe - c - 1);
-            D[r * nb + cc] -= D[r * nb + c] * D[c * nb + cc];
+    // unblocked LU of the NB x NB diagonal block by the first warp (lane r owns row r)
+    if (tid < 32) {
+        int r = tid & 15;
+        T rowv[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) rowv[c] = D[r][c];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            T piv = Sc<T>::inv(shfl_row(rowv[c], c));       // pivot row c is final now
+            T l = rowv[c] * piv;
+            if (r > c) rowv[c] = l;
+#pragma unroll
+            for (int cc = c + 1; cc < NB; ++cc) {
+                T u = shfl_row(rowv[cc], c);
+                if (r > c) rowv[cc] -= l * u;
+            }
         }
-        __syncthreads();
+        if (tid < NB) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) D[r][c] = rowv[c];
+        }
     }
-    for (int e = tid; e < nbe * nbe; e += blockDim.x) {
-        int r = e % nbe, c = e / nbe;
-        A[(t + r) + (t + c) * (long long)ld] = D[r * nb + c];
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        T* S = scratch + (size_t)blockIdx.y * NB * NB;
+        for (int e = tid; e < NB * NB; e += blockDim.x) S[e] = D[e % NB][e / NB];
     }
-    T v[NBMAX];
-    if (tid < R) {
+    if (isrow) {
         // row a of A21:  v U11 = row
-        long long row = t + nbe + tid;
-        for (int c = 0; c < nbe; ++c) v[c] = A[row + (t + c) * (long long)ld];
-        for (int c = 0; c < nbe; ++c) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
             T acc = v[c];
-            for (int c2 = 0; c2 < c; ++c2) acc -= v[c2] * D[c2 * nb + c];
-            v[c] = acc * Sc<T>::inv(D[c * nb + c]);
+#pragma unroll
+            for (int c2 = 0; c2 < c; ++c2) acc -= v[c2] * D[c2][c];
+            v[c] = acc * Sc<T>::inv(D[c][c]);
         }
-        for (int c = 0; c < nbe; ++c) A[row + (t + c) * (long long)ld] = v[c];
-    } else if (tid >= R && tid < 2 * R) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (c < nbe) A[row + (t + c) * (long long)ld] = v[c];
+    } else if (iscol) {
         // column b of A12:  L11 w = col (unit lower)
-        long long col = t + nbe + (tid - R);
-        T* cp = A + col * (long long)ld;
-        for (int r = 0; r < nbe; ++r) v[r] = cp[t + r];
-        for (int r = 0; r < nbe; ++r) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
             T acc = v[r];
-            for (int r2 = 0; r2 < r; ++r2) acc -= D[r * nb + r2] * v[r2];
+#pragma unroll
+            for (int r2 = 0; r2 < r; ++r2) acc -= D[r][r2] * v[r2];
             v[r] = acc;
         }
-        for (int r = 0; r < nbe; ++r) cp[t + r] = v[r];
+        T* cp = A + col * (long long)ld + t;
+#pragma unroll
+        for (int r = 0; r < NB; ++r) if (r < nbe) cp[r] = v[r];
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, int nb, long long t) {
-    __shared__ T Ls[NBMAX][32];
-    __shared__ T Us[NBMAX][33];
+k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, const T* __restrict__ scratch) {
+    __shared__ T Ls[NB][32];
+    __shared__ T Us[NB][33];
     T* A = LU + (size_t)blockIdx.z * nel + pw;
-    int nbe = (int)min((long long)nb, n2 - t);
+    int nbe = (int)min((long long)NB, n2 - t);
     int R = (int)min((long long)p, n2 - (t + nbe));
     int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
-    if (a0 >= R || b0 >= R) return;
     int tid = threadIdx.x;
-    long long r0 = t + nbe + a0, c0 = t + nbe + b0;
-    for (int e = tid; e < nbe * 32; e += 256) {
-        int a = e % 32, c = e / 32;
-        Ls[c][a] = (a0 + a < R) ? A[(r0 + a) + (t + c) * (long long)ld] : Sc<T>::zero();
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        // put the factored diagonal block (parked by the panel kernel) in place
+        const T* S = scratch + (size_t)blockIdx.z * NB * NB;
+        for (int e = tid; e < nbe * nbe; e += 256) {
+            int r = e % nbe, c = e / nbe;
+            A[(t + r) + (t + c) * (long long)ld] = S[r + c * NB];
+        }
     }
-    for (int e = tid; e < nbe * 32; e += 256) {
-        int c = e % nbe, b = e / nbe;
-        Us[c][b] = (b0 + b < R) ? A[(t + c) + (c0 + b) * (long long)ld] : Sc<T>::zero();
+    if (a0 >= R || b0 >= R) return;
+    long long r0 = t + nbe + a0, c0 = t + nbe + b0;
+    // thread -> rows (ta, ta+16), cols (tb, tb+16); start the C loads early
+    int ta = tid % 16, tb = tid / 16;
+    bool m0 = (a0 + ta < R), m1 = (a0 + ta + 16 < R), n0 = (b0 + tb < R), n1 = (b0 + tb + 16 < R);
+    T* c00 = A + (r0 + ta) + (c0 + tb) * (long long)ld;
+    T* c01 = A + (r0 + ta) + (c0 + tb + 16) * (long long)ld;
+    T old00 = (m0 && n0) ? c00[0] : Sc<T>::zero(), old10 = (m1 && n0) ? c00[16] : Sc<T>::zero();
+    T old01 = (m0 && n1) ? c01[0] : Sc<T>::zero(), old11 = (m1 && n1) ? c01[16] : Sc<T>::zero();
+    for (int e = tid; e < NB * 32; e += 256) {
+        int a = e % 32, c = e / 32;
+        Ls[c][a] = (a0 + a < R && c < nbe) ? A[(r0 + a) + (t + c) * (long long)ld] : Sc<T>::zero();
+    }
+    for (int e = tid; e < NB * 32; e += 256) {
+        int c = e % NB, b = e / NB;
+        Us[c][b] = (b0 + b < R && c < nbe) ? A[(t + c) + (c0 + b) * (long long)ld] : Sc<T>::zero();
     }
     __syncthreads();
-    // thread -> rows (ta, ta+16), cols (tb, tb+16)
-    int ta = tid % 16, tb = tid / 16;
     T acc00 = Sc<T>::zero(), acc01 = Sc<T>::zero(), acc10 = Sc<T>::zero(), acc11 = Sc<T>::zero();
-    for (int c = 0; c < nbe; ++c) {
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
         T l0 = Ls[c][ta], l1 = Ls[c][ta + 16];
         T u0 = Us[c][tb], u1 = Us[c][tb + 16];
         acc00 += l0 * u0; acc01 += l0 * u1; acc10 += l1 * u0; acc11 += l1 * u1;
     }
-    int a, b;
-    a = a0 + ta; b = b0 + tb;
-    if (a < R && b < R) A[(r0 + ta) + (c0 + tb) * (long long)ld] -= acc00;
-    b = b0 + tb + 16;
-    if (a < R && b < R) A[(r0 + ta) + (c0 + tb + 16) * (long long)ld] -= acc01;
-    a = a0 + ta + 16; b = b0 + tb;
-    if (a < R && b < R) A[(r0 + ta + 16) + (c0 + tb) * (long long)ld] -= acc10;
-    b = b0 + tb + 16;
-    if (a < R && b < R) A[(r0 + ta + 16) + (c0 + tb + 16) * (long long)ld] -= acc11;
+    if (m0 && n0) c00[0] = old00 - acc00;
+    if (m1 && n0) c00[16] = old10 - acc10;
+    if (m0 && n1) c01[0] = old01 - acc01;
+    if (m1 && n1) c01[16] = old11 - acc11;
 }
 
 template <typename T>
 static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
-    int pth = 2 * bp.p;
-    if (pth < bp.nb * bp.nb) pth = bp.nb * bp.nb;
-    pth = ((pth + 31) / 32) * 32;
-    CS_CHECK(pth <= 1024, "half bandwidth too large for the panel kernel (2p <= 1024)");
-    CS_CHECK(bp.nb <= NBMAX, "nb too large");
-    size_t sm = (size_t)bp.nb * bp.nb * sizeof(T);
+    CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
+    static void* scratch = nullptr;
+    static size_t scratch_bytes = 0;
+    size_t need = (size_t)nsys * NB * NB * sizeof(T);
+    if (need > scratch_bytes) {
+        if (scratch) cudaFree(scratch);
+        CS_CUDA(cudaMalloc(&scratch, need));
+        scratch_bytes = need;
+    }
     int tiles = (bp.p + 31) / 32;
-    for (long long t = 0; t < bp.n2; t += bp.nb) {
-        k_lu_panel<T><<<nsys, pth, sm, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nb, t);
-        if (t + bp.nb < bp.n2) {
-            dim3 g(tiles, tiles, nsys);
-            k_lu_update<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nb, t);
-        }
+    int chunks = (bp.p + 63) / 64;
+    for (long long t = 0; t < bp.n2; t += NB) {
+        dim3 gp(chunks, nsys);
+        k_lu_panel<T><<<gp, 128, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (T*)scratch);
+        dim3 g(tiles, tiles, nsys);
+        k_lu_update<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
     }
     CS_CUDA(cudaGetLastError());
     return CS_OK;
@@ -354,82 +410,161 @@ int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaSt
 }
 
 // ---------------------------------------------------------- banded solve ----
-// One CTA per (vector, mode): forward then backward substitution, both in the
-// column-oriented (axpy) form so that every read of L / U is a contiguous
-// column segment of the band.
-template <typename T> __device__ __forceinline__ T shfl_t(T v, int src);
-template <> __device__ __forceinline__ double shfl_t<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-template <> __device__ __forceinline__ cplx shfl_t<cplx>(cplx v, int src) {
-    return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+// One CTA per (vector, mode): forward then backward substitution in the
+// column-oriented (axpy) form.  The block column of L / U needed by step s+1 is
+// prefetched into shared memory with cp.async while step s computes (double
+// buffer); the active window of the right-hand side lives in a circular
+// shared-memory buffer, so the sequential critical path touches no global memory.
+template <typename TL>
+__device__ __forceinline__ void prefetch_cols(TL* __restrict__ dst, int ldd, const TL* __restrict__ A, int ld,
+                                              long long row0, int nrows, long long col0, int ncols) {
+    // dst[r + c*ldd] = A[(row0 + r) + (col0 + c)*ld]
+    int tot = nrows * ncols;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        int r = e % nrows, c = e / nrows;
+        __pipeline_memcpy_async(dst + r + c * ldd, A + (row0 + r) + (col0 + c) * (long long)ld, sizeof(TL));
+    }
 }
 
 template <typename TL, typename TV>
-__global__ void k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, int nb,
-                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm) {
+__global__ void k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
+                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     int v = blockIdx.y, m = blockIdx.x;
     int f = shift_of_vec ? shift_of_vec[v] : 0;
     const TL* A = LU + ((size_t)f * nmodes + m) * nel + pw;
     TV* b = xm + ((size_t)v * nmodes + m) * n2;
-    __shared__ TV y1[NBMAX];
+    const int ldd = NB + p;                                   // rows per staged block column
+    TL* buf0 = reinterpret_cast<TL*>(smem_raw);
+    TL* buf1 = buf0 + (size_t)ldd * NB;
+    TV* win = reinterpret_cast<TV*>(buf1 + (size_t)ldd * NB); // circular window, wsz = power of two >= p + 2 NB
+    __shared__ TV y1[NB];
     int tid = threadIdx.x, lane = tid & 31;
-    // ---- forward: L y = b (unit lower) ----
-    for (long long t = 0; t < n2; t += nb) {
-        int nbe = (int)min((long long)nb, n2 - t);
+    const int wm = wsz - 1;
+    long long nsteps = (n2 + NB - 1) / NB;
+
+    // ================= forward: L y = b (unit lower) =================
+    for (int e = tid; e < NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
+    {
+        int nbe = (int)min((long long)NB, n2);
+        int R = (int)min((long long)p, n2 - nbe);
+        prefetch_cols<TL>(buf0, ldd, A, ld, 0, nbe + R, 0, nbe);
+        __pipeline_commit();
+    }
+    for (long long s = 0; s < nsteps; ++s) {
+        long long t = s * NB;
+        int nbe = (int)min((long long)NB, n2 - t);
         int R = (int)min((long long)p, n2 - (t + nbe));
+        TL* cur = (s & 1) ? buf1 : buf0;
+        TL* nxt = (s & 1) ? buf0 : buf1;
+        if (s + 1 < nsteps) {
+            long long t2 = t + NB;
+            int nbe2 = (int)min((long long)NB, n2 - t2);
+            int R2 = (int)min((long long)p, n2 - (t2 + nbe2));
+            prefetch_cols<TL>(nxt, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
+        }
+        __pipeline_commit();
+        // rows entering the window this step: t + NB + p .. t + 2 NB + p - 1 (first touched next step)
+        for (long long e = t + NB + p + tid; e < t + 2 * NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
+        __pipeline_wait_prior(1);
+        __syncthreads();
         if (tid < 32) {
-            TV br = (lane < nbe) ? b[t + lane] : Sc<TV>::zero();
-            for (int c = 0; c < nbe; ++c) {
+            TV br = (lane < nbe) ? win[(t + lane) & wm] : Sc<TV>::zero();
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
                 TV yc = shfl_t<TV>(br, c);
-                if (lane > c && lane < nbe) br -= A[(t + lane) + (t + c) * (long long)ld] * yc;
+                if (lane > c && lane < nbe) br -= cur[lane + c * ldd] * yc;
             }
             if (lane < nbe) { y1[lane] = br; b[t + lane] = br; }
         }
         __syncthreads();
         if (tid < R) {
-            long long row = t + nbe + tid;
-            TV acc = b[row];
-            for (int c = 0; c < nbe; ++c) acc -= A[row + (t + c) * (long long)ld] * y1[c];
-            b[row] = acc;
+            TV acc = win[(t + nbe + tid) & wm];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (c < nbe) acc -= cur[(nbe + tid) + c * ldd] * y1[c];
+            win[(t + nbe + tid) & wm] = acc;
         }
         __syncthreads();
     }
-    // ---- backward: U x = y ----
-    long long tlast = ((n2 - 1) / nb) * nb;
-    for (long long t = tlast; t >= 0; t -= nb) {
-        int nbe = (int)min((long long)nb, n2 - t);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+
+    // ================= backward: U x = y =================
+    long long tlast = (nsteps - 1) * NB;
+    // window now indexes rows downwards; (re)load the last p + NB rows of y
+    for (long long e = max(0LL, n2 - (NB + p) - NB) + tid; e < n2; e += blockDim.x) win[e & wm] = b[e];
+    {
+        int nbe = (int)(n2 - tlast);
+        int Ra = (int)min((long long)p, tlast);
+        prefetch_cols<TL>(buf0, ldd, A, ld, tlast - Ra, Ra + nbe, tlast, nbe);
+        __pipeline_commit();
+    }
+    for (long long s = 0; s < nsteps; ++s) {
+        long long t = tlast - s * NB;
+        int nbe = (int)min((long long)NB, n2 - t);
         int Ra = (int)min((long long)p, t);
+        TL* cur = (s & 1) ? buf1 : buf0;
+        TL* nxt = (s & 1) ? buf0 : buf1;
+        if (s + 1 < nsteps) {
+            long long t2 = t - NB;
+            int Ra2 = (int)min((long long)p, t2);
+            prefetch_cols<TL>(nxt, ldd, A, ld, t2 - Ra2, Ra2 + NB, t2, NB);
+        }
+        __pipeline_commit();
+        // rows entering the window: t - p - 2 NB .. t - p - NB - 1 (first touched at step s + 2 at the latest)
+        for (long long e = t - p - 2 * NB + tid; e < t - p - NB; e += blockDim.x) if (e >= 0) win[e & wm] = b[e];
+        __pipeline_wait_prior(1);
+        __syncthreads();
+        // staged block: rows [t - Ra, t + nbe), local row index = row - (t - Ra)
         if (tid < 32) {
-            TV br = (lane < nbe) ? b[t + lane] : Sc<TV>::zero();
-            for (int c = nbe - 1; c >= 0; --c) {
-                TV xc = shfl_t<TV>(br, c);
-                xc = Sc<TL>::inv(A[(t + c) + (t + c) * (long long)ld]) * xc;
-                if (lane == c) br = xc;
-                if (lane < c) br -= A[(t + lane) + (t + c) * (long long)ld] * xc;
+            TV br = (lane < nbe) ? win[(t + lane) & wm] : Sc<TV>::zero();
+#pragma unroll
+            for (int c = NB - 1; c >= 0; --c) {
+                if (c < nbe) {
+                    TV xc = shfl_t<TV>(br, c);
+                    xc = Sc<TL>::inv(cur[(Ra + c) + c * ldd]) * xc;
+                    if (lane == c) br = xc;
+                    if (lane < c) br -= cur[(Ra + lane) + c * ldd] * xc;
+                }
             }
             if (lane < nbe) { y1[lane] = br; b[t + lane] = br; }
         }
         __syncthreads();
         if (tid < Ra) {
             long long row = t - Ra + tid;
-            TV acc = b[row];
-            for (int c = 0; c < nbe; ++c) acc -= A[row + (t + c) * (long long)ld] * y1[c];
-            b[row] = acc;
+            TV acc = win[row & wm];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (c < nbe) acc -= cur[tid + c * ldd] * y1[c];
+            win[row & wm] = acc;
         }
         __syncthreads();
     }
+    __pipeline_wait_prior(0);
 }
 
 int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st) {
     int th = ((bp.p + 31) / 32) * 32;
-    if (th < 32) th = 32;
+    if (th < 64) th = 64;
     CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel");
-    CS_CHECK(bp.nb <= 32, "nb must be <= 32 for the warp triangular solve");
+    CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
+    CS_CHECK(lu_cplx == xm_cplx, "LU and mode vectors must have the same scalar type");
     dim3 g(bp.nmodes, nvec);
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
-    if (lu_cplx && xm_cplx) k_band_solve<cplx, cplx><<<g, th, 0, st>>>((const cplx*)LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nb, bp.nmodes, shift_of_vec_d, (cplx*)xm);
-    else if (!lu_cplx && !xm_cplx) k_band_solve<double, double><<<g, th, 0, st>>>((const double*)LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nb, bp.nmodes, shift_of_vec_d, (double*)xm);
-    else CS_CHECK(false, "LU and mode vectors must have the same scalar type");
+    int wsz = 64;
+    while (wsz < bp.p + 3 * NB) wsz <<= 1;
+    size_t es = lu_cplx ? sizeof(cplx) : sizeof(double);
+    size_t sm = 2 * (size_t)(NB + bp.p) * NB * es + (size_t)wsz * es;
+    CS_CHECK(sm <= 220 * 1024, "half bandwidth too large for the shared-memory staged solve");
+    if (lu_cplx) {
+        static bool attr_c = false;
+        if (!attr_c) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<cplx, cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_c = true; }
+        k_band_solve<cplx, cplx><<<g, th, sm, st>>>((const cplx*)LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nmodes, shift_of_vec_d, (cplx*)xm, wsz);
+    } else {
+        static bool attr_d = false;
+        if (!attr_d) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_d = true; }
+        k_band_solve<double, double><<<g, th, sm, st>>>((const double*)LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nmodes, shift_of_vec_d, (double*)xm, wsz);
+    }
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

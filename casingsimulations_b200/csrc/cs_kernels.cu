@@ -176,6 +176,9 @@ int launch_edge_scale(const MeshD& m, const double* in, double* out, int mode, c
 // y_c = sum_f g_f (x_c - x_nbr(f)); faces on the outer r / bottom / top boundary
 // have no neighbour (Dirichlet phi = 0 outside; SimPEG Problem3D_CC, run.py:339-344)
 // g = area^2 / MfRho laid out like a face vector.  40 B/cell (3-D), 32 B/cell (2-D).
+// One thread per cell, i fastest.  (A z-marching variant with x / g_z carried in registers
+// was measured slower on B200 -- 63-97 us vs 55 us at 4.86 M cells: fewer, longer threads
+// expose less memory-level parallelism than 4.86 M independent ones.)
 template <typename T>
 __global__ void k_dc_apply(MeshD m, const double* __restrict__ g, double shift0,
                            const T* __restrict__ x, T* __restrict__ y) {
@@ -317,56 +320,191 @@ int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaSt
 // wF = alpha / area^2.  Serves FDEM-h (alpha = MfRho, beta = MeMu, s = i w),
 // FDEM-e / TDEM-e (alpha = MfMui, beta = MeSigma, s = i w | 1/dt).  3-D complex:
 // x 48 + y 48 + wF 24 + beta 24 = 144 B/cell; 2-D symmetric: 56 B/cell.
-template <typename T> struct WCirc {
-    const MeshD& m; EdgeV<T> e; const double *wx, *wy, *wz;
-    __device__ WCirc(const MeshD& m_, const T* v, const double* w) : m(m_), e(m_, v) {
-        wx = w; wy = w + m_.nFx; wz = w + m_.nFx + m_.nFy;
-    }
-    __device__ __forceinline__ T operator()(int kind, int i, int j, int k) const {
-        long long c = m.cidx(i, j, k);
-        if (kind == 0) return wx[c] * circFx(m, e, i, j, k);
-        if (kind == 1) return wy[c] * circFy(m, e, i, j, k);
-        return wz[c] * circFz(m, e, i, j, k);
-    }
-};
+// Implementation: each CTA owns a tile of 128 radial cells x TJ azimuthal cells (+ one halo
+// row j0-1, + one halo lane when the tile is not the last in r) and marches EDGE_KZ node
+// levels in z.  Per level every thread computes the three faces it owns (Fx, Fy of cell
+// level k and Fz of node level k) exactly once from registers + a few neighbour loads,
+// publishes w*circ in (double-buffered) shared memory, and after one barrier gathers the
+// faces around its three edges.  The faces of the level below stay in registers.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+static const int EDGE_TI = 128;
+static const int EDGE_PF = 2;       // levels of software prefetch distance
+static const int EDGE_KZ = 24;
 
-template <typename T>
-__global__ void __launch_bounds__(TPB)
+template <typename T, bool SYM>
+__global__ void __launch_bounds__(EDGE_TI * 5)
 k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ beta,
-          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y) {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    Slot sl;
-    if (!slot_of(m, t, m.nz + 1, sl)) return;
-    int sys = blockIdx.y;
+          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y, int tj, int nchunk, int istride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);           // [2][3][rows][EDGE_TI]
+    const int rows = blockDim.y;
+    const int li = threadIdx.x, row = threadIdx.y;
+    const int i = blockIdx.x * istride + li;
+    const int sys = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
+    const int j0 = blockIdx.y * tj;
+    const int jraw = SYM ? 0 : j0 + row - 1;           // row 0 is the halo row j0 - 1
+    const bool valid = (i < m.nx) && (SYM || jraw < m.nth);
+    const int j = SYM ? 0 : (jraw < 0 ? m.nth - 1 : (jraw >= m.nth ? 0 : jraw));
+    const bool out_ok = valid && (SYM || row >= 1) && (li < istride || i + 1 >= m.nx);
+    const bool has_ip = (i + 1 < m.nx);                // a neighbour at i+1 exists (then li+1 is in the tile)
     x += sys * m.nE;
     y += sys * m.nE;
-    T s = Sc<T>::from(s_d[2 * sys], s_d[2 * sys + 1]);
-    int i = sl.i, j = sl.j, k = sl.k;
-    WCirc<T> f(m, x, wF);
-    long long c = m.cidx(i, j, k);
-    {
-        long long e = m.nEx + c;
-        y[e] = m.lEy(i, j) * gathEy<T>(m, f, i, j, k) + s * (beta[e] * x[e]);
-    }
-    if (m.sym) return;
-    y[c] = m.lEx(i) * gathEx<T>(m, f, i, j, k) + s * (beta[c] * x[c]);
-    if (k < m.nz) {
-        long long e = m.nEx + m.nEy + m.ez(i, j, k);
-        y[e] = m.lEz(k) * gathEz<T>(m, f, i, j, k) + s * (beta[e] * x[e]);
-        if (i == 0 && j == 0) {
-            long long a = m.nEx + m.nEy + m.ezaxis(k);
-            y[a] = m.lEz(k) * gathEzAxis<T>(m, f, k) + s * (beta[a] * x[a]);
+    const T s = Sc<T>::from(s_d[2 * sys], s_d[2 * sys + 1]);
+    const T* X = x; const T* Y = x + m.nEx; const T* Z = x + m.nEx + m.nEy;
+    T* YX = y; T* YY = y + m.nEx; T* YZ = y + m.nEx + m.nEy;
+    const double* wx = wF; const double* wy = wF + m.nFx; const double* wz = wF + m.nFx + m.nFy;
+    const double* bx = beta; const double* by = beta + m.nEx; const double* bz = beta + m.nEx + m.nEy;
+    const int k0 = chunk * EDGE_KZ, k1 = min(m.nz + 1, k0 + EDGE_KZ);
+    const int ii = valid ? i : 0;
+    const int jp = SYM ? 0 : m.jp(j);
+    const double lex = SYM ? 0.0 : m.lEx(ii), ley = m.lEy(ii, j), leym = (ii > 0) ? m.lEy(ii - 1, j) : 0.0;
+    const long long col = (long long)ii + (long long)m.nx * j, colp = (long long)ii + (long long)m.nx * jp;
+    const T zero = Sc<T>::zero();
+    T Xk = zero, Yk = zero, tFxp = zero, tFyp = zero;
+    if (valid) {
+        Yk = Y[col + m.nxy * k0];
+        if (!SYM) Xk = X[col + m.nxy * k0];
+        if (k0 > 0) {
+            // faces of cell level k0 - 1 (normally carried over from the previous level)
+            int km = k0 - 1;
+            long long c = col + m.nxy * km;
+            T Ykm = Y[c];
+            T cfx = (-ley) * (Yk - Ykm);
+            if (!SYM) {
+                T Zk_ = Z[m.ez(ii, j, km)], Zjp_ = Z[m.ez(ii, jp, km)];
+                T Zim_ = (ii > 0) ? Z[m.ez(ii - 1, j, km)] : Z[m.ezaxis(km)];
+                cfx += m.lEz(km) * (Zjp_ - Zk_);
+                tFyp = wy[c] * (lex * (Xk - X[c]) - m.lEz(km) * (Zk_ - Zim_));
+            }
+            tFxp = wx[c] * cfx;
         }
     }
+    for (int k = k0; k < k1; ++k) {
+        const bool cell = (k < m.nz);
+        T* sb = sm + (size_t)(k & 1) * 3 * rows * EDGE_TI;
+        if (valid && k + EDGE_PF < k1) {
+            // pull the lines this thread owns at level k + EDGE_PF towards L1 (neighbours'
+            // values are owned -- and prefetched -- by the neighbouring threads)
+            const int kp = k + EDGE_PF;
+            const long long cp = col + m.nxy * kp;
+            prefetch_l1(wz + cp); prefetch_l1(by + cp);
+            if (kp < m.nz) { prefetch_l1(Y + cp + m.nxy); prefetch_l1(wx + cp); }
+            if (!SYM) {
+                prefetch_l1(bx + cp);
+                if (kp < m.nz) {
+                    prefetch_l1(X + cp + m.nxy); prefetch_l1(wy + cp);
+                    long long e = m.ez(ii, j, kp);
+                    prefetch_l1(Z + e); prefetch_l1(bz + e);
+                }
+            }
+        }
+        T tFx = zero, tFy = zero, tFz = zero, Xk1 = zero, Yk1 = zero, Zk = zero;
+        const long long c = col + m.nxy * k;
+        if (valid) {
+            T Yim = (ii > 0) ? Y[c - 1] : zero;
+            T cfz = ley * Yk - leym * Yim;
+            if (!SYM) cfz -= lex * (X[colp + m.nxy * k] - Xk);
+            tFz = wz[c] * cfz;
+            if (cell) {
+                Yk1 = Y[c + m.nxy];
+                T cfx = (-ley) * (Yk1 - Yk);
+                if (!SYM) {
+                    const double lez = m.lEz(k);
+                    Xk1 = X[c + m.nxy];
+                    Zk = Z[m.ez(ii, j, k)];
+                    T Zjp = Z[m.ez(ii, jp, k)];
+                    T Zim = (ii > 0) ? Z[m.ez(ii - 1, j, k)] : Z[m.ezaxis(k)];
+                    cfx += lez * (Zjp - Zk);
+                    tFy = wy[c] * (lex * (Xk1 - Xk) - lez * (Zk - Zim));
+                }
+                tFx = wx[c] * cfx;
+            }
+        }
+        sb[(0 * rows + row) * EDGE_TI + li] = tFx;
+        sb[(1 * rows + row) * EDGE_TI + li] = tFy;
+        sb[(2 * rows + row) * EDGE_TI + li] = tFz;
+        __syncthreads();
+        if (out_ok) {
+            T tFz_ip = has_ip ? sb[(2 * rows + row) * EDGE_TI + li + 1] : zero;
+            {
+                T r = tFx - tFxp + tFz - tFz_ip;
+                YY[c] = ley * r + s * (by[c] * Yk);
+            }
+            if (!SYM) {
+                T tFz_jm = sb[(2 * rows + row - 1) * EDGE_TI + li];
+                T r = tFyp - tFy + tFz - tFz_jm;
+                YX[c] = lex * r + s * (bx[c] * Xk);
+                if (cell) {
+                    T tFx_jm = sb[(0 * rows + row - 1) * EDGE_TI + li];
+                    T tFy_ip = has_ip ? sb[(1 * rows + row) * EDGE_TI + li + 1] : zero;
+                    T r2 = tFx_jm - tFx - tFy + tFy_ip;
+                    long long e = m.ez(ii, j, k);
+                    YZ[e] = m.lEz(k) * r2 + s * (bz[e] * Zk);
+                }
+            }
+        }
+        tFxp = tFx; tFyp = tFy; Xk = Xk1; Yk = Yk1;
+    }
+}
+
+// the single shared axis edge per z level: lEz * sum_j wFy(0,j,k) circFy(0,j,k) + s beta x
+template <typename T>
+__global__ void k_edge_op_axis(MeshD m, const double* __restrict__ wF, const double* __restrict__ beta,
+                               const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y) {
+    int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31, sys = blockIdx.y;
+    if (k >= m.nz) return;
+    x += sys * m.nE;
+    y += sys * m.nE;
+    const T* X = x; const T* Z = x + m.nEx + m.nEy;
+    const double* wy = wF + m.nFx;
+    T az = Z[m.ezaxis(k)];
+    double re = 0.0, im = 0.0;
+    for (int j = lane; j < m.nth; j += 32) {
+        long long c = m.cidx(0, j, k);
+        T v = wy[c] * (m.lEx(0) * (X[c + m.nxy] - X[c]) - m.lEz(k) * (Z[m.ez(0, j, k)] - az));
+        re += Sc<T>::re(v); im += Sc<T>::im(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) { re += __shfl_down_sync(0xffffffffu, re, o); im += __shfl_down_sync(0xffffffffu, im, o); }
+    if (lane == 0) {
+        T s = Sc<T>::from(s_d[2 * sys], s_d[2 * sys + 1]);
+        long long a = m.nEx + m.nEy + m.ezaxis(k);
+        y[a] = m.lEz(k) * Sc<T>::from(re, im) + s * (beta[a] * az);
+    }
+}
+
+template <typename T>
+static int launch_edge_op_t(const MeshD& m, const double* wF, const double* beta, const double* s_d,
+                            const T* x, T* y, int nsys, cudaStream_t st) {
+    int nlev = m.nz + 1;
+    int nchunk = (nlev + EDGE_KZ - 1) / EDGE_KZ;
+    int itiles = (m.nx <= EDGE_TI) ? 1 : (m.nx + EDGE_TI - 2) / (EDGE_TI - 1);
+    int istride = (itiles == 1) ? EDGE_TI : EDGE_TI - 1;
+    if (m.sym) {
+        dim3 blk(EDGE_TI, 1), grd(itiles, 1, nchunk * nsys);
+        size_t smb = 2 * 3 * 1 * EDGE_TI * sizeof(T);
+        k_edge_op<T, true><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, 1, nchunk, istride);
+    } else {
+        int tj = m.nth < 4 ? m.nth : 4;
+        dim3 blk(EDGE_TI, tj + 1), grd(itiles, (m.nth + tj - 1) / tj, nchunk * nsys);
+        size_t smb = 2 * 3 * (size_t)(tj + 1) * EDGE_TI * sizeof(T);
+        static bool attr_set = false;            // one flag per template instantiation
+        if (!attr_set) {
+            CS_CUDA(cudaFuncSetAttribute(k_edge_op<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 3 * 5 * EDGE_TI * (int)sizeof(T)));
+            attr_set = true;
+        }
+        k_edge_op<T, false><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, tj, nchunk, istride);
+        dim3 ga((m.nz + 7) / 8, nsys);
+        k_edge_op_axis<T><<<ga, 256, 0, st>>>(m, wF, beta, s_d, x, y);
+    }
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
 }
 
 int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const double* s_d,
                    const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st) {
-    long long n = m.nxy * (m.nz + 1);
-    if (cplx_vec) k_edge_op<cplx><<<grid1(n, nsys), TPB, 0, st>>>(m, wF, beta, s_d, (const cplx*)x, (cplx*)y);
-    else k_edge_op<double><<<grid1(n, nsys), TPB, 0, st>>>(m, wF, beta, s_d, (const double*)x, (double*)y);
-    CS_CUDA(cudaGetLastError());
-    return CS_OK;
+    if (cplx_vec) return launch_edge_op_t<cplx>(m, wF, beta, s_d, (const cplx*)x, (cplx*)y, nsys, st);
+    return launch_edge_op_t<double>(m, wF, beta, s_d, (const double*)x, (double*)y, nsys, st);
 }
 
 // ============================ K4': fused face-form operator ======================
