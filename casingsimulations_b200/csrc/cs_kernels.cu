@@ -5,6 +5,7 @@
 // neighbour values come from L1/L2 (a z-plane is nx*nth*16 B <= 223 KB).
 #include "cs_internal.h"
 #include "cs_stencil.cuh"
+#include <cuda_pipeline.h>
 
 namespace cs {
 
@@ -322,31 +323,38 @@ int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaSt
 // x 48 + y 48 + wF 24 + beta 24 = 144 B/cell; 2-D symmetric: 56 B/cell.
 // Implementation: each CTA owns a tile of 128 radial cells x TJ azimuthal cells (+ one halo
 // row j0-1, + one halo lane when the tile is not the last in r) and marches EDGE_KZ node
-// levels in z.  Per level every thread computes the three faces it owns (Fx, Fy of cell
-// level k and Fz of node level k) exactly once from registers + a few neighbour loads,
-// publishes w*circ in (double-buffered) shared memory, and after one barrier gathers the
-// faces around its three edges.  The faces of the level below stay in registers.
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-static const int EDGE_TI = 128;
-static const int EDGE_PF = 2;       // levels of software prefetch distance
-static const int EDGE_KZ = 24;
+// levels in z.  The x values of a level (a (TJ+2) x 129 tile of each of Ex, Ey at node
+// level s and of Ez at cell level s, halos included) are staged in shared memory by
+// cp.async (LDGSTS) three levels ahead through a 4-slot ring, so the DRAM latency is
+// decoupled from the arithmetic.  Per level every thread computes the three faces it owns
+// (Fx, Fy of cell level k, Fz of node level k) exactly once, publishes w*circ in shared
+// memory and, after a barrier, gathers the faces around its three edges; the faces of the
+// level below stay in registers; weights are register-prefetched one level ahead.
+static const int EDGE_NS = 4;             // ring slots
 
-template <typename T, bool SYM>
-__global__ void __launch_bounds__(EDGE_TI * 5)
+template <typename T, bool SYM, int TI>
+__global__ void __launch_bounds__(TI * 5, (TI <= 64 ? 2 : 1))
 k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ beta,
-          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y, int tj, int nchunk, int istride) {
+          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y, int tj, int nchunk, int kz, int istride) {
+    constexpr int TW = TI + 1;                         // staged tile width: lanes i0-1 .. i0+TI-1
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sm = reinterpret_cast<T*>(smem_raw);           // [2][3][rows][EDGE_TI]
-    const int rows = blockDim.y;
+    const int rows = blockDim.y;                       // face rows: (halo j0-1) + tj   [SYM: 1]
+    const int trows = SYM ? 1 : rows + 1;              // staged x rows: j0-1 .. j0+tj
+    const int tsz = trows * TW;                        // elements per staged array
+    const int ncomp = SYM ? 1 : 3;
+    T* stage = reinterpret_cast<T*>(smem_raw);         // [EDGE_NS][ncomp][trows][TW]
+    T* fxb = stage + (size_t)EDGE_NS * ncomp * tsz;    // [2][3][rows][TI] face exchange (double buffer)
     const int li = threadIdx.x, row = threadIdx.y;
-    const int i = blockIdx.x * istride + li;
+    const int tid = row * TI + li, nthr = TI * rows;
+    const int i0 = blockIdx.x * istride;
+    const int i = i0 + li;
     const int sys = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
     const int j0 = blockIdx.y * tj;
-    const int jraw = SYM ? 0 : j0 + row - 1;           // row 0 is the halo row j0 - 1
+    const int jraw = SYM ? 0 : j0 + row - 1;
     const bool valid = (i < m.nx) && (SYM || jraw < m.nth);
     const int j = SYM ? 0 : (jraw < 0 ? m.nth - 1 : (jraw >= m.nth ? 0 : jraw));
     const bool out_ok = valid && (SYM || row >= 1) && (li < istride || i + 1 >= m.nx);
-    const bool has_ip = (i + 1 < m.nx);                // a neighbour at i+1 exists (then li+1 is in the tile)
+    const bool has_ip = (i + 1 < m.nx);
     x += sys * m.nE;
     y += sys * m.nE;
     const T s = Sc<T>::from(s_d[2 * sys], s_d[2 * sys + 1]);
@@ -354,97 +362,144 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
     T* YX = y; T* YY = y + m.nEx; T* YZ = y + m.nEx + m.nEy;
     const double* wx = wF; const double* wy = wF + m.nFx; const double* wz = wF + m.nFx + m.nFy;
     const double* bx = beta; const double* by = beta + m.nEx; const double* bz = beta + m.nEx + m.nEy;
-    const int k0 = chunk * EDGE_KZ, k1 = min(m.nz + 1, k0 + EDGE_KZ);
+    const int nlev = m.nz + 1;
+    const int k0 = chunk * kz, k1 = min(nlev, k0 + kz);
+    const int kbeg = (k0 > 0) ? k0 - 1 : 0;            // one extra level below: its faces feed level k0
     const int ii = valid ? i : 0;
-    const int jp = SYM ? 0 : m.jp(j);
     const double lex = SYM ? 0.0 : m.lEx(ii), ley = m.lEy(ii, j), leym = (ii > 0) ? m.lEy(ii - 1, j) : 0.0;
-    const long long col = (long long)ii + (long long)m.nx * j, colp = (long long)ii + (long long)m.nx * jp;
+    const long long col = (long long)ii + (long long)m.nx * j;
+    const long long ezc = 1 + (long long)ii + (long long)m.nx * j;       // Ez offset inside a level block
     const T zero = Sc<T>::zero();
-    T Xk = zero, Yk = zero, tFxp = zero, tFyp = zero;
-    if (valid) {
-        Yk = Y[col + m.nxy * k0];
-        if (!SYM) Xk = X[col + m.nxy * k0];
-        if (k0 > 0) {
-            // faces of cell level k0 - 1 (normally carried over from the previous level)
-            int km = k0 - 1;
-            long long c = col + m.nxy * km;
-            T Ykm = Y[c];
-            T cfx = (-ley) * (Yk - Ykm);
+
+    // ---- staging descriptors: which tile elements this thread copies every level ----------
+    constexpr int NQ = 3;                               // ceil(tsz / nthr) <= 3 for every configuration used
+    int eoff[NQ]; long long cb[NQ]; long long zb[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        int e = tid + q * nthr;
+        eoff[q] = -1; cb[q] = -1; zb[q] = -1;
+        if (e < tsz) {
+            eoff[q] = e;
+            int rr = e / TW, ll = e - rr * TW;
+            int gi = i0 - 1 + ll, gj = 0;
+            bool jok = true;
             if (!SYM) {
-                T Zk_ = Z[m.ez(ii, j, km)], Zjp_ = Z[m.ez(ii, jp, km)];
-                T Zim_ = (ii > 0) ? Z[m.ez(ii - 1, j, km)] : Z[m.ezaxis(km)];
-                cfx += m.lEz(km) * (Zjp_ - Zk_);
-                tFyp = wy[c] * (lex * (Xk - X[c]) - m.lEz(km) * (Zk_ - Zim_));
+                int jr = j0 - 1 + rr;
+                jok = jr <= m.nth;                      // one wrapped row past the end is still needed (jp)
+                gj = jr < 0 ? m.nth - 1 : (jr >= m.nth ? jr - m.nth : jr);
             }
-            tFxp = wx[c] * cfx;
+            if (jok && gi >= 0 && gi < m.nx) { cb[q] = (long long)gi + (long long)m.nx * gj; zb[q] = 1 + cb[q]; }
+            else if (jok && gi == -1) zb[q] = 0;        // the axis edge stands in for Ez(r_0)
         }
     }
-    for (int k = k0; k < k1; ++k) {
-        const bool cell = (k < m.nz);
-        T* sb = sm + (size_t)(k & 1) * 3 * rows * EDGE_TI;
-        if (valid && k + EDGE_PF < k1) {
-            // pull the lines this thread owns at level k + EDGE_PF towards L1 (neighbours'
-            // values are owned -- and prefetched -- by the neighbouring threads)
-            const int kp = k + EDGE_PF;
-            const long long cp = col + m.nxy * kp;
-            prefetch_l1(wz + cp); prefetch_l1(by + cp);
-            if (kp < m.nz) { prefetch_l1(Y + cp + m.nxy); prefetch_l1(wx + cp); }
-            if (!SYM) {
-                prefetch_l1(bx + cp);
-                if (kp < m.nz) {
-                    prefetch_l1(X + cp + m.nxy); prefetch_l1(wy + cp);
-                    long long e = m.ez(ii, j, kp);
-                    prefetch_l1(Z + e); prefetch_l1(bz + e);
-                }
+    auto load_stage = [&](int sl) {
+        if (sl > m.nz) return;                          // beyond the top node level: nothing to load
+        T* st = stage + (size_t)(sl % EDGE_NS) * ncomp * tsz;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (eoff[q] < 0) continue;
+            int e = eoff[q];
+            if (cb[q] >= 0) {
+                long long c = cb[q] + m.nxy * sl;
+                __pipeline_memcpy_async(st + e, Y + c, sizeof(T));
+                if (!SYM) __pipeline_memcpy_async(st + tsz + e, X + c, sizeof(T));
+            } else {
+                st[e] = zero;
+                if (!SYM) st[tsz + e] = zero;
+            }
+            if (!SYM && sl < m.nz) {
+                if (zb[q] >= 0) __pipeline_memcpy_async(st + 2 * tsz + e, Z + sl * m.ezp + zb[q], sizeof(T));
+                else st[2 * tsz + e] = zero;
             }
         }
-        T tFx = zero, tFy = zero, tFz = zero, Xk1 = zero, Yk1 = zero, Zk = zero;
-        const long long c = col + m.nxy * k;
+    };
+    load_stage(kbeg);     __pipeline_commit();
+    load_stage(kbeg + 1); __pipeline_commit();
+    load_stage(kbeg + 2); __pipeline_commit();
+
+    T tFxp = zero, tFyp = zero;
+    double wzk = 0.0, wxk = 0.0, wyk = 0.0, byk = 0.0, bxk = 0.0, bzk = 0.0;
+    if (valid) {
+        long long c = col + m.nxy * kbeg;
+        wzk = wz[c];
+        byk = by[c];
+        if (!SYM) bxk = bx[c];
+        if (kbeg < m.nz) { wxk = wx[c]; if (!SYM) { wyk = wy[c]; bzk = bz[kbeg * m.ezp + ezc]; } }
+    }
+    __pipeline_wait_prior(1);                            // stages kbeg, kbeg+1 landed
+    __syncthreads();
+    const int so = (SYM ? 0 : row) * TW + li;            // (row, lane-1) inside a staged array; +1 = own lane
+    for (int k = kbeg; k < k1; ++k) {
+        const bool cell = (k < m.nz);
+        load_stage(k + 3);
+        __pipeline_commit();
+        // prefetch next level's weights into registers
+        double wzn = 0.0, wxn = 0.0, wyn = 0.0, byn = 0.0, bxn = 0.0, bzn = 0.0;
+        if (valid && k + 1 < k1) {
+            long long c = col + m.nxy * (k + 1);
+            wzn = wz[c];
+            byn = by[c];
+            if (!SYM) bxn = bx[c];
+            if (k + 1 < m.nz) { wxn = wx[c]; if (!SYM) { wyn = wy[c]; bzn = bz[(k + 1) * m.ezp + ezc]; } }
+        }
+        const T* sk = stage + (size_t)(k % EDGE_NS) * ncomp * tsz;
+        const T* sk1 = stage + (size_t)((k + 1) % EDGE_NS) * ncomp * tsz;
+        T* fx = fxb + (size_t)(k & 1) * 3 * rows * TI;
+        T tFx = zero, tFy = zero, tFz = zero, Xk = zero, Zk = zero;
+        T Yk = sk[so + 1];
         if (valid) {
-            T Yim = (ii > 0) ? Y[c - 1] : zero;
+            T Yim = sk[so];
             T cfz = ley * Yk - leym * Yim;
-            if (!SYM) cfz -= lex * (X[colp + m.nxy * k] - Xk);
-            tFz = wz[c] * cfz;
+            if (!SYM) {
+                Xk = sk[tsz + so + 1];
+                cfz -= lex * (sk[tsz + so + TW + 1] - Xk);
+            }
+            tFz = wzk * cfz;
             if (cell) {
-                Yk1 = Y[c + m.nxy];
+                T Yk1 = sk1[so + 1];
                 T cfx = (-ley) * (Yk1 - Yk);
                 if (!SYM) {
                     const double lez = m.lEz(k);
-                    Xk1 = X[c + m.nxy];
-                    Zk = Z[m.ez(ii, j, k)];
-                    T Zjp = Z[m.ez(ii, jp, k)];
-                    T Zim = (ii > 0) ? Z[m.ez(ii - 1, j, k)] : Z[m.ezaxis(k)];
+                    T Xk1 = sk1[tsz + so + 1];
+                    Zk = sk[2 * tsz + so + 1];
+                    T Zjp = sk[2 * tsz + so + TW + 1];
+                    T Zim = sk[2 * tsz + so];
                     cfx += lez * (Zjp - Zk);
-                    tFy = wy[c] * (lex * (Xk1 - Xk) - lez * (Zk - Zim));
+                    tFy = wyk * (lex * (Xk1 - Xk) - lez * (Zk - Zim));
                 }
-                tFx = wx[c] * cfx;
+                tFx = wxk * cfx;
             }
         }
-        sb[(0 * rows + row) * EDGE_TI + li] = tFx;
-        sb[(1 * rows + row) * EDGE_TI + li] = tFy;
-        sb[(2 * rows + row) * EDGE_TI + li] = tFz;
+        fx[(0 * rows + row) * TI + li] = tFx;
+        fx[(1 * rows + row) * TI + li] = tFy;
+        fx[(2 * rows + row) * TI + li] = tFz;
+        // the one barrier of the level: publishes the faces AND (thanks to the wait) the
+        // staged tiles that the next level reads
+        __pipeline_wait_prior(1);                        // stages <= k+2 landed
         __syncthreads();
-        if (out_ok) {
-            T tFz_ip = has_ip ? sb[(2 * rows + row) * EDGE_TI + li + 1] : zero;
+        if (out_ok && k >= k0) {
+            const long long c = col + m.nxy * k;
+            T tFz_ip = has_ip ? fx[(2 * rows + row) * TI + li + 1] : zero;
             {
                 T r = tFx - tFxp + tFz - tFz_ip;
-                YY[c] = ley * r + s * (by[c] * Yk);
+                YY[c] = ley * r + s * (byk * Yk);
             }
             if (!SYM) {
-                T tFz_jm = sb[(2 * rows + row - 1) * EDGE_TI + li];
+                T tFz_jm = fx[(2 * rows + row - 1) * TI + li];
                 T r = tFyp - tFy + tFz - tFz_jm;
-                YX[c] = lex * r + s * (bx[c] * Xk);
+                YX[c] = lex * r + s * (bxk * Xk);
                 if (cell) {
-                    T tFx_jm = sb[(0 * rows + row - 1) * EDGE_TI + li];
-                    T tFy_ip = has_ip ? sb[(1 * rows + row) * EDGE_TI + li + 1] : zero;
+                    T tFx_jm = fx[(0 * rows + row - 1) * TI + li];
+                    T tFy_ip = has_ip ? fx[(1 * rows + row) * TI + li + 1] : zero;
                     T r2 = tFx_jm - tFx - tFy + tFy_ip;
-                    long long e = m.ez(ii, j, k);
-                    YZ[e] = m.lEz(k) * r2 + s * (bz[e] * Zk);
+                    YZ[k * m.ezp + ezc] = m.lEz(k) * r2 + s * (bzk * Zk);
                 }
             }
         }
-        tFxp = tFx; tFyp = tFy; Xk = Xk1; Yk = Yk1;
+        tFxp = tFx; tFyp = tFy;
+        wzk = wzn; wxk = wxn; wyk = wyn; byk = byn; bxk = bxn; bzk = bzn;
     }
+    __pipeline_wait_prior(0);
 }
 
 // the single shared axis edge per z level: lEz * sum_j wFy(0,j,k) circFy(0,j,k) + s beta x
@@ -473,27 +528,48 @@ __global__ void k_edge_op_axis(MeshD m, const double* __restrict__ wF, const dou
     }
 }
 
+template <typename T, bool SYM, int TI>
+static int launch_edge_op_cfg(const MeshD& m, const double* wF, const double* beta, const double* s_d,
+                              const T* x, T* y, int nsys, cudaStream_t st) {
+    static int nsm = 0;
+    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
+    int nlev = m.nz + 1;
+    int itiles = (m.nx <= TI) ? 1 : (m.nx + TI - 2) / (TI - 1);
+    int istride = (itiles == 1) ? TI : TI - 1;
+    int tj = SYM ? 1 : (m.nth < 4 ? m.nth : 4);
+    int jtiles = SYM ? 1 : (m.nth + tj - 1) / tj;
+    // z chunks: ~2 waves of resident CTAs when the mesh is large enough, at least ~16 levels
+    // per chunk so the extra priming level stays cheap
+    int resident = (TI <= 64) ? 2 : 1;
+    long long plane_ctas = (long long)itiles * jtiles * nsys;
+    int nchunk = (int)((2LL * nsm * resident + plane_ctas - 1) / plane_ctas);
+    int maxchunk = (nlev + 15) / 16;
+    if (nchunk > maxchunk) nchunk = maxchunk;
+    if (nchunk < 1) nchunk = 1;
+    int kz = (nlev + nchunk - 1) / nchunk;
+    nchunk = (nlev + kz - 1) / kz;
+    int rows = SYM ? 1 : tj + 1;
+    int trows = SYM ? 1 : rows + 1, ncomp = SYM ? 1 : 3;
+    size_t smb = ((size_t)EDGE_NS * ncomp * trows * (TI + 1) + 2 * 3 * (size_t)rows * TI) * sizeof(T);
+    CS_CHECK(trows * (TI + 1) <= 3 * TI * rows, "staging descriptor count too small");
+    dim3 blk(TI, rows), grd(itiles, jtiles, nchunk * nsys);
+    static bool attr_set = false;                // one flag per template instantiation
+    if (!attr_set) {
+        size_t mx = ((size_t)EDGE_NS * 3 * 6 * (TI + 1) + 2 * 3 * 5 * TI) * sizeof(T);
+        CS_CUDA(cudaFuncSetAttribute(k_edge_op<T, SYM, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        attr_set = true;
+    }
+    k_edge_op<T, SYM, TI><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, tj, nchunk, kz, istride);
+    return CS_OK;
+}
+
 template <typename T>
 static int launch_edge_op_t(const MeshD& m, const double* wF, const double* beta, const double* s_d,
                             const T* x, T* y, int nsys, cudaStream_t st) {
-    int nlev = m.nz + 1;
-    int nchunk = (nlev + EDGE_KZ - 1) / EDGE_KZ;
-    int itiles = (m.nx <= EDGE_TI) ? 1 : (m.nx + EDGE_TI - 2) / (EDGE_TI - 1);
-    int istride = (itiles == 1) ? EDGE_TI : EDGE_TI - 1;
     if (m.sym) {
-        dim3 blk(EDGE_TI, 1), grd(itiles, 1, nchunk * nsys);
-        size_t smb = 2 * 3 * 1 * EDGE_TI * sizeof(T);
-        k_edge_op<T, true><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, 1, nchunk, istride);
+        CS_TRY((launch_edge_op_cfg<T, true, 128>(m, wF, beta, s_d, x, y, nsys, st)));
     } else {
-        int tj = m.nth < 4 ? m.nth : 4;
-        dim3 blk(EDGE_TI, tj + 1), grd(itiles, (m.nth + tj - 1) / tj, nchunk * nsys);
-        size_t smb = 2 * 3 * (size_t)(tj + 1) * EDGE_TI * sizeof(T);
-        static bool attr_set = false;            // one flag per template instantiation
-        if (!attr_set) {
-            CS_CUDA(cudaFuncSetAttribute(k_edge_op<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 3 * 5 * EDGE_TI * (int)sizeof(T)));
-            attr_set = true;
-        }
-        k_edge_op<T, false><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, tj, nchunk, istride);
+        CS_TRY((launch_edge_op_cfg<T, false, 64>(m, wF, beta, s_d, x, y, nsys, st)));
         dim3 ga((m.nz + 7) / 8, nsys);
         k_edge_op_axis<T><<<ga, 256, 0, st>>>(m, wF, beta, s_d, x, y);
     }
