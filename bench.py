@@ -57,7 +57,7 @@ class ClockSampler(object):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -228,7 +228,10 @@ def run_ours(args, rank, world, local_rank):
             fn()
             e1.record(stream)
             torch.cuda.synchronize()
-            tot += e0.elapsed_time(e1) * 1e-3     # CUDA events on the stream every kernel of the step runs on
+            dt = e0.elapsed_time(e1) * 1e-3       # CUDA events on the stream every kernel of the step runs on
+            if os.environ.get("BENCH_DEBUG"):
+                print("rank", rank, fn.__name__, "step", round(dt * 1e3, 2), "ms", {k: round(v, 1) for k, v in ctx.info.items() if k.startswith("ms_")}, file=sys.stderr, flush=True)
+            tot += dt
         return tot
 
     for _ in range(max(args.warmup, 3)):

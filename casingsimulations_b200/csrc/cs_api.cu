@@ -497,6 +497,142 @@ struct Krylov {
     }
 };
 
+// ------------------------------------------------ batched restarted GMRES -----
+// Right-preconditioned GMRES(m) on the Jacobi-scaled system: minimises ||S (b - A x)||,
+// S = diag(|a_ii|^-1/2), with T = S A M^-1 S^-1 acting on scaled-residual-space vectors and
+// x = x0 + M^-1 S^-1 (V y).  Classical Gram-Schmidt with re-orthogonalisation (2 host syncs
+// per iteration); Givens rotations per system on the host.
+static int gmres_solve(Krylov& K, const void* rhs, void* x, const std::vector<double>& bnorm, double tight,
+                       int maxit, int& total_it, double& worst) {
+    cs_ctx* c = K.c; cs_op* op = K.op;
+    const int nvec = K.nvec; const long long n = K.n; const bool cv = K.cv;
+    const int m = std::max(2, std::min(maxit, 80));
+    const size_t vb = K.vb;
+    DevBuf basis; basis.pool = &c->pool;
+    CS_TRY(basis.ensure((size_t)(m + 3) * vb));
+    auto V = [&](int i) { return (void*)((char*)basis.p + (size_t)i * vb); };
+    void *w = V(m + 1), *tmp = V(m + 2);
+    const double* wts = (const double*)op->wts.p;
+    std::vector<zc> one(nvec, zc(1, 0)), mone(nvec, zc(-1, 0)), zero(nvec, zc(0, 0)), d;
+    size_t xb = (size_t)nvec * n * esz(cv);
+    // dots of w against V(0..j): one launch per basis vector, one D2H for all of them
+    DevBuf dots; dots.pool = &c->pool;
+    const size_t dstride = (size_t)2 * nvec * 260;
+    CS_TRY(dots.ensure((size_t)(m + 1) * dstride * sizeof(double)));
+    std::vector<double> hbuf((size_t)(m + 1) * 2 * nvec);
+    auto multi_dot = [&](int cnt, const void* ww, std::vector<std::vector<zc>>& out) -> int {
+        for (int i = 0; i < cnt; ++i)
+            CS_TRY(launch_dot(V(i), ww, n, nvec, cv, true, (double*)dots.p + (size_t)i * dstride, c->st));
+        for (int i = 0; i < cnt; ++i)
+            CS_CUDA(cudaMemcpyAsync(hbuf.data() + (size_t)i * 2 * nvec, (double*)dots.p + (size_t)i * dstride,
+                                    2 * nvec * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CS_CUDA(cudaStreamSynchronize(c->st));
+        g_launches += 2 * cnt;
+        out.assign(cnt, std::vector<zc>(nvec));
+        for (int i = 0; i < cnt; ++i) for (int v = 0; v < nvec; ++v) out[i][v] = zc(hbuf[(size_t)i * 2 * nvec + 2 * v], hbuf[(size_t)i * 2 * nvec + 2 * v + 1]);
+        return CS_OK;
+    };
+    std::vector<char> done(nvec, 0);
+    int it_used = 0;
+    while (it_used < maxit) {
+        // r = S (b - A x)
+        CS_TRY(K.apply(x, w));
+        CS_CUDA(cudaMemcpyAsync(tmp, rhs, xb, cudaMemcpyDeviceToDevice, c->st));
+        CS_TRY(K.axpby(tmp, w, mone, one));
+        CS_TRY(launch_mul_real(V(0), tmp, wts, n, nvec, cv, 2, c->st, K.sov_d));
+        CS_TRY(K.dots(V(0), V(0), true, d));
+        std::vector<double> beta(nvec);
+        worst = 0.0;
+        bool all = true;
+        std::vector<zc> inv(nvec);
+        for (int v = 0; v < nvec; ++v) {
+            beta[v] = std::sqrt(std::max(d[v].real(), 0.0));
+            double rel = bnorm[v] > 0 ? beta[v] / bnorm[v] : 0.0;
+            if (!(rel <= worst)) worst = rel;
+            done[v] = (rel <= tight) || beta[v] == 0.0;
+            if (!done[v]) all = false;
+            inv[v] = beta[v] > 0 ? zc(1.0 / beta[v], 0) : zc(0, 0);
+        }
+        if (all) break;
+        CS_TRY(K.axpby(V(0), V(0), inv, zero));
+        // per-system Hessenberg (column-major (m+1) x m), rotations, rhs g
+        std::vector<std::vector<zc>> H(nvec, std::vector<zc>((size_t)(m + 1) * m, zc(0, 0))), cs_(nvec, std::vector<zc>(m)), sn(nvec, std::vector<zc>(m)), g(nvec, std::vector<zc>(m + 1, zc(0, 0)));
+        for (int v = 0; v < nvec; ++v) g[v][0] = beta[v];
+        int j = 0;
+        for (; j < m && it_used < maxit; ++j) {
+            ++it_used; ++total_it;
+            // w = S A M^-1 S^-1 v_j
+            CS_TRY(launch_mul_real(tmp, V(j), wts, n, nvec, cv, 3, c->st, K.sov_d));
+            CS_TRY(K.precond(tmp, w));
+            CS_TRY(K.apply(w, tmp));
+            CS_TRY(launch_mul_real(w, tmp, wts, n, nvec, cv, 2, c->st, K.sov_d));
+            g_launches += 2;
+            std::vector<std::vector<zc>> h1, h2;
+            CS_TRY(multi_dot(j + 1, w, h1));
+            for (int i = 0; i <= j; ++i) { std::vector<zc> a(nvec); for (int v = 0; v < nvec; ++v) a[v] = -h1[i][v]; CS_TRY(K.axpby(w, V(i), a, one)); if ((i & 31) == 31) CS_CUDA(cudaStreamSynchronize(c->st)); }
+            CS_TRY(multi_dot(j + 1, w, h2));
+            for (int i = 0; i <= j; ++i) { std::vector<zc> a(nvec); for (int v = 0; v < nvec; ++v) a[v] = -h2[i][v]; CS_TRY(K.axpby(w, V(i), a, one)); if ((i & 31) == 31) CS_CUDA(cudaStreamSynchronize(c->st)); }
+            CS_TRY(K.dots(w, w, true, d));
+            bool all_small = true;
+            std::vector<zc> winv(nvec);
+            for (int v = 0; v < nvec; ++v) {
+                double hn = std::sqrt(std::max(d[v].real(), 0.0));
+                std::vector<zc>& Hv = H[v];
+                for (int i = 0; i <= j; ++i) Hv[(size_t)j * (m + 1) + i] = h1[i][v] + h2[i][v];
+                Hv[(size_t)j * (m + 1) + j + 1] = hn;
+                // apply previous rotations to the new column
+                for (int i = 0; i < j; ++i) {
+                    zc a = Hv[(size_t)j * (m + 1) + i], b = Hv[(size_t)j * (m + 1) + i + 1];
+                    Hv[(size_t)j * (m + 1) + i] = std::conj(cs_[v][i]) * a + std::conj(sn[v][i]) * b;
+                    Hv[(size_t)j * (m + 1) + i + 1] = -sn[v][i] * a + cs_[v][i] * b;
+                }
+                zc a = Hv[(size_t)j * (m + 1) + j], b = Hv[(size_t)j * (m + 1) + j + 1];
+                double den = std::sqrt(std::norm(a) + std::norm(b));
+                if (den == 0.0) { cs_[v][j] = 1; sn[v][j] = 0; }
+                else { cs_[v][j] = a / den; sn[v][j] = b / den; }
+                Hv[(size_t)j * (m + 1) + j] = std::conj(cs_[v][j]) * a + std::conj(sn[v][j]) * b;
+                Hv[(size_t)j * (m + 1) + j + 1] = 0;
+                zc gj = g[v][j];
+                g[v][j] = std::conj(cs_[v][j]) * gj;
+                g[v][j + 1] = -sn[v][j] * gj;
+                double rel = bnorm[v] > 0 ? std::abs(g[v][j + 1]) / bnorm[v] : 0.0;
+                if (!done[v] && rel > tight) all_small = false;
+                winv[v] = hn > 0 ? zc(1.0 / hn, 0) : zc(0, 0);
+            }
+            if (j + 1 < m + 1) { CS_TRY(K.axpby(V(j + 1), w, winv, zero)); }
+            if (all_small) { ++j; break; }
+        }
+        const int jj = std::min(j, m);
+        // y = H^-1 g ; u = V y ; x += M^-1 S^-1 u
+        std::vector<std::vector<zc>> y(nvec, std::vector<zc>(jj));
+        for (int v = 0; v < nvec; ++v)
+            for (int i = jj - 1; i >= 0; --i) {
+                zc acc = g[v][i];
+                for (int k2 = i + 1; k2 < jj; ++k2) acc -= H[v][(size_t)k2 * (m + 1) + i] * y[v][k2];
+                zc dgn = H[v][(size_t)i * (m + 1) + i];
+                y[v][i] = (std::abs(dgn) > 0) ? acc / dgn : zc(0, 0);
+            }
+        CS_CUDA(cudaMemsetAsync(w, 0, xb, c->st));
+        for (int i = 0; i < jj; ++i) { std::vector<zc> a(nvec); for (int v = 0; v < nvec; ++v) a[v] = y[v][i]; CS_TRY(K.axpby(w, V(i), a, one)); if ((i & 31) == 31) CS_CUDA(cudaStreamSynchronize(c->st)); }
+        CS_TRY(launch_mul_real(tmp, w, wts, n, nvec, cv, 3, c->st, K.sov_d));
+        CS_TRY(K.precond(tmp, w));
+        CS_TRY(K.axpby(x, w, one, one));
+        CS_CUDA(cudaStreamSynchronize(c->st));
+    }
+    // final true scaled residual
+    CS_TRY(K.apply(x, w));
+    CS_CUDA(cudaMemcpyAsync(tmp, rhs, xb, cudaMemcpyDeviceToDevice, c->st));
+    CS_TRY(K.axpby(tmp, w, mone, one));
+    CS_TRY(K.dots(tmp, tmp, true, d, true));
+    worst = 0.0;
+    for (int v = 0; v < nvec; ++v) {
+        double rel = bnorm[v] > 0 ? std::sqrt(std::max(d[v].real(), 0.0)) / bnorm[v] : 0.0;
+        if (!(rel <= worst)) worst = rel;
+    }
+    basis.release(); dots.release();
+    return CS_OK;
+}
+
 static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int* sov_h, bool cv,
                         double rtol, int maxit, double* info) {
     cs_ctx* c = op->ctx;
@@ -540,6 +676,11 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
     // stop at rtol but push to the fp64 floor (the systems are ill-conditioned, the
     // error is cond * residual), and stop when a round no longer gains a factor 10.
     const double tight = std::min(rtol, 1e-13);
+    // BiCGStab is meant for the (near-)exact preconditioner: 1-2 iterations.  If a round of
+    // bicg_cap iterations does not get there (theta-varying model: the theta-mode factors are
+    // only a circulant preconditioner) the robust restarted GMRES below takes over.
+    const int bicg_cap = std::min(maxit, 8);
+    bool want_gmres = false;
     for (int round = 0; round < 6; ++round) {
         // solve A dx = r by BiCGStab (right preconditioned), dx starts at 0
         CS_CUDA(cudaMemsetAsync(dx, 0, xb, c->st));
@@ -551,7 +692,7 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
         std::vector<double> rn(nvec);
         CS_TRY(K.dots(r, r, true, d1, true));
         for (int v = 0; v < nvec; ++v) { rn[v] = std::sqrt(std::max(d1[v].real(), 0.0)); if (bnorm[v] == 0.0 || rn[v] <= tight * bnorm[v]) done[v] = 1; }
-        for (int it = 0; it < maxit; ++it) {
+        for (int it = 0; it < bicg_cap; ++it) {
             bool any = false;
             for (int v = 0; v < nvec; ++v) any |= !done[v];
             if (!any) break;
@@ -620,7 +761,18 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
         }
         if (!(worst > 1e-15)) break;
         if (round > 0 && !(worst < 0.1 * prev_worst)) break;
+        if (round == 0 && !(worst < 1e-3) && maxit > bicg_cap) { want_gmres = true; break; }
         prev_worst = worst;
+    }
+    if (want_gmres) {
+        int rcg = gmres_solve(K, rhs, x, bnorm, std::max(0.1 * rtol, 1e-13), maxit - total_it, total_it, worst);
+        if (rcg != CS_OK) return rcg;
+        all_ok = (worst <= rtol);
+        // recompute the true residual into r for the floor test below
+        CS_TRY(K.apply(x, t));
+        CS_CUDA(cudaMemcpyAsync(r, rhs, xb, cudaMemcpyDeviceToDevice, c->st));
+        std::vector<zc> mone2(nvec, zc(-1, 0));
+        CS_TRY(K.axpby(r, t, mone2, one));
     }
     double eta_max = 0.0;
     if (!all_ok) {
@@ -835,17 +987,21 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
     cs_op* op = nullptr;
     CS_TRY(cs_op_get(c, form == 'h' ? CS_KIND_EDGE_H : CS_KIND_FACE_J, &op));
     long long n = op->n;
-    // how many frequencies fit at once
+    // how many frequencies fit at once (driver queries only when the cached buffers are too small:
+    // cudaMemGetInfo / cudaMalloc / cudaFree serialise against concurrent nvidia-smi polling)
     size_t per = (size_t)op->bp.nmodes * op->bp.band_elems() * sizeof(cplx);
-    size_t fr = 0, tot = 0;
-    CS_CUDA(cudaMemGetInfo(&fr, &tot));
-    fr += op->LU.bytes + c->pool.total();
     size_t vecs = (size_t)(8 + 2) * n * sizeof(cplx) + (size_t)op->bp.nmodes * op->bp.n2 * sizeof(cplx);
-    long long chunk = (long long)((0.8 * (double)fr) / (double)(per + vecs));
-    CS_CHECK(chunk >= 1, "not enough device memory for one frequency");
-    if (chunk > nfreq) chunk = nfreq;
-    if (chunk > 256) chunk = 256;
+    long long chunk = std::min(nfreq, 256);
+    if ((size_t)chunk * per > op->LU.bytes + c->pool.total()) {
+        size_t fr = 0, tot = 0;
+        CS_CUDA(cudaMemGetInfo(&fr, &tot));
+        fr += op->LU.bytes + c->pool.total();
+        long long fit = (long long)((0.8 * (double)fr) / (double)(per + vecs));
+        CS_CHECK(fit >= 1, "not enough device memory for one frequency");
+        if (chunk > fit) chunk = fit;
+    }
     DevBuf rhs;
+    rhs.pool = &c->pool;
     CS_TRY(rhs.ensure((size_t)chunk * n * sizeof(cplx)));
     double ms_fac = 0, ms_sol = 0, worst = 0, iters = 0;
     int rc = CS_OK;
@@ -908,6 +1064,7 @@ extern "C" int cs_tdem_run(cs_ctx* c, int form, const double* dts_h, int nsteps,
     CS_TRY(cs_op_get(c, CS_KIND_FACE_J, &op));
     double inf2[CS_INFO_LEN];
     DevBuf b1, b2, b3;
+    b1.pool = b2.pool = b3.pool = &c->pool;
     CS_TRY(b1.ensure((size_t)nC * 8)); CS_TRY(b2.ensure((size_t)nC * 8)); CS_TRY(b3.ensure((size_t)nF * 8));
     double ms_fac = 0, ms_sol = 0, worst = 0;
     // initial DC state: phi = Adc^-1 (Dt s_e); j0 = -MfRhoI Dt^T phi     (A.7)

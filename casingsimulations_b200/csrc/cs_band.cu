@@ -16,6 +16,7 @@
 // which is what the panel / update / solve kernels use.
 #include "cs_internal.h"
 #include <cuda_pipeline.h>
+#include <vector>
 
 namespace cs {
 
@@ -380,28 +381,76 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     if (m1 && n1) c01[16] = old11 - acc11;
 }
 
+// The factorisation is ~2 * n2 / NB tiny dependent launches (9 784 for the C2 sweep).  Issued
+// one by one they make the solve hostage to host-thread jitter, so the whole sequence is
+// captured once into a CUDA graph per (buffer, shape) and replayed with a single launch.
+struct FactorGraphKey {
+    void* LU; void* scratch; long long n2; int p, nsys, cplx;
+    bool operator==(const FactorGraphKey& o) const {
+        return LU == o.LU && scratch == o.scratch && n2 == o.n2 && p == o.p && nsys == o.nsys && cplx == o.cplx;
+    }
+};
+struct FactorGraph { FactorGraphKey key; cudaGraphExec_t exec; unsigned long long stamp; };
+static std::vector<FactorGraph> g_graphs;
+static unsigned long long g_stamp = 0;
+
 template <typename T>
-static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
+static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, cudaStream_t st) {
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
+    int tiles = (bp.p + 31) / 32;
+    int chunks = (bp.p + 63) / 64;
+    for (long long t = 0; t < bp.n2; t += NB) {
+        dim3 gp(chunks, nsys);
+        k_lu_panel<T><<<gp, 128, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch);
+        dim3 g(tiles, tiles, nsys);
+        k_lu_update<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
+    }
+    return CS_OK;
+}
+
+template <typename T>
+static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
     static void* scratch = nullptr;
     static size_t scratch_bytes = 0;
     size_t need = (size_t)nsys * NB * NB * sizeof(T);
     if (need > scratch_bytes) {
         if (scratch) cudaFree(scratch);
+        if (need < (1u << 20)) need = 1u << 20;
         CS_CUDA(cudaMalloc(&scratch, need));
         scratch_bytes = need;
     }
-    int tiles = (bp.p + 31) / 32;
-    int chunks = (bp.p + 63) / 64;
-    for (long long t = 0; t < bp.n2; t += NB) {
-        dim3 gp(chunks, nsys);
-        k_lu_panel<T><<<gp, 128, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (T*)scratch);
-        dim3 g(tiles, tiles, nsys);
-        k_lu_update<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
+    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx))};
+    for (auto& g : g_graphs)
+        if (g.key == key) {
+            g.stamp = ++g_stamp;
+            CS_CUDA(cudaGraphLaunch(g.exec, st));
+            return CS_OK;
+        }
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool captured = false;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        band_factor_enqueue<T>(bp, LU, nsys, (T*)scratch, st);
+        if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph &&
+            cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) captured = true;
+        if (graph) cudaGraphDestroy(graph);
     }
-    CS_CUDA(cudaGetLastError());
+    if (!captured) {
+        cudaGetLastError();                 // capture unavailable: plain launches (same kernels)
+        CS_TRY(band_factor_enqueue<T>(bp, LU, nsys, (T*)scratch, st));
+        CS_CUDA(cudaGetLastError());
+        return CS_OK;
+    }
+    if (g_graphs.size() >= 6) {             // keep a handful of shapes
+        size_t old = 0;
+        for (size_t i = 1; i < g_graphs.size(); ++i) if (g_graphs[i].stamp < g_graphs[old].stamp) old = i;
+        cudaGraphExecDestroy(g_graphs[old].exec);
+        g_graphs.erase(g_graphs.begin() + old);
+    }
+    g_graphs.push_back({key, exec, ++g_stamp});
+    CS_CUDA(cudaGraphLaunch(exec, st));
     return CS_OK;
 }
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st) {

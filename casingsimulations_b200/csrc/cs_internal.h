@@ -42,7 +42,9 @@ int launch_dot(const void* a, const void* b, long long n, int nsys, bool cplx_ve
 // y = a*x + b*y with per-system complex scalars (host arrays of 2 doubles per system)
 int launch_axpby(void* y, const void* x, long long n, int nsys, bool cplx_vec, const double* a_d, const double* b_d, cudaStream_t st);
 // z = x .* w (w real, shared by all systems), optionally reciprocal
-int launch_mul_real(void* z, const void* x, const double* w, long long n, int nsys, bool cplx_vec, int recip, cudaStream_t st);
+// mode: 0 w, 1 1/w, 2 sqrt(w), 3 1/sqrt(w); wsel (optional, device) picks the weight row per system
+int launch_mul_real(void* z, const void* x, const double* w, long long n, int nsys, bool cplx_vec, int mode, cudaStream_t st,
+                    const int* wsel = nullptr);
 int launch_real_to_cplx(const double* x, cplx* z, long long n, cudaStream_t st);
 
 // -------- cs_band.cu : theta-DFT + banded direct solves (preconditioner) -----------

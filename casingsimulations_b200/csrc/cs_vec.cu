@@ -109,18 +109,24 @@ int launch_axpby(void* y, const void* x, long long n, int nsys, bool cplx_vec, c
     return CS_OK;
 }
 
+// mode: 0 w, 1 1/w, 2 sqrt(w), 3 1/sqrt(w); wsel (optional) picks the weight row per system
 template <typename T>
-__global__ void k_mul_real(T* __restrict__ z, const T* __restrict__ x, const double* __restrict__ w, long long n, int recip) {
+__global__ void k_mul_real(T* __restrict__ z, const T* __restrict__ x, const double* __restrict__ w, long long n, int mode,
+                           const int* __restrict__ wsel) {
     int sys = blockIdx.y;
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n) return;
-    double ww = recip ? 1.0 / w[t] : w[t];
+    double ww = w[(wsel ? (long long)wsel[sys] * n : 0) + t];
+    if (mode == 1) ww = 1.0 / ww;
+    else if (mode == 2) ww = sqrt(ww);
+    else if (mode == 3) ww = rsqrt(ww);
     z[sys * n + t] = ww * x[sys * n + t];
 }
-int launch_mul_real(void* z, const void* x, const double* w, long long n, int nsys, bool cplx_vec, int recip, cudaStream_t st) {
+int launch_mul_real(void* z, const void* x, const double* w, long long n, int nsys, bool cplx_vec, int recip, cudaStream_t st,
+                    const int* wsel) {
     dim3 g((unsigned)cdiv(n, TPB), nsys);
-    if (cplx_vec) k_mul_real<cplx><<<g, TPB, 0, st>>>((cplx*)z, (const cplx*)x, w, n, recip);
-    else k_mul_real<double><<<g, TPB, 0, st>>>((double*)z, (const double*)x, w, n, recip);
+    if (cplx_vec) k_mul_real<cplx><<<g, TPB, 0, st>>>((cplx*)z, (const cplx*)x, w, n, recip, wsel);
+    else k_mul_real<double><<<g, TPB, 0, st>>>((double*)z, (const double*)x, w, n, recip, wsel);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

@@ -271,3 +271,63 @@ def test_full_size_c3_dc_3d_properties():
     lin = phia[0] - phi[1]
     assert float(torch.linalg.norm(lin - phi[0]) / torch.linalg.norm(phi[0])) < 1e-6
     ctx.close()
+
+
+def test_theta_varying_flawed_casing_krylov(tmp_path):
+    """A flawed casing (theta-limited flaw, model.py:583-668) breaks the block-circulant structure:
+    the theta-mode factorisation (built from the theta = 0 column) is then only a preconditioner
+    and BiCGStab has to do real work.  Parity against the oracle on the same 3-D mesh."""
+    tmp = str(tmp_path / "flaw")
+    nth = 8
+    mp = cs.model.FlawedCasingInHalfspace(directory=tmp, sigma_back=1e-1, src_a=np.r_[0.0, 0.0, 0.0],
+                                          src_b=np.r_[1000.0, 0.0, 0.0], freqs=np.r_[5.0], casing_l=100.0,
+                                          flaw_r=np.r_[0.04, 0.06], flaw_z=np.r_[-60.0, -40.0],
+                                          flaw_theta=np.r_[np.pi / 2, np.pi], sigma_flaw=1e-1)
+    mg = cs.CasingMeshGenerator(directory=tmp, modelParameters=mp, hy=np.ones(nth) * 2 * np.pi / nth, npadx=4, npadz=5, csz=10.0)
+    th = mg.mesh.vectorCCy[0]
+    mp.src_a, mp.src_b = np.r_[0.0, th, 0.0], np.r_[1000.0, th, 0.0]
+    assert mp.paint_params() is None                      # painted through sigma()/mur(), uploaded with cs_model_set
+    m = mg.mesh
+    sig = mp.sigma(m).reshape(tuple(m.vnC), order="F")
+    assert np.ptp(sig, axis=1).max() > 0                  # genuinely theta-dependent
+    # DC
+    a = np.array([[0.05125, th, -5.0]])
+    b = np.array([[500.0, th, -5.0]])
+    sim = run.SimulationDC(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a, src_b=b,
+                           solver_opts=dict(maxit=300, rtol=1e-7))
+    f = sim.run(save=False)
+    info = sim.prob.info
+    print("flawed DC info", info)
+    assert info["iters"] >= 2                              # not a one-shot direct solve any more
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, OracleFDEM
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    P = OracleDC(om, mp.sigma(m))
+    phi_lu, phi = P.fields(a, b), P.fields(a, b, refine=True)
+    err = rel(f[:, "phi"], phi)
+    print("flawed DC gpu vs truth", err, "splu vs truth", rel(phi_lu, phi))
+    assert err < max(1e-4, 10 * rel(phi_lu, phi))
+    sim.prob.clean()
+    # FDEM-h
+    src = sources.TopCasingSrc(directory=tmp, modelParameters=mp, meshGenerator=mg)
+    simf = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src, solver_opts=dict(maxit=300, rtol=1e-7))
+    ff = simf.run(save=False)
+    print("flawed FDEM info", simf.prob.info)
+    Pf = OracleFDEM(om, mp.sigma(m), mp.mu(m))
+    s = simf.survey.srcList[0]
+    h_lu, h_true = Pf.solve(s.freq, np.real(s.s_e)), Pf.solve(s.freq, np.real(s.s_e), refine=True)
+    j_lu, j_true = Pf.j_from(s.freq, h_lu, np.real(s.s_e)), Pf.j_from(s.freq, h_true, np.real(s.s_e))
+    jg = ff[s, "j"][:, 0]
+    A, rhs = Pf.getA(s.freq), Pf.getRHS(s.freq, np.real(s.s_e))
+    d = np.sqrt(np.abs(A.diagonal()))
+    res = np.linalg.norm((A @ ff[s, "h"][:, 0] - rhs) / d) / np.linalg.norm(rhs / d)
+    print("flawed FDEM scaled residual", res, "j gpu vs splu", rel(jg, j_lu), "gpu vs refined", rel(jg, j_true),
+          "splu vs refined", rel(j_lu, j_true))
+    assert res < 1e-6
+    # the extended-precision refinement does not always converge for this 3-D system (SuperLU's
+    # factors are too inaccurate); compare with whichever reference is self-consistent
+    # (measured: refinement diverges here; GPU (scaled residual 7e-10) and SuperLU disagree by
+    # 7 % in j -- the 5 Hz 3-D curl-curl system with 2.5 mm air cells is beyond fp64 for a direct
+    # solve, cf. DESIGN.md section 2.1).  The residual is the hard criterion, j only a sanity bound.
+    ref = j_true if rel(j_lu, j_true) < 1e-2 else j_lu
+    assert rel(jg, ref) < 0.2
+    simf.prob.clean()
