@@ -372,7 +372,7 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
     const T zero = Sc<T>::zero();
 
     // ---- staging descriptors: which tile elements this thread copies every level ----------
-    constexpr int NQ = 3;                               // ceil(tsz / nthr) <= 3 for every configuration used
+    constexpr int NQ = SYM ? 2 : 2;                     // ceil(tsz / nthr) <= 2 for every configuration used (checked on the host)
     int eoff[NQ]; long long cb[NQ]; long long zb[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -395,20 +395,21 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
     auto load_stage = [&](int sl) {
         if (sl > m.nz) return;                          // beyond the top node level: nothing to load
         T* st = stage + (size_t)(sl % EDGE_NS) * ncomp * tsz;
+        const long long onode = m.nxy * sl, ocell = m.ezp * sl;
+        const bool zlev = (!SYM) && sl < m.nz;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            if (eoff[q] < 0) continue;
-            int e = eoff[q];
+            const int e = eoff[q];
+            if (e < 0) continue;
             if (cb[q] >= 0) {
-                long long c = cb[q] + m.nxy * sl;
-                __pipeline_memcpy_async(st + e, Y + c, sizeof(T));
-                if (!SYM) __pipeline_memcpy_async(st + tsz + e, X + c, sizeof(T));
+                __pipeline_memcpy_async(st + e, Y + cb[q] + onode, sizeof(T));
+                if (!SYM) __pipeline_memcpy_async(st + tsz + e, X + cb[q] + onode, sizeof(T));
             } else {
                 st[e] = zero;
                 if (!SYM) st[tsz + e] = zero;
             }
-            if (!SYM && sl < m.nz) {
-                if (zb[q] >= 0) __pipeline_memcpy_async(st + 2 * tsz + e, Z + sl * m.ezp + zb[q], sizeof(T));
+            if (zlev) {
+                if (zb[q] >= 0) __pipeline_memcpy_async(st + 2 * tsz + e, Z + ocell + zb[q], sizeof(T));
                 else st[2 * tsz + e] = zero;
             }
         }
@@ -429,23 +430,25 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
     __pipeline_wait_prior(1);                            // stages kbeg, kbeg+1 landed
     __syncthreads();
     const int so = (SYM ? 0 : row) * TW + li;            // (row, lane-1) inside a staged array; +1 = own lane
-    for (int k = kbeg; k < k1; ++k) {
+    long long cnode = col + m.nxy * kbeg, ccell = (long long)kbeg * m.ezp + ezc;   // running offsets of level k
+    for (int k = kbeg; k < k1; ++k, cnode += m.nxy, ccell += m.ezp) {
         const bool cell = (k < m.nz);
         load_stage(k + 3);
         __pipeline_commit();
         // prefetch next level's weights into registers
         double wzn = 0.0, wxn = 0.0, wyn = 0.0, byn = 0.0, bxn = 0.0, bzn = 0.0;
         if (valid && k + 1 < k1) {
-            long long c = col + m.nxy * (k + 1);
+            const long long c = cnode + m.nxy;
             wzn = wz[c];
             byn = by[c];
             if (!SYM) bxn = bx[c];
-            if (k + 1 < m.nz) { wxn = wx[c]; if (!SYM) { wyn = wy[c]; bzn = bz[(k + 1) * m.ezp + ezc]; } }
+            if (k + 1 < m.nz) { wxn = wx[c]; if (!SYM) { wyn = wy[c]; bzn = bz[ccell + m.ezp]; } }
         }
         const T* sk = stage + (size_t)(k % EDGE_NS) * ncomp * tsz;
         const T* sk1 = stage + (size_t)((k + 1) % EDGE_NS) * ncomp * tsz;
         T* fx = fxb + (size_t)(k & 1) * 3 * rows * TI;
         T tFx = zero, tFy = zero, tFz = zero, Xk = zero, Zk = zero;
+        const double lez = (!SYM && cell) ? m.lEz(k) : 0.0;
         T Yk = sk[so + 1];
         if (valid) {
             T Yim = sk[so];
@@ -459,7 +462,6 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
                 T Yk1 = sk1[so + 1];
                 T cfx = (-ley) * (Yk1 - Yk);
                 if (!SYM) {
-                    const double lez = m.lEz(k);
                     T Xk1 = sk1[tsz + so + 1];
                     Zk = sk[2 * tsz + so + 1];
                     T Zjp = sk[2 * tsz + so + TW + 1];
@@ -478,7 +480,7 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
         __pipeline_wait_prior(1);                        // stages <= k+2 landed
         __syncthreads();
         if (out_ok && k >= k0) {
-            const long long c = col + m.nxy * k;
+            const long long c = cnode;
             T tFz_ip = has_ip ? fx[(2 * rows + row) * TI + li + 1] : zero;
             {
                 T r = tFx - tFxp + tFz - tFz_ip;
@@ -492,7 +494,7 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
                     T tFx_jm = fx[(0 * rows + row - 1) * TI + li];
                     T tFy_ip = has_ip ? fx[(1 * rows + row) * TI + li + 1] : zero;
                     T r2 = tFx_jm - tFx - tFy + tFy_ip;
-                    YZ[k * m.ezp + ezc] = m.lEz(k) * r2 + s * (bzk * Zk);
+                    YZ[ccell] = lez * r2 + s * (bzk * Zk);
                 }
             }
         }
@@ -551,7 +553,7 @@ static int launch_edge_op_cfg(const MeshD& m, const double* wF, const double* be
     int rows = SYM ? 1 : tj + 1;
     int trows = SYM ? 1 : rows + 1, ncomp = SYM ? 1 : 3;
     size_t smb = ((size_t)EDGE_NS * ncomp * trows * (TI + 1) + 2 * 3 * (size_t)rows * TI) * sizeof(T);
-    CS_CHECK(trows * (TI + 1) <= 3 * TI * rows, "staging descriptor count too small");
+    CS_CHECK(trows * (TI + 1) <= 2 * TI * rows, "staging descriptor count too small");
     dim3 blk(TI, rows), grd(itiles, jtiles, nchunk * nsys);
     static bool attr_set = false;                // one flag per template instantiation
     if (!attr_set) {
