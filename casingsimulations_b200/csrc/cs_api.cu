@@ -78,6 +78,7 @@ struct cs_op {
     long long* csr_indptr = nullptr; int* csr_indices = nullptr; void* csr_vals = nullptr; long long csr_nnz = 0;
     BandPlan bp;
     DevBuf kband;                 // storage behind bp.Kband (pooled)
+    DevBuf bw1, bw2, bmass, bmap, bjstr, bmdiag;   // pooled storage behind w1 / w2 / mass / band maps
     DevBuf LU, wts;               // wts: [nshift][n] = 1/|diag A(s)|, the norm of the convergence tests
     bool lu_cplx = false;
     std::vector<zc> shifts;
@@ -97,16 +98,16 @@ struct cs_ctx {
     std::map<int, cs_op*> ops;
     DevBuf work, scal, modes, tmp1, tmp2;
     Pool pool;
+    std::vector<std::pair<std::vector<unsigned long long>, cudaGraphExec_t>> probe_graphs;
     double* pin = nullptr;         // pinned host scratch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 static void op_free(cs_op* op) {
     if (!op) return;
-    cudaFree(op->w1); cudaFree(op->w2);
+    op->bw1.release(); op->bw2.release(); op->bmass.release();
     cudaFree(op->csr_indptr); cudaFree(op->csr_indices); cudaFree(op->csr_vals);
-    if (op->family == 2 && !op->is_csr) cudaFree(op->mass);   // edge family: mass aliases w2
-    cudaFree(op->bp.map3d); cudaFree(op->bp.jstr); cudaFree(op->bp.mdiag);
+    op->bmap.release(); op->bjstr.release(); op->bmdiag.release();
     op->kband.release(); op->bp.Kband = nullptr;
     op->LU.release(); op->wts.release();
     delete op;
@@ -266,9 +267,11 @@ static int build_plan(cs_op* op) {
     bp.ldab = 2 * bp.pw + 1;
     bp.nmodes = nth;
     bp.cplx_band = (nth > 1) || op->csr_cplx;
-    CS_CUDA(cudaMalloc(&bp.map3d, bp.n2 * sizeof(long long)));
-    CS_CUDA(cudaMalloc(&bp.jstr, bp.n2 * sizeof(int)));
-    CS_CUDA(cudaMalloc(&bp.mdiag, bp.n2 * sizeof(double)));
+    op->bmap.pool = op->bjstr.pool = op->bmdiag.pool = &c->pool;
+    CS_TRY(op->bmap.ensure(bp.n2 * sizeof(long long)));
+    CS_TRY(op->bjstr.ensure(bp.n2 * sizeof(int)));
+    CS_TRY(op->bmdiag.ensure(bp.n2 * sizeof(double)));
+    bp.map3d = (long long*)op->bmap.p; bp.jstr = (int*)op->bjstr.p; bp.mdiag = (double*)op->bmdiag.p;
     CS_CUDA(cudaMemcpyAsync(bp.map3d, map.data(), bp.n2 * sizeof(long long), cudaMemcpyHostToDevice, c->st));
     CS_CUDA(cudaMemcpyAsync(bp.jstr, js.data(), bp.n2 * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CS_CUDA(cudaStreamSynchronize(c->st));
@@ -293,15 +296,38 @@ static int probe_plan(cs_op* op) {
     CS_TRY(c->scal.ensure(4096));
     CS_CUDA(cudaMemsetAsync(c->scal.p, 0, 4096, c->st));     // shift 0
     int ncol = 2 * bp.p + 1;
-    double sh0 = op->shift0;
-    for (int col = 0; col < ncol; ++col) {
-        CS_TRY(band_probe_fill(bp, col, c->tmp1.p, op->n, cv, c->st));
-        CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, 1, cv));
-        CS_TRY(band_dft_gather(bp, c->tmp2.p, cv, c->modes.p, cv, bp.nmodes, op->n, 1, c->st));
-        CS_TRY(band_probe_store(bp, col, c->modes.p, c->st));
-        g_launches += 4;
+    // ~4 * (2p+1) tiny launches: replay them as one cached CUDA graph (keyed by every pointer
+    // and size baked into the launches) so that host jitter cannot stretch the assembly
+    std::vector<unsigned long long> key = {(unsigned long long)c->tmp1.p, (unsigned long long)c->tmp2.p, (unsigned long long)c->modes.p,
+        (unsigned long long)c->scal.p, (unsigned long long)bp.Kband, (unsigned long long)bp.map3d, (unsigned long long)bp.jstr,
+        (unsigned long long)op->w1, (unsigned long long)op->w2, (unsigned long long)op->csr_vals, (unsigned long long)op->kind,
+        (unsigned long long)bp.n2, (unsigned long long)bp.p, (unsigned long long)bp.nmodes, (unsigned long long)op->n,
+        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables};
+    g_launches += 4LL * ncol;
+    for (auto& g : c->probe_graphs)
+        if (g.first == key) { CS_CUDA(cudaGraphLaunch(g.second, c->st)); return CS_OK; }
+    auto enqueue = [&]() -> int {
+        for (int col = 0; col < ncol; ++col) {
+            CS_TRY(band_probe_fill(bp, col, c->tmp1.p, op->n, cv, c->st));
+            CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, 1, cv));
+            CS_TRY(band_dft_gather(bp, c->tmp2.p, cv, c->modes.p, cv, bp.nmodes, op->n, 1, c->st));
+            CS_TRY(band_probe_store(bp, col, c->modes.p, c->st));
+        }
+        return CS_OK;
+    };
+    // warm the per-kernel attribute setup outside of capture (cudaFuncSetAttribute is not capturable)
+    CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, 1, cv));
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; bool ok = false;
+    if (cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        int rcq = enqueue();
+        if (cudaStreamEndCapture(c->st, &graph) == cudaSuccess && graph && rcq == CS_OK &&
+            cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) ok = true;
+        if (graph) cudaGraphDestroy(graph);
     }
-    (void)sh0;
+    if (!ok) { cudaGetLastError(); return enqueue(); }
+    if (c->probe_graphs.size() >= 6) { cudaGraphExecDestroy(c->probe_graphs.front().second); c->probe_graphs.erase(c->probe_graphs.begin()); }
+    c->probe_graphs.push_back({key, exec});
+    CS_CUDA(cudaGraphLaunch(exec, c->st));
     return CS_OK;
 }
 
@@ -325,14 +351,20 @@ static int op_get(cs_ctx* c, int kind, bool with_plan, cs_op** out) {
     double* t1 = (double*)c->tmp1.p;
     int rc = CS_OK;
     auto fail = [&](int r) { op_free(op); return r; };
+    op->bw1.pool = op->bw2.pool = op->bmass.pool = &c->pool;
+    auto palloc = [&](DevBuf& b, double** dst, long long cnt) -> bool {
+        if (b.ensure((size_t)cnt * sizeof(double)) != CS_OK) return false;
+        *dst = (double*)b.p;
+        return true;
+    };
     if (kind == CS_KIND_DC || kind == CS_KIND_DC_GROUNDED) {
         op->family = 0; op->n = m.nC; op->shift0 = (kind == CS_KIND_DC_GROUNDED) ? 1.0 : 0.0;
-        if (cudaMalloc(&op->w1, m.nF * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(CS_ERR); }
+        if (!palloc(op->bw1, &op->w1, m.nF)) return fail(CS_ERR);
         rc = launch_face_ip(m, c->sigma, 1, 0, t1, c->st); if (rc) return fail(rc);       // MfRho
         rc = launch_face_scale(m, t1, op->w1, 0, c->st); if (rc) return fail(rc);         // area^2 / MfRho
     } else if (kind == CS_KIND_EDGE_H || kind == CS_KIND_EDGE_E) {
         op->family = 1; op->n = m.nE;
-        if (cudaMalloc(&op->w1, m.nF * sizeof(double)) != cudaSuccess || cudaMalloc(&op->w2, m.nE * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(CS_ERR); }
+        if (!palloc(op->bw1, &op->w1, m.nF) || !palloc(op->bw2, &op->w2, m.nE)) return fail(CS_ERR);
         const double* pa = (kind == CS_KIND_EDGE_H) ? c->sigma : c->mu;     // alpha = Mf(1/prop)
         const double* pb = (kind == CS_KIND_EDGE_H) ? c->mu : c->sigma;     // beta  = Me(prop)
         rc = launch_face_ip(m, pa, 1, 0, t1, c->st); if (rc) return fail(rc);
@@ -341,8 +373,7 @@ static int op_get(cs_ctx* c, int kind, bool with_plan, cs_op** out) {
         op->mass = op->w2;
     } else if (kind == CS_KIND_FACE_J || kind == CS_KIND_FACE_B) {
         op->family = 2; op->n = m.nF;
-        if (cudaMalloc(&op->w1, m.nF * sizeof(double)) != cudaSuccess || cudaMalloc(&op->w2, m.nE * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&op->mass, m.nF * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(CS_ERR); }
+        if (!palloc(op->bw1, &op->w1, m.nF) || !palloc(op->bw2, &op->w2, m.nE) || !palloc(op->bmass, &op->mass, m.nF)) return fail(CS_ERR);
         const double* pa = (kind == CS_KIND_FACE_J) ? c->sigma : c->mu;     // alpha = Mf(1/prop)
         const double* pg = (kind == CS_KIND_FACE_J) ? c->mu : c->sigma;     // gamma = 1/Me(prop)
         rc = launch_face_ip(m, pa, 1, 0, op->mass, c->st); if (rc) return fail(rc);       // alpha
@@ -759,7 +790,7 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
             if (!(rel <= rtol)) all_ok = false;
             if (!(rel <= worst)) worst = rel;   // also catches NaN
         }
-        if (!(worst > 1e-15)) break;
+        if (!(worst > std::min(1e-3 * rtol, 1e-13))) break;      // >= 3 digits below the target: done
         if (round > 0 && !(worst < 0.1 * prev_worst)) break;
         if (round == 0 && !(worst < 1e-3) && maxit > bicg_cap) { want_gmres = true; break; }
         prev_worst = worst;
@@ -858,6 +889,7 @@ extern "C" int cs_ctx_destroy(cs_ctx* c) {
     cudaFree(c->tables); cudaFree(c->sigma); cudaFree(c->mu);
     c->work.release(); c->scal.release(); c->modes.release(); c->tmp1.release(); c->tmp2.release();
     c->pool.clear();
+    for (auto& g : c->probe_graphs) cudaGraphExecDestroy(g.second);
     cudaFreeHost(c->pin);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->st);
