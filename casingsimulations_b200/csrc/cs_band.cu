@@ -381,6 +381,55 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     if (m1 && n1) c01[16] = old11 - acc11;
 }
 
+// After the factorisation every NB x NB diagonal block holds L11 \ U11.  The triangular solves
+// with those blocks are the sequential heart of the substitution kernels, so they are replaced
+// once, here (fully parallel: one warp per block), by the explicit inverses
+//   strictly lower part <- inv(L11) (unit diagonal implicit),  upper part <- inv(U11),
+// which turns every block step of k_band_solve into two small dependency-free mat-vecs.
+template <typename T>
+__global__ void k_invert_diag(T* __restrict__ LU, size_t nel, long long n2, int pw, int ld) {
+    __shared__ T D[NB][NB + 1];
+    T* A = LU + (size_t)blockIdx.y * nel + pw;
+    long long t = (long long)blockIdx.x * NB;
+    int nbe = (int)min((long long)NB, n2 - t);
+    int lane = threadIdx.x;
+    for (int e = lane; e < NB * NB; e += 32) {
+        int r = e % NB, c = e / NB;
+        T val = (r == c) ? Sc<T>::one() : Sc<T>::zero();
+        if (r < nbe && c < nbe) val = A[(t + r) + (t + c) * (long long)ld];
+        D[r][c] = val;
+    }
+    __syncwarp();
+    T xl[NB], xu[NB];
+    int j = lane & 15;
+    // column j of inv(L), L unit lower
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        T acc = (r == j) ? Sc<T>::one() : Sc<T>::zero();
+#pragma unroll
+        for (int k = 0; k < r; ++k) if (k >= j) acc -= D[r][k] * xl[k];
+        xl[r] = (r >= j) ? acc : Sc<T>::zero();
+    }
+    // column j of inv(U), U upper with diagonal
+#pragma unroll
+    for (int r = NB - 1; r >= 0; --r) {
+        T acc = (r == j) ? Sc<T>::one() : Sc<T>::zero();
+#pragma unroll
+        for (int k = r + 1; k < NB; ++k) if (k <= j) acc -= D[r][k] * xu[k];
+        xu[r] = (r <= j) ? acc * Sc<T>::inv(D[r][r]) : Sc<T>::zero();
+    }
+    __syncwarp();
+    if (lane < NB && j < nbe) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+            if (r < nbe) {
+                if (r > j) A[(t + r) + (t + j) * (long long)ld] = xl[r];
+                else A[(t + r) + (t + j) * (long long)ld] = xu[r];
+            }
+        }
+    }
+}
+
 // The factorisation is ~2 * n2 / NB tiny dependent launches (9 784 for the C2 sweep).  Issued
 // one by one they make the solve hostage to host-thread jitter, so the whole sequence is
 // captured once into a CUDA graph per (buffer, shape) and replayed with a single launch.
@@ -406,6 +455,8 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
         dim3 g(tiles, tiles, nsys);
         k_lu_update<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
     }
+    dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
+    k_invert_diag<T><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
     return CS_OK;
 }
 
@@ -464,158 +515,184 @@ int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaSt
 // prefetched into shared memory with cp.async while step s computes (double
 // buffer); the active window of the right-hand side lives in a circular
 // shared-memory buffer, so the sequential critical path touches no global memory.
-template <typename TL>
+// Thread layout of k_band_solve: 4 threads per staged row (quarter q = tid & 3 owns block
+// columns q, q+4, q+8, q+12), so a block step is 4 cp.async + 4 complex FMAs + a 2-stage
+// shuffle reduction per thread instead of 16 + 16 sequential ones, and ~14 warps share the SM.
+template <typename TL, int TPR>
 __device__ __forceinline__ void prefetch_cols(TL* __restrict__ dst, int ldd, const TL* __restrict__ A, int ld,
                                               long long row0, int nrows, long long col0, int ncols) {
     // dst[r + c*ldd] = A[(row0 + r) + (col0 + c)*ld]
-    int tot = nrows * ncols;
-    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
-        int r = e % nrows, c = e / nrows;
-        __pipeline_memcpy_async(dst + r + c * ldd, A + (row0 + r) + (col0 + c) * (long long)ld, sizeof(TL));
+    const int r = threadIdx.x / TPR, q = threadIdx.x % TPR;
+    if (r < nrows) {
+        const TL* src = A + (row0 + r) + col0 * (long long)ld;
+        TL* d = dst + r;
+#pragma unroll
+        for (int i = 0; i < NB / TPR; ++i) {
+            int c = q + TPR * i;
+            if (c < ncols) __pipeline_memcpy_async(d + c * ldd, src + c * (long long)ld, sizeof(TL));
+        }
     }
 }
 
-template <typename TL, typename TV>
-__global__ void k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz) {
+template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int m);
+template <> __device__ __forceinline__ double shfl_xor_t<double>(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ cplx shfl_xor_t<cplx>(cplx v, int m) {
+    return mk(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
+template <typename TL, typename TV, int TPR>
+__global__ void __launch_bounds__(TPR == 1 ? 1024 : 512)
+k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
+                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int v = blockIdx.y, m = blockIdx.x;
     int f = shift_of_vec ? shift_of_vec[v] : 0;
     const TL* A = LU + ((size_t)f * nmodes + m) * nel + pw;
     TV* b = xm + ((size_t)v * nmodes + m) * n2;
     const int ldd = NB + p;                                   // rows per staged block column
-    TL* buf0 = reinterpret_cast<TL*>(smem_raw);
-    TL* buf1 = buf0 + (size_t)ldd * NB;
-    TV* win = reinterpret_cast<TV*>(buf1 + (size_t)ldd * NB); // circular window, wsz = power of two >= p + 2 NB
-    __shared__ TV y1[NB];
-    int tid = threadIdx.x, lane = tid & 31;
+    const size_t ssz = (size_t)ldd * NB;                      // elements per stage
+    TL* ring = reinterpret_cast<TL*>(smem_raw);               // [nst][NB][ldd]
+    TV* win = reinterpret_cast<TV*>(ring + (size_t)nst * ssz);   // circular window, wsz = power of two >= p + 5 NB
+    __shared__ TV yw[32][NB];                                 // per-warp copy of the block solution
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r16 = lane & 15, half = lane >> 4;              // block mat-vec: lane <-> (row, column parity)
+    const int urow = tid / TPR, uq = tid % TPR;               // window update: thread <-> (row, column group)
     const int wm = wsz - 1;
-    long long nsteps = (n2 + NB - 1) / NB;
+    const long long nsteps = (n2 + NB - 1) / NB;
+    const TV zero = Sc<TV>::zero();
 
-    // ================= forward: L y = b (unit lower) =================
-    for (int e = tid; e < NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
-    {
-        int nbe = (int)min((long long)NB, n2);
-        int R = (int)min((long long)p, n2 - nbe);
-        prefetch_cols<TL>(buf0, ldd, A, ld, 0, nbe + R, 0, nbe);
-        __pipeline_commit();
-    }
-    for (long long s = 0; s < nsteps; ++s) {
-        long long t = s * NB;
-        int nbe = (int)min((long long)NB, n2 - t);
-        int R = (int)min((long long)p, n2 - (t + nbe));
-        TL* cur = (s & 1) ? buf1 : buf0;
-        TL* nxt = (s & 1) ? buf0 : buf1;
-        if (s + 1 < nsteps) {
-            long long t2 = t + NB;
+    // ================= forward: L y = b (unit lower; diagonal blocks hold inv(L11)) =================
+    auto fwd_prefetch = [&](long long s) {
+        if (s < nsteps) {
+            long long t2 = s * NB;
             int nbe2 = (int)min((long long)NB, n2 - t2);
             int R2 = (int)min((long long)p, n2 - (t2 + nbe2));
-            prefetch_cols<TL>(nxt, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
+            prefetch_cols<TL, TPR>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
         }
         __pipeline_commit();
-        // rows entering the window this step: t + NB + p .. t + 2 NB + p - 1 (first touched next step)
-        for (long long e = t + NB + p + tid; e < t + 2 * NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
-        __pipeline_wait_prior(1);
-        __syncthreads();
-        if (tid < 32) {
-            TV br = (lane < nbe) ? win[(t + lane) & wm] : Sc<TV>::zero();
+    };
+    for (int e = tid; e < 2 * NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
+    for (int q = 0; q < nst - 1; ++q) fwd_prefetch(q);
+    for (long long s = 0; s < nsteps; ++s) {
+        const long long t = s * NB;
+        const int nbe = (int)min((long long)NB, n2 - t);
+        const int R = (int)min((long long)p, n2 - (t + nbe));
+        const TL* cur = ring + (size_t)(s % nst) * ssz;
+        __pipeline_wait_prior(nst - 2);                       // stage s has landed
+        __syncthreads();                                      // ... and is visible; window of step s-1 complete
+        fwd_prefetch(s + nst - 1);                            // refills the slot step s-1 just released
+        // rows entering the window (first touched at step s+1): t + 2 NB + p .. t + 3 NB + p - 1
+        if (tid < NB) { long long e = t + 2 * NB + p + tid; if (e < n2) win[e & wm] = b[e]; }
+        // every warp computes y1 = inv(L11) b1 for itself: lane (r, half) sums the columns of its parity
+        TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
 #pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                TV yc = shfl_t<TV>(br, c);
-                if (lane > c && lane < nbe) br -= cur[lane + c * ldd] * yc;
+        for (int i = 0; i < NB / 2; ++i) {
+            int c = 2 * i + half;
+            if (c < r16) yr += cur[r16 + c * ldd] * win[(t + c) & wm];
+        }
+        yr += shfl_xor_t<TV>(yr, 16);
+        if (lane < NB) yw[warp][lane] = yr;
+        __syncwarp();
+        if (warp == 0 && lane < nbe) b[t + lane] = yr;
+        // window update: row (nbe + urow) of the staged block, 4 threads per row
+        TV acc = zero;
+        if (urow < R) {
+#pragma unroll
+            for (int i = 0; i < NB / TPR; ++i) {
+                int c = uq + TPR * i;
+                if (c < nbe) acc += cur[(nbe + urow) + c * ldd] * yw[warp][c];
             }
-            if (lane < nbe) { y1[lane] = br; b[t + lane] = br; }
         }
-        __syncthreads();
-        if (tid < R) {
-            TV acc = win[(t + nbe + tid) & wm];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) if (c < nbe) acc -= cur[(nbe + tid) + c * ldd] * y1[c];
-            win[(t + nbe + tid) & wm] = acc;
-        }
-        __syncthreads();
+        if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
+        if (TPR >= 4) acc += shfl_xor_t<TV>(acc, 2);
+        if (uq == 0 && urow < R) win[(t + nbe + urow) & wm] -= acc;
     }
     __pipeline_wait_prior(0);
     __syncthreads();
 
-    // ================= backward: U x = y =================
-    long long tlast = (nsteps - 1) * NB;
-    // window now indexes rows downwards; (re)load the last p + NB rows of y
-    for (long long e = max(0LL, n2 - (NB + p) - NB) + tid; e < n2; e += blockDim.x) win[e & wm] = b[e];
-    {
-        int nbe = (int)(n2 - tlast);
-        int Ra = (int)min((long long)p, tlast);
-        prefetch_cols<TL>(buf0, ldd, A, ld, tlast - Ra, Ra + nbe, tlast, nbe);
-        __pipeline_commit();
-    }
-    for (long long s = 0; s < nsteps; ++s) {
-        long long t = tlast - s * NB;
-        int nbe = (int)min((long long)NB, n2 - t);
-        int Ra = (int)min((long long)p, t);
-        TL* cur = (s & 1) ? buf1 : buf0;
-        TL* nxt = (s & 1) ? buf0 : buf1;
-        if (s + 1 < nsteps) {
-            long long t2 = t - NB;
+    // ================= backward: U x = y (diagonal blocks hold inv(U11)) =================
+    const long long tlast = (nsteps - 1) * NB;
+    auto bwd_prefetch = [&](long long s) {
+        if (s < nsteps) {
+            long long t2 = tlast - s * NB;
+            int nbe2 = (int)min((long long)NB, n2 - t2);
             int Ra2 = (int)min((long long)p, t2);
-            prefetch_cols<TL>(nxt, ldd, A, ld, t2 - Ra2, Ra2 + NB, t2, NB);
+            prefetch_cols<TL, TPR>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2);
         }
         __pipeline_commit();
-        // rows entering the window: t - p - 2 NB .. t - p - NB - 1 (first touched at step s + 2 at the latest)
-        for (long long e = t - p - 2 * NB + tid; e < t - p - NB; e += blockDim.x) if (e >= 0) win[e & wm] = b[e];
-        __pipeline_wait_prior(1);
+    };
+    // window now slides downwards; (re)load the last p + 3 NB rows of y
+    for (long long e = max(0LL, n2 - (3 * NB + p)) + tid; e < n2; e += blockDim.x) win[e & wm] = b[e];
+    for (int q = 0; q < nst - 1; ++q) bwd_prefetch(q);
+    for (long long s = 0; s < nsteps; ++s) {
+        const long long t = tlast - s * NB;
+        const int nbe = (int)min((long long)NB, n2 - t);
+        const int Ra = (int)min((long long)p, t);
+        const TL* cur = ring + (size_t)(s % nst) * ssz;       // rows [t - Ra, t + nbe), local row = row - (t - Ra)
+        __pipeline_wait_prior(nst - 2);
         __syncthreads();
-        // staged block: rows [t - Ra, t + nbe), local row index = row - (t - Ra)
-        if (tid < 32) {
-            TV br = (lane < nbe) ? win[(t + lane) & wm] : Sc<TV>::zero();
+        bwd_prefetch(s + nst - 1);
+        // rows entering the window (first touched at step s+1): t - p - 2 NB .. t - p - NB - 1
+        if (tid < NB) { long long e = t - p - 2 * NB + tid; if (e >= 0) win[e & wm] = b[e]; }
+        TV xr = zero;
 #pragma unroll
-            for (int c = NB - 1; c >= 0; --c) {
-                if (c < nbe) {
-                    TV xc = shfl_t<TV>(br, c);
-                    xc = Sc<TL>::inv(cur[(Ra + c) + c * ldd]) * xc;
-                    if (lane == c) br = xc;
-                    if (lane < c) br -= cur[(Ra + lane) + c * ldd] * xc;
-                }
+        for (int i = 0; i < NB / 2; ++i) {
+            int c = 2 * i + half;
+            if (c >= r16 && c < nbe && r16 < nbe) xr += cur[(Ra + r16) + c * ldd] * win[(t + c) & wm];
+        }
+        xr += shfl_xor_t<TV>(xr, 16);
+        if (lane < NB) yw[warp][lane] = xr;
+        __syncwarp();
+        if (warp == 0 && lane < nbe) b[t + lane] = xr;
+        TV acc = zero;
+        if (urow < Ra) {
+#pragma unroll
+            for (int i = 0; i < NB / TPR; ++i) {
+                int c = uq + TPR * i;
+                if (c < nbe) acc += cur[urow + c * ldd] * yw[warp][c];
             }
-            if (lane < nbe) { y1[lane] = br; b[t + lane] = br; }
         }
-        __syncthreads();
-        if (tid < Ra) {
-            long long row = t - Ra + tid;
-            TV acc = win[row & wm];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) if (c < nbe) acc -= cur[tid + c * ldd] * y1[c];
-            win[row & wm] = acc;
-        }
-        __syncthreads();
+        if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
+        if (TPR >= 4) acc += shfl_xor_t<TV>(acc, 2);
+        if (uq == 0 && urow < Ra) win[(t - Ra + urow) & wm] -= acc;
     }
     __pipeline_wait_prior(0);
 }
 
-int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st) {
-    int th = ((bp.p + 31) / 32) * 32;
-    if (th < 64) th = 64;
-    CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel");
-    CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
-    CS_CHECK(lu_cplx == xm_cplx, "LU and mode vectors must have the same scalar type");
+template <typename T, int TPR>
+static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, int th, size_t sm, int wsz, int nst, cudaStream_t st) {
+    static bool attr = false;                    // one flag per instantiation
+    if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024)); attr = true; }
     dim3 g(bp.nmodes, nvec);
-    size_t nel = bp.band_elems();
-    int ld = bp.ldab - 1;
-    int wsz = 64;
-    while (wsz < bp.p + 3 * NB) wsz <<= 1;
-    size_t es = lu_cplx ? sizeof(cplx) : sizeof(double);
-    size_t sm = 2 * (size_t)(NB + bp.p) * NB * es + (size_t)wsz * es;
-    CS_CHECK(sm <= 220 * 1024, "half bandwidth too large for the shared-memory staged solve");
-    if (lu_cplx) {
-        static bool attr_c = false;
-        if (!attr_c) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<cplx, cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_c = true; }
-        k_band_solve<cplx, cplx><<<g, th, sm, st>>>((const cplx*)LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nmodes, shift_of_vec_d, (cplx*)xm, wsz);
-    } else {
-        static bool attr_d = false;
-        if (!attr_d) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_d = true; }
-        k_band_solve<double, double><<<g, th, sm, st>>>((const double*)LU, nel, bp.n2, bp.p, bp.pw, ld, bp.nmodes, shift_of_vec_d, (double*)xm, wsz);
-    }
+    k_band_solve<T, T, TPR><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
+}
+
+template <typename T>
+static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, cudaStream_t st) {
+    int rowsn = bp.p + NB;
+    int tpr = (4 * rowsn <= 512) ? 4 : (2 * rowsn <= 512 ? 2 : 1);
+    int th = ((tpr * rowsn + 31) / 32) * 32;
+    if (th < 64) th = 64;
+    CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel (p + 16 <= 1024)");
+    int wsz = 64;
+    while (wsz < bp.p + 5 * NB) wsz <<= 1;
+    size_t stage_b = (size_t)rowsn * NB * sizeof(T);
+    int nst = (int)((200 * 1024 - (size_t)wsz * sizeof(T)) / stage_b);   // ring depth: as deep as shared memory allows
+    if (nst > 6) nst = 6;
+    CS_CHECK(nst >= 2, "half bandwidth too large for the shared-memory staged solve");
+    size_t sm = (size_t)nst * stage_b + (size_t)wsz * sizeof(T);
+    if (tpr == 4) return band_solve_launch<T, 4>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+    if (tpr == 2) return band_solve_launch<T, 2>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+    return band_solve_launch<T, 1>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+}
+
+int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st) {
+    CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
+    CS_CHECK(lu_cplx == xm_cplx, "LU and mode vectors must have the same scalar type");
+    if (lu_cplx) return band_solve_t<cplx>(bp, (const cplx*)LU, (cplx*)xm, nvec, shift_of_vec_d, st);
+    return band_solve_t<double>(bp, (const double*)LU, (double*)xm, nvec, shift_of_vec_d, st);
 }
 
 }  // namespace cs
