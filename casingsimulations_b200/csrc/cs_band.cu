@@ -562,59 +562,72 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     const TV zero = Sc<TV>::zero();
 
     // ================= forward: L y = b (unit lower; diagonal blocks hold inv(L11)) =================
-    auto fwd_prefetch = [&](long long s) {
+    auto fwd_prefetch = [&](int s) {
         if (s < nsteps) {
-            long long t2 = s * NB;
+            long long t2 = (long long)s * NB;
             int nbe2 = (int)min((long long)NB, n2 - t2);
             int R2 = (int)min((long long)p, n2 - (t2 + nbe2));
             prefetch_cols<TL, TPR>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
         }
         __pipeline_commit();
     };
-    for (int e = tid; e < 2 * NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
+    for (int e = tid; e < 3 * NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
     for (int q = 0; q < nst - 1; ++q) fwd_prefetch(q);
-    for (long long s = 0; s < nsteps; ++s) {
-        const long long t = s * NB;
-        const int nbe = (int)min((long long)NB, n2 - t);
-        const int R = (int)min((long long)p, n2 - (t + nbe));
-        const TL* cur = ring + (size_t)(s % nst) * ssz;
-        __pipeline_wait_prior(nst - 2);                       // stage s has landed
-        __syncthreads();                                      // ... and is visible; window of step s-1 complete
-        fwd_prefetch(s + nst - 1);                            // refills the slot step s-1 just released
-        // rows entering the window (first touched at step s+1): t + 2 NB + p .. t + 3 NB + p - 1
-        if (tid < NB) { long long e = t + 2 * NB + p + tid; if (e < n2) win[e & wm] = b[e]; }
-        // every warp computes y1 = inv(L11) b1 for itself: lane (r, half) sums the columns of its parity
-        TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
-#pragma unroll
-        for (int i = 0; i < NB / 2; ++i) {
-            int c = 2 * i + half;
-            if (c < r16) yr += cur[r16 + c * ldd] * win[(t + c) & wm];
-        }
-        yr += shfl_xor_t<TV>(yr, 16);
-        if (lane < NB) yw[warp][lane] = yr;
-        __syncwarp();
-        if (warp == 0 && lane < nbe) b[t + lane] = yr;
-        // window update: row (nbe + urow) of the staged block, 4 threads per row
-        TV acc = zero;
-        if (urow < R) {
-#pragma unroll
-            for (int i = 0; i < NB / TPR; ++i) {
-                int c = uq + TPR * i;
-                if (c < nbe) acc += cur[(nbe + urow) + c * ldd] * yw[warp][c];
+    {
+        // entering rows are loaded one step before they are stored (the global-load latency
+        // would otherwise stall warp 0 in front of every barrier)
+        TV pend = zero;
+        long long pe = 3 * NB + p + tid;                      // row loaded into pend (threads < NB)
+        if (tid < NB && pe < n2) pend = b[pe];
+        int slot = 0;
+        const int ns = (int)nsteps;
+        for (int s = 0; s < ns; ++s) {
+            const long long t = (long long)s * NB;
+            const int nbe = (int)min((long long)NB, n2 - t);
+            const int R = (int)min((long long)p, n2 - (t + nbe));
+            const TL* cur = ring + (size_t)slot * ssz;
+            slot = (slot + 1 == nst) ? 0 : slot + 1;
+            __pipeline_wait_prior(nst - 2);                   // stage s has landed
+            __syncthreads();                                  // ... and is visible; window of step s-1 complete
+            fwd_prefetch(s + nst - 1);                        // refills the slot step s-1 just released
+            if (tid < NB) {
+                if (pe < n2) win[pe & wm] = pend;             // rows t + 3 NB + p .. (first touched at step s + 2)
+                pe += NB;
+                if (pe < n2) pend = b[pe];
             }
+            // every warp computes y1 = inv(L11) b1 for itself: lane (r, half) sums the columns of its parity
+            TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
+#pragma unroll
+            for (int i = 0; i < NB / 2; ++i) {
+                int c = 2 * i + half;
+                if (c < r16) yr += cur[r16 + c * ldd] * win[(t + c) & wm];
+            }
+            yr += shfl_xor_t<TV>(yr, 16);
+            if (lane < NB) yw[warp][lane] = yr;
+            __syncwarp();
+            if (warp == 0 && lane < nbe) b[t + lane] = yr;
+            // window update: row (nbe + urow) of the staged block, TPR threads per row
+            TV acc = zero;
+            if (urow < R) {
+#pragma unroll
+                for (int i = 0; i < NB / TPR; ++i) {
+                    int c = uq + TPR * i;
+                    if (c < nbe) acc += cur[(nbe + urow) + c * ldd] * yw[warp][c];
+                }
+            }
+            if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
+            if (TPR >= 4) acc += shfl_xor_t<TV>(acc, 2);
+            if (uq == 0 && urow < R) win[(t + nbe + urow) & wm] -= acc;
         }
-        if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
-        if (TPR >= 4) acc += shfl_xor_t<TV>(acc, 2);
-        if (uq == 0 && urow < R) win[(t + nbe + urow) & wm] -= acc;
     }
     __pipeline_wait_prior(0);
     __syncthreads();
 
     // ================= backward: U x = y (diagonal blocks hold inv(U11)) =================
     const long long tlast = (nsteps - 1) * NB;
-    auto bwd_prefetch = [&](long long s) {
+    auto bwd_prefetch = [&](int s) {
         if (s < nsteps) {
-            long long t2 = tlast - s * NB;
+            long long t2 = tlast - (long long)s * NB;
             int nbe2 = (int)min((long long)NB, n2 - t2);
             int Ra2 = (int)min((long long)p, t2);
             prefetch_cols<TL, TPR>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2);
@@ -622,39 +635,50 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
         __pipeline_commit();
     };
     // window now slides downwards; (re)load the last p + 3 NB rows of y
-    for (long long e = max(0LL, n2 - (3 * NB + p)) + tid; e < n2; e += blockDim.x) win[e & wm] = b[e];
+    for (long long e = max(0LL, n2 - (4 * NB + p)) + tid; e < n2; e += blockDim.x) win[e & wm] = b[e];
     for (int q = 0; q < nst - 1; ++q) bwd_prefetch(q);
-    for (long long s = 0; s < nsteps; ++s) {
-        const long long t = tlast - s * NB;
-        const int nbe = (int)min((long long)NB, n2 - t);
-        const int Ra = (int)min((long long)p, t);
-        const TL* cur = ring + (size_t)(s % nst) * ssz;       // rows [t - Ra, t + nbe), local row = row - (t - Ra)
-        __pipeline_wait_prior(nst - 2);
-        __syncthreads();
-        bwd_prefetch(s + nst - 1);
-        // rows entering the window (first touched at step s+1): t - p - 2 NB .. t - p - NB - 1
-        if (tid < NB) { long long e = t - p - 2 * NB + tid; if (e >= 0) win[e & wm] = b[e]; }
-        TV xr = zero;
-#pragma unroll
-        for (int i = 0; i < NB / 2; ++i) {
-            int c = 2 * i + half;
-            if (c >= r16 && c < nbe && r16 < nbe) xr += cur[(Ra + r16) + c * ldd] * win[(t + c) & wm];
-        }
-        xr += shfl_xor_t<TV>(xr, 16);
-        if (lane < NB) yw[warp][lane] = xr;
-        __syncwarp();
-        if (warp == 0 && lane < nbe) b[t + lane] = xr;
-        TV acc = zero;
-        if (urow < Ra) {
-#pragma unroll
-            for (int i = 0; i < NB / TPR; ++i) {
-                int c = uq + TPR * i;
-                if (c < nbe) acc += cur[urow + c * ldd] * yw[warp][c];
+    {
+        TV pend = zero;
+        long long pe = n2 - (4 * NB + p) - NB + tid;          // next rows below the loaded window
+        if (tid < NB && pe >= 0) pend = b[pe];
+        int slot = 0;
+        const int ns = (int)nsteps;
+        for (int s = 0; s < ns; ++s) {
+            const long long t = tlast - (long long)s * NB;
+            const int nbe = (int)min((long long)NB, n2 - t);
+            const int Ra = (int)min((long long)p, t);
+            const TL* cur = ring + (size_t)slot * ssz;        // rows [t - Ra, t + nbe), local row = row - (t - Ra)
+            slot = (slot + 1 == nst) ? 0 : slot + 1;
+            __pipeline_wait_prior(nst - 2);
+            __syncthreads();
+            bwd_prefetch(s + nst - 1);
+            if (tid < NB) {
+                if (pe >= 0) win[pe & wm] = pend;
+                pe -= NB;
+                if (pe >= 0) pend = b[pe];
             }
+            TV xr = zero;
+#pragma unroll
+            for (int i = 0; i < NB / 2; ++i) {
+                int c = 2 * i + half;
+                if (c >= r16 && c < nbe && r16 < nbe) xr += cur[(Ra + r16) + c * ldd] * win[(t + c) & wm];
+            }
+            xr += shfl_xor_t<TV>(xr, 16);
+            if (lane < NB) yw[warp][lane] = xr;
+            __syncwarp();
+            if (warp == 0 && lane < nbe) b[t + lane] = xr;
+            TV acc = zero;
+            if (urow < Ra) {
+#pragma unroll
+                for (int i = 0; i < NB / TPR; ++i) {
+                    int c = uq + TPR * i;
+                    if (c < nbe) acc += cur[urow + c * ldd] * yw[warp][c];
+                }
+            }
+            if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
+            if (TPR >= 4) acc += shfl_xor_t<TV>(acc, 2);
+            if (uq == 0 && urow < Ra) win[(t - Ra + urow) & wm] -= acc;
         }
-        if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
-        if (TPR >= 4) acc += shfl_xor_t<TV>(acc, 2);
-        if (uq == 0 && urow < Ra) win[(t - Ra + urow) & wm] -= acc;
     }
     __pipeline_wait_prior(0);
 }
@@ -677,7 +701,7 @@ static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const 
     if (th < 64) th = 64;
     CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel (p + 16 <= 1024)");
     int wsz = 64;
-    while (wsz < bp.p + 5 * NB) wsz <<= 1;
+    while (wsz < bp.p + 7 * NB) wsz <<= 1;
     size_t stage_b = (size_t)rowsn * NB * sizeof(T);
     int nst = (int)((200 * 1024 - (size_t)wsz * sizeof(T)) / stage_b);   // ring depth: as deep as shared memory allows
     if (nst > 6) nst = 6;
