@@ -17,6 +17,7 @@
 #include "cs_internal.h"
 #include <cuda_pipeline.h>
 #include <vector>
+#include <cstdlib>
 
 namespace cs {
 
@@ -381,6 +382,215 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     if (m1 && n1) c01[16] = old11 - acc11;
 }
 
+// ---------------------------------------------------- two-level blocking -----
+// The NB = 16 scheme above is a chain of 2 * n2 / 16 dependent launches whose length, not
+// the flops, sets the factorisation time.  For panels that fit shared memory the outer block
+// is NBB = 64 columns: k_panel64 factors a whole 64-column panel inside ONE CTA per 64-row
+// chunk (four 16-column sub-steps with the panel resident in shared memory: no global
+// round trips, no launches), k_update64 applies the rank-64 update.  Column chunks hold rows
+// of A21 and the block A11; row chunks hold columns of A12 TRANSPOSED together with A11^T:
+// running the same Doolittle code on the transposed view yields U' = D L11^T, so
+// U12^T = (A12^T U'^-1) D -- both panel kinds share one code path.
+static const int NBB = 64;
+static const int GS = NBB + 1;      // shared-memory row pitch (elements)
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_panel64(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t0, T* __restrict__ scratch, int chunks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* G = reinterpret_cast<T*>(smem_raw);            // [NBB][GS]  view of A11 (row chunk: transposed)
+    T* Q = G + NBB * GS;                              // [NBB][GS]  64 panel rows x 64 panel columns
+    T* A = LU + (size_t)blockIdx.y * nel + pw;        // dense view base
+    const int tid = threadIdx.x;
+    const bool rowpanel = (int)blockIdx.x >= chunks;
+    const int ch = rowpanel ? blockIdx.x - chunks : blockIdx.x;
+    const int nbb = (int)min((long long)NBB, n2 - t0);
+    const int R = (int)min((long long)p, n2 - (t0 + nbb));
+    const long long pbase = t0 + nbb + 64LL * ch;     // first global row (column) of this chunk
+    const int nq = (int)max(0LL, min(64LL, (long long)R - 64LL * ch));   // valid panel rows in this chunk
+    const T zero = Sc<T>::zero(), one = Sc<T>::one();
+    // ---- load (band-masked: entries farther than pw from the diagonal are not stored = zero)
+    for (int e = tid; e < NBB * NBB; e += 256) {
+        int r = e % NBB, c = e / NBB;                  // consecutive threads -> consecutive global rows
+        T g = (r == c) ? one : zero;
+        if (r < nbb && c < nbb) g = (abs(r - c) <= pw) ? A[(t0 + r) + (t0 + c) * (long long)ld] : zero;
+        if (!rowpanel) G[r * GS + c] = g; else G[c * GS + r] = g;
+        T q = zero;
+        if (r < nq && c < nbb) {
+            long long gr = pbase + r, gc = t0 + c;
+            if (gr - gc <= pw) q = rowpanel ? A[gc + gr * (long long)ld] : A[gr + gc * (long long)ld];
+        }
+        Q[r * GS + c] = q;
+    }
+    __syncthreads();
+    for (int o = 0; o < NBB; o += NB) {
+        // ---- a. unblocked LU of the 16 x 16 diagonal sub-block by warp 0 (lane r owns row r)
+        if (tid < 32) {
+            int r = tid & 15;
+            T rowv[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) rowv[c] = G[(o + r) * GS + o + c];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                T piv = Sc<T>::inv(shfl_row(rowv[c], c));
+                T l = rowv[c] * piv;
+                if (r > c) rowv[c] = l;
+#pragma unroll
+                for (int cc = c + 1; cc < NB; ++cc) {
+                    T u = shfl_row(rowv[cc], c);
+                    if (r > c) rowv[cc] -= l * u;
+                }
+            }
+            if (tid < NB) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) G[(o + r) * GS + o + c] = rowv[c];
+            }
+        }
+        __syncthreads();
+        // ---- b. triangular solves against the sub-block
+        //   threads   0.. 63 : panel rows      q U^-1
+        //   threads  64..127 : rows of G below the sub-block   g U^-1   (L part)
+        //   threads 128..191 : columns of G right of the sub-block   L^-1 g   (U part)
+        {
+            T v[NB];
+            const int grp = tid >> 6, idx = tid & 63;
+            if (grp == 0 || (grp == 1 && idx >= o + NB)) {
+                T* rowp = (grp == 0 ? Q : G) + idx * GS + o;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) v[c] = rowp[c];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    T acc = v[c];
+#pragma unroll
+                    for (int c2 = 0; c2 < c; ++c2) acc -= v[c2] * G[(o + c2) * GS + o + c];
+                    v[c] = acc * Sc<T>::inv(G[(o + c) * GS + o + c]);
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c) rowp[c] = v[c];
+            } else if (grp == 2 && idx >= o + NB) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) v[r] = G[(o + r) * GS + idx];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    T acc = v[r];
+#pragma unroll
+                    for (int r2 = 0; r2 < r; ++r2) acc -= G[(o + r) * GS + o + r2] * v[r2];
+                    v[r] = acc;
+                }
+#pragma unroll
+                for (int r = 0; r < NB; ++r) G[(o + r) * GS + idx] = v[r];
+            }
+        }
+        __syncthreads();
+        // ---- c. trailing update inside the panel: rows (64 panel rows + rows of G below) x later columns
+        if (o + NB < NBB) {
+            const int rr = tid & 127, cg = tid >> 7;     // row task, column parity
+            const bool isq = rr < 64;
+            const int gr = isq ? rr : (o + NB + (rr - 64));           // G row for rr >= 64
+            if (isq || gr < NBB) {
+                T* rowp = (isq ? Q : G) + (isq ? rr : gr) * GS;
+                T l[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) l[k] = rowp[o + k];
+                // four independent accumulator chains per thread (fp64 FMA latency, not rate, is the limit)
+                for (int c = o + NB + cg; c < NBB; c += 8) {
+                    T a0 = rowp[c], a1 = (c + 2 < NBB) ? rowp[c + 2] : zero, a2 = (c + 4 < NBB) ? rowp[c + 4] : zero, a3 = (c + 6 < NBB) ? rowp[c + 6] : zero;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const T* gk = G + (o + k) * GS + c;
+                        a0 -= l[k] * gk[0];
+                        if (c + 2 < NBB) a1 -= l[k] * gk[2];
+                        if (c + 4 < NBB) a2 -= l[k] * gk[4];
+                        if (c + 6 < NBB) a3 -= l[k] * gk[6];
+                    }
+                    rowp[c] = a0;
+                    if (c + 2 < NBB) rowp[c + 2] = a1;
+                    if (c + 4 < NBB) rowp[c + 4] = a2;
+                    if (c + 6 < NBB) rowp[c + 6] = a3;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- store
+    if (rowpanel) {
+        // U12^T = (A12^T U'^-1) D, D = diag(U') ; transposed store
+        for (int e = tid; e < NBB * NBB; e += 256) {
+            int c = e % NBB, r = e / NBB;               // consecutive threads -> consecutive global rows (= panel col c)
+            if (r < nq && c < nbb) {
+                long long gr = pbase + r, gc = t0 + c;
+                if (gr - gc <= pw) A[gc + gr * (long long)ld] = Q[r * GS + c] * G[c * GS + c];
+            }
+        }
+    } else {
+        for (int e = tid; e < NBB * NBB; e += 256) {
+            int r = e % NBB, c = e / NBB;
+            if (r < nq && c < nbb) {
+                long long gr = pbase + r, gc = t0 + c;
+                if (gr - gc <= pw) A[gr + gc * (long long)ld] = Q[r * GS + c];
+            }
+        }
+        if (ch == 0) {
+            // park the factored diagonal block (other CTAs may still be reading A11)
+            T* S = scratch + (size_t)blockIdx.y * NBB * NBB;
+            for (int e = tid; e < NBB * NBB; e += 256) S[e] = G[(e % NBB) * GS + e / NBB];
+        }
+    }
+}
+
+// A22 -= L21 (R x 64) U12 (64 x R) on 32 x 32 tiles; tile (0,0) also copies the parked diagonal block in place
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_update64(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t0, const T* __restrict__ scratch) {
+    __shared__ T Ls[NB][32];
+    __shared__ T Us[NB][33];
+    T* A = LU + (size_t)blockIdx.z * nel + pw;
+    const int nbb = (int)min((long long)NBB, n2 - t0);
+    const int R = (int)min((long long)p, n2 - (t0 + nbb));
+    const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        const T* S = scratch + (size_t)blockIdx.z * NBB * NBB;
+        for (int e = tid; e < NBB * NBB; e += 256) {
+            int r = e % NBB, c = e / NBB;
+            if (r < nbb && c < nbb && abs(r - c) <= pw) A[(t0 + r) + (t0 + c) * (long long)ld] = S[e];
+        }
+    }
+    if (a0 >= R || b0 >= R) return;
+    const long long r0 = t0 + nbb + a0, c0 = t0 + nbb + b0;
+    const int ta = tid % 16, tb = tid / 16;
+    const bool m0 = (a0 + ta < R), m1 = (a0 + ta + 16 < R), n0 = (b0 + tb < R), n1 = (b0 + tb + 16 < R);
+    T* c00 = A + (r0 + ta) + (c0 + tb) * (long long)ld;
+    T* c01 = A + (r0 + ta) + (c0 + tb + 16) * (long long)ld;
+    T old00 = (m0 && n0) ? c00[0] : Sc<T>::zero(), old10 = (m1 && n0) ? c00[16] : Sc<T>::zero();
+    T old01 = (m0 && n1) ? c01[0] : Sc<T>::zero(), old11 = (m1 && n1) ? c01[16] : Sc<T>::zero();
+    T acc00 = Sc<T>::zero(), acc01 = Sc<T>::zero(), acc10 = Sc<T>::zero(), acc11 = Sc<T>::zero();
+    for (int k0 = 0; k0 < nbb; k0 += NB) {
+        for (int e = tid; e < NB * 32; e += 256) {
+            int a = e % 32, c = e / 32;
+            long long gr = r0 + a, gc = t0 + k0 + c;
+            Ls[c][a] = (a0 + a < R && k0 + c < nbb && gr - gc <= pw) ? A[gr + gc * (long long)ld] : Sc<T>::zero();
+        }
+        for (int e = tid; e < NB * 32; e += 256) {
+            int c = e % NB, bq = e / NB;
+            long long gr = t0 + k0 + c, gc = c0 + bq;
+            Us[c][bq] = (b0 + bq < R && k0 + c < nbb && gc - gr <= pw) ? A[gr + gc * (long long)ld] : Sc<T>::zero();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            T l0 = Ls[c][ta], l1 = Ls[c][ta + 16];
+            T u0 = Us[c][tb], u1 = Us[c][tb + 16];
+            acc00 += l0 * u0; acc01 += l0 * u1; acc10 += l1 * u0; acc11 += l1 * u1;
+        }
+        __syncthreads();
+    }
+    if (m0 && n0) c00[0] = old00 - acc00;
+    if (m1 && n0) c00[16] = old10 - acc10;
+    if (m0 && n1) c01[0] = old01 - acc01;
+    if (m1 && n1) c01[16] = old11 - acc11;
+}
+
 // After the factorisation every NB x NB diagonal block holds L11 \ U11.  The triangular solves
 // with those blocks are the sequential heart of the substitution kernels, so they are replaced
 // once, here (fully parallel: one warp per block), by the explicit inverses
@@ -443,12 +653,30 @@ struct FactorGraph { FactorGraphKey key; cudaGraphExec_t exec; unsigned long lon
 static std::vector<FactorGraph> g_graphs;
 static unsigned long long g_stamp = 0;
 
+// 16 = single-level blocking (default); 64 = two-level blocking (env CS_FACTOR_BLOCK=64).  The
+// two-level path is bit-for-bit tested but measured slower on B200 for p = 109 (113 ms vs 92 ms
+// for the C2 sweep): the 64-column panel kernel is a long chain of dependent fp64 operations in
+// one CTA.  Kept selectable for wider bands / future tuning.
+static int g_factor_block = -1;
+
 template <typename T>
 static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, cudaStream_t st) {
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
     int tiles = (bp.p + 31) / 32;
     int chunks = (bp.p + 63) / 64;
+    if (g_factor_block == 64) {
+        size_t smb = 2 * (size_t)NBB * GS * sizeof(T);
+        for (long long t = 0; t < bp.n2; t += NBB) {
+            dim3 gp(2 * chunks, nsys);
+            k_panel64<T><<<gp, 256, smb, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, chunks);
+            dim3 g(tiles, tiles, nsys);
+            k_update64<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
+        }
+        dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
+        k_invert_diag<T><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
+        return CS_OK;
+    }
     for (long long t = 0; t < bp.n2; t += NB) {
         dim3 gp(chunks, nsys);
         k_lu_panel<T><<<gp, 128, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch);
@@ -463,16 +691,24 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
 template <typename T>
 static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
+    if (g_factor_block < 0) {
+        const char* e = getenv("CS_FACTOR_BLOCK");
+        g_factor_block = (e && atoi(e) == 64) ? 64 : 16;
+    }
+    {
+        static bool attr = false;                // per instantiation
+        if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_panel64<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NBB * GS * sizeof(T)))); attr = true; }
+    }
     static void* scratch = nullptr;
     static size_t scratch_bytes = 0;
-    size_t need = (size_t)nsys * NB * NB * sizeof(T);
+    size_t need = (size_t)nsys * NBB * NBB * sizeof(T);
     if (need > scratch_bytes) {
         if (scratch) cudaFree(scratch);
         if (need < (1u << 20)) need = 1u << 20;
         CS_CUDA(cudaMalloc(&scratch, need));
         scratch_bytes = need;
     }
-    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx))};
+    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * g_factor_block};
     for (auto& g : g_graphs)
         if (g.key == key) {
             g.stamp = ++g_stamp;
