@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 METRIC = "fdem_casing_solve_seconds_per_frequency"
 UNIT = "s/frequency"
 NFREQ_PER_GPU = 32
+NCU_TRAFFIC_K4 = 705.5e6      # bytes per launch of k_edge_op<cplx> on the 109x32x1394 mesh (497.7 MB read + 207.8 MB written)
 WORKLOAD = ("C2: FDEM-h, CasingInHalfspace (sigma_casing 5.5e6 S/m), CasingMeshGenerator 109x1x717 = 78153 cells, "
             "TopCasingSrc, 32 freqs 0.1 Hz-1 kHz per GPU")
 
@@ -100,6 +101,17 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def blas_threads():
+    """threads the CPU arm can actually use: SuperLU itself is sequential, its supernodal BLAS
+    calls go through scipy's OpenBLAS thread pool"""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info()]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def oracle_sample(mg, mp, src_se, freqs):
     """scipy assembly + SuperLU factor/solve, one frequency at a time (the reference's loop)."""
     from oracle.cyl_oracle import OracleCylMesh, OracleFDEM, paint_casing_in_halfspace
@@ -125,7 +137,7 @@ def run_reference(args, rank):
         return
     mp, mg, src = build_inputs(NFREQ_PER_GPU)
     se = src.s_e
-    sample = [0.1, 1000.0]                      # slowest and fastest ends of the sweep
+    sample = [float(f) for f in np.logspace(-1, 3, NFREQ_PER_GPU)[[0, 10, 21, 31]]]     # 4 of the 32 frequencies
     for _ in range(args.warmup if args.warmup < 2 else 1):
         oracle_sample(mg, mp, se, sample[:1])
     ts = []
@@ -137,10 +149,11 @@ def run_reference(args, rank):
             "warmup": args.warmup, "ms_per_step": v * NFREQ_PER_GPU * 1e3, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "2 of the 32 frequencies (0.1 Hz, 1 kHz) per step; scipy assembly amortised over the "
-                                       "sweep + SuperLU factor+solve per frequency; SuperLU is single-threaded; host has "
-                                       "{} cores; MKL PARDISO not installable offline".format(os.cpu_count())},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                             "sample": "4 of the 32 frequencies (0.1, 1.95, 51.3, 1000 Hz) per step; scipy assembly amortised over "
+                                       "the sweep + SuperLU factor+solve per frequency (the reference's fallback SolverLU, "
+                                       "run.py:19-24; SuperLU sequential, BLAS threads as found; host has {} cores; MKL PARDISO "
+                                       "not installable offline)".format(os.cpu_count())},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -165,7 +178,8 @@ def stencil_roofline(torch, dev, reps=20):
     alg = 144.0 * ctx.nC
     out = {"bound": "hbm", "kernel": "k_edge_op<cplx> (K4: C^T MfRho C + i w MeMu, 3-D 109x32x1394, 4.86 M cells)",
            "achieved": alg / t / 1e9, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
-           "traffic": None, "bytes_per_launch": alg, "us_per_launch": t * 1e6, "cells": ctx.nC}
+           "traffic": NCU_TRAFFIC_K4, "traffic_source": "profiles/r01_ncu_k_edge_op.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+           "bytes_per_launch": alg, "us_per_launch": t * 1e6, "cells": ctx.nC}
     opd = ctx.op(_lib.KIND_DC, plan=False)
     xd = torch.randn(ctx.nC, dtype=torch.float64, device=ctx.device)
     torch.cuda.synchronize()
@@ -275,10 +289,10 @@ def run_ours(args, rank, world, local_rank):
                                "ms_assemble": info.get("ms_assemble"), "ms_factor": info.get("ms_factor"),
                                "ms_solve": info.get("ms_solve"), "rel_l2_vs_oracle_h": par},
                 "roofline": roof,
-                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                                  "sample": "2 of the 32 frequencies ({:.3g} Hz, {:.3g} Hz): scipy assembly (amortised over "
-                                           "the sweep) + SuperLU factor + solve; single-threaded; host has {} cores; MKL "
-                                           "PARDISO not installable offline".format(freqs[0], freqs[-1], os.cpu_count())},
+                                           "the sweep) + SuperLU factor + solve (SuperLU sequential, BLAS threads as found); "
+                                           "host has {} cores; MKL PARDISO not installable offline".format(freqs[0], freqs[-1], os.cpu_count())},
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     ctx.close()
