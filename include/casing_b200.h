@@ -39,7 +39,7 @@ typedef struct cs_op cs_op;
 #define CS_INFO_N_LAUNCH 6   /* kernels launched by this call                 */
 #define CS_INFO_BYTES 7      /* algorithmic bytes moved by the stencil applies */
 #define CS_INFO_CONVERGED 8
-#define CS_INFO_BACKWARD_ERR 9 /* set when relres stalls above rtol at the fp64 floor: ||r~||/(8||x~||+||b~||) <= 1e-14 is accepted */
+#define CS_INFO_BACKWARD_ERR 9 /* set when relres stalls above rtol at the fp64 floor: ||r~||/(8||x~||+||b~||) <= 2e-15 is accepted */
 #define CS_INFO_LEN 16
 
 const char* cs_last_error(void);

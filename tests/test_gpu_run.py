@@ -132,7 +132,7 @@ def test_simulation_dc_and_casing_currents(tmp_path):
     b = np.array([[1000.0, 0.0, -2.5]])
     sim = run.SimulationDC(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a, src_b=b)
     f = sim.run()
-    assert sim.prob.info["relres"] <= 1e-10 or sim.prob.info["backward_err"] <= 1e-14     # fp64 floor, see DESIGN.md
+    assert sim.prob.info["relres"] <= 1e-10 or sim.prob.info["backward_err"] <= 2e-15     # fp64 floor, see DESIGN.md
     assert np.array_equal(np.load(os.path.join(tmp, "fieldsDC.npy")), f[:, "phiSolution"])
     from oracle.cyl_oracle import OracleCylMesh, OracleDC, casing_currents
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
@@ -227,7 +227,7 @@ def test_full_size_c1_dc():
     f = sim.run(save=False)
     info = sim.prob.info
     print("C1 info", info)
-    assert info["relres"] <= 1e-10 or info["backward_err"] <= 1e-14
+    assert info["relres"] <= 1e-10 or info["backward_err"] <= 2e-15
     from oracle.cyl_oracle import OracleCylMesh, OracleDC
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
     P = OracleDC(om, mp.sigma(m))
@@ -261,7 +261,7 @@ def test_full_size_c3_dc_3d_properties():
     q[1, ib] = 1.0                            # unit source at b
     phi = ctx.solve_dc(q)
     print("C3 info", ctx.info)
-    assert ctx.info["relres"] <= 1e-10 or ctx.info["backward_err"] <= 1e-14
+    assert ctx.info["relres"] <= 1e-10 or ctx.info["backward_err"] <= 2e-15
     qa = torch.zeros((1, m.nC), dtype=torch.float64, device=ctx.device)
     qa[0, ia] = 1.0
     phia = ctx.solve_dc(qa)
