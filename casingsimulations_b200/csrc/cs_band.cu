@@ -777,7 +777,7 @@ template <> __device__ __forceinline__ cplx shfl_xor_t<cplx>(cplx v, int m) {
 }
 
 template <typename TL, typename TV, int TPR>
-__global__ void __launch_bounds__(TPR == 1 ? 1024 : 512)
+__global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 512))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
                              int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -932,7 +932,7 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
 template <typename T>
 static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, cudaStream_t st) {
     int rowsn = bp.p + NB;
-    int tpr = (4 * rowsn <= 512) ? 4 : (2 * rowsn <= 512 ? 2 : 1);
+    int tpr = (4 * rowsn <= 512) ? 4 : (2 * rowsn <= 768 ? 2 : 1);
     int th = ((tpr * rowsn + 31) / 32) * 32;
     if (th < 64) th = 64;
     CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel (p + 16 <= 1024)");
