@@ -718,9 +718,32 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool captured = false;
+    // The chain is latency-bound and barely depends on the number of systems per launch, so the
+    // systems are split into up to 4 groups whose chains run concurrently on forked streams
+    // (inside the captured graph: parallel branches) and hide each other's latency.
+    static cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    if (!ev_fork) {
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        for (int g = 0; g < 3; ++g) { cudaStreamCreateWithFlags(&aux[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming); }
+    }
+    const int groups = (nsys >= 16) ? 4 : (nsys >= 6 ? 2 : 1);
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        band_factor_enqueue<T>(bp, LU, nsys, (T*)scratch, st);
-        if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph &&
+        bool okq = true;
+        if (groups > 1) {
+            okq = okq && cudaEventRecord(ev_fork, st) == cudaSuccess;
+            for (int g = 1; g < groups; ++g) okq = okq && cudaStreamWaitEvent(aux[g - 1], ev_fork, 0) == cudaSuccess;
+        }
+        for (int g = 0; g < groups && okq; ++g) {
+            int s0 = (int)((long long)nsys * g / groups), s1 = (int)((long long)nsys * (g + 1) / groups);
+            cudaStream_t sg = (g == 0) ? st : aux[g - 1];
+            okq = okq && band_factor_enqueue<T>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NBB * NBB, sg) == CS_OK;
+        }
+        for (int g = 1; g < groups; ++g) {
+            okq = okq && cudaEventRecord(ev_join[g - 1], aux[g - 1]) == cudaSuccess;
+            okq = okq && cudaStreamWaitEvent(st, ev_join[g - 1], 0) == cudaSuccess;
+        }
+        if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && okq &&
             cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) captured = true;
         if (graph) cudaGraphDestroy(graph);
     }
