@@ -177,9 +177,12 @@ int launch_edge_scale(const MeshD& m, const double* in, double* out, int mode, c
 // y_c = sum_f g_f (x_c - x_nbr(f)); faces on the outer r / bottom / top boundary
 // have no neighbour (Dirichlet phi = 0 outside; SimPEG Problem3D_CC, run.py:339-344)
 // g = area^2 / MfRho laid out like a face vector.  40 B/cell (3-D), 32 B/cell (2-D).
-// One thread per cell, i fastest.  (A z-marching variant with x / g_z carried in registers
-// was measured slower on B200 -- 63-97 us vs 55 us at 4.86 M cells: fewer, longer threads
-// expose less memory-level parallelism than 4.86 M independent ones.)
+// One thread per cell, i fastest: 55 us at 4.86 M cells = 3.5 TB/s = 54 % of the measured copy peak.
+// Two alternatives were built and measured on B200 and did not beat it: a register z-marching
+// variant (63-97 us: fewer, longer threads expose less memory-level parallelism) and a K4-style
+// tiled kernel with cp.async-staged x planes (55 us: DRAM traffic and L2 traffic drop, but at one
+// cell per thread per level the staging / addressing overhead is 226 instructions per cell and the
+// kernel becomes issue-bound, ncu issue-active 63 %).  Next step: several cells per thread.
 template <typename T>
 __global__ void k_dc_apply(MeshD m, const double* __restrict__ g, double shift0,
                            const T* __restrict__ x, T* __restrict__ y) {

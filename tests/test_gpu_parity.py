@@ -215,3 +215,33 @@ def test_casing_currents(gpu_ctx, nth):
     z, cref = casing_charges(ch, om, CASING["casing_b"], cz)
     cg = gpu_ctx.casing_charges(gpu_ctx.to_device(ch), CASING["casing_b"], cz).cpu().numpy()
     assert rel(cg[(om.vectorCCz > cz[0]) & (om.vectorCCz < cz[1])], cref) < 1e-13
+
+
+def test_apply_matches_oracle_at_size():
+    """the probing-based preconditioner would happily invert a wrong operator, so the stencil kernels are
+    also checked against the oracle's assembled matrices at a size where index arithmetic crosses
+    32-bit-unfriendly strides (109 x 8 x 460 = 401 120 cells): DC and the 3-D edge form."""
+    import casingsimulations_b200 as cs
+    from casingsimulations_b200 import _lib
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC
+    mp = cs.model.CasingInHalfspace(src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0])
+    mg = cs.CasingMeshGenerator(modelParameters=mp, npadx=10, npadz=25, csz=2.5, hy=np.ones(8) * 2 * np.pi / 8)
+    m = mg.mesh
+    assert m.nC >= 400000
+    ctx = _lib.Context(0)
+    ctx.set_mesh(m.hx, m.hy, m.hz, m.x0[2])
+    ctx.paint(mp.paint_params())
+    op = ctx.op(_lib.KIND_DC, plan=False)
+    x = rnd(m.nC, False, 3)
+    y = op.apply(ctx.to_device(x)).cpu().numpy()
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    A = OracleDC(om, mp.sigma(m)).getA()
+    assert rel(y, A @ x) < 1e-12
+    from oracle.cyl_oracle import OracleFDEM
+    P = OracleFDEM(om, mp.sigma(m), mp.mu(m), "h")
+    ope = ctx.op(_lib.KIND_EDGE_H, plan=False)
+    xe = rnd(m.nE, True, 5)
+    s = 2j * np.pi * 3.0
+    ye = ope.apply(ctx.to_device(xe), shifts=s).cpu().numpy()
+    assert rel(ye, P.C.T @ (P.MfRho @ (P.C @ xe)) + s * (P.MeMu @ xe)) < 1e-12
+    ctx.close()
