@@ -116,7 +116,8 @@ class _Problem(object):
             m = np.asarray(m, dtype=float)
             nC = self.mesh.nC
             assert m.size == 2 * nC, "model vector must be [sigma; mu] (model.py:848-868)"
-            ctx.set_model(ctx.to_device(m[:nC]), ctx.to_device(m[nC:]))
+            self._sigma_d, self._mu_d = ctx.to_device(m[:nC]), ctx.to_device(m[nC:])
+            ctx.set_model(self._sigma_d, self._mu_d)
 
     def clean(self):
         if self._ctx is not None:
@@ -244,12 +245,9 @@ class _ProblemTDEM(_Problem):
             return f._sol[:, idx, :]
         if name == "e":      # e = Mf^-1 MfRho j
             ctx = self.ctx
-            w = (ctx.face_inner_product(self._sigma_like(), True, False) / ctx.face_inner_product()).cpu().numpy()
+            w = (ctx.face_inner_product(self._sigma_d, True, False) / ctx.face_inner_product()).cpu().numpy()
             return f._sol[:, idx, :] * w[:, None, None]
         raise KeyError(name)
-
-    def _sigma_like(self):
-        raise KeyError("e from TDEM j needs the model on the device; use fields[:, 'j']")
 
 
 class BaseSimulation(BaseCasing):

@@ -169,6 +169,9 @@ def test_simulation_tdem(tmp_path, nth):
     tol = max(1e-6, 10 * rel(Flu, Fref))
     assert rel(jsol, Fref) < tol, (rel(jsol, Fref), tol)
     assert rel(f[:, "j", 3][:, 0], Fref[:, 3]) < tol
+    e = f[:, "e"]
+    w = om.getFaceInnerProduct(1.0 / mp.sigma(m)).diagonal() / om.getFaceInnerProduct().diagonal()
+    assert e.shape == jsol.shape and rel(e, jsol * w[:, None]) < 1e-12
     sim.prob.clean()
 
 
@@ -331,3 +334,36 @@ def test_theta_varying_flawed_casing_krylov(tmp_path):
     ref = j_true if rel(j_lu, j_true) < 1e-2 else j_lu
     assert rel(jg, ref) < 0.2
     simf.prob.clean()
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_against_committed_golden_vectors(nth):
+    """tests/golden/small_casing.npz (oracle, extended-precision refined; see make_golden.py): the GPU
+    path reproduces the committed vectors without re-solving anything on the CPU."""
+    from conftest import CASING, paint_params, small_casing_mesh
+    from casingsimulations_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "small_casing.npz"))
+    tag = "n%d_" % nth
+    hx, hy, hz, z0 = small_casing_mesh(nth)
+    ctx = _lib.Context(0)
+    ctx.set_mesh(hx, hy, hz, z0)
+    s_d, m_d = ctx.paint(paint_params(CASING))
+    assert np.array_equal(s_d.cpu().numpy(), g[tag + "sigma"]) and np.array_equal(m_d.cpu().numpy(), g[tag + "mu"])
+    assert rel(ctx.face_inner_product(s_d, True, False).cpu().numpy(), g[tag + "MfRho"]) < 1e-14
+    assert rel(ctx.edge_inner_product(m_d).cpu().numpy(), g[tag + "MeMu"]) < 1e-14
+    mesh = cs.CylMesh([hx, hy, hz], x0=[0, 0, z0])
+    from casingsimulations_b200.mesh import closestPoints
+    q = np.zeros((1, mesh.nC))
+    q[0, closestPoints(mesh, g[tag + "dc_a"][0])[0]] = 1.0
+    q[0, closestPoints(mesh, g[tag + "dc_b"][0])[0]] = -1.0
+    phi = ctx.solve_dc(ctx.to_device(q)).cpu().numpy()[0]
+    assert rel(phi, g[tag + "dc_phi"]) < 5e-6
+    se = ctx.to_device(g[tag + "s_e"])
+    u = ctx.solve_fdem("h", [100.0], se)
+    j = ctx.fields_fdem("h", "j", 100.0, u[0], se).cpu().numpy()
+    assert rel(j, g[tag + "fdem_j_100Hz"]) < (1e-6 if nth == 1 else 1e-4)
+    if nth == 1:
+        assert rel(u[0].cpu().numpy(), g[tag + "fdem_h_100Hz"]) < 1e-6
+    F = ctx.tdem_run("j", np.r_[np.ones(3) * 1e-5, np.ones(3) * 1e-4], se).cpu().numpy().T
+    assert rel(F, g[tag + "tdem_j"]) < 1e-6
+    ctx.close()
