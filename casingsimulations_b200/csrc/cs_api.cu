@@ -262,7 +262,8 @@ static int build_plan(cs_op* op) {
         }
     }
     if (bp.p > bp.n2 - 1) bp.p = (int)std::max(1LL, bp.n2 - 1);
-    bp.nb = 16;
+    bp.scalar_field = (op->family == 0) || (op->family == 1 && m.sym);
+    bp.nb = band_choose_nb(bp.p);
     bp.pw = bp.p + bp.nb;
     bp.ldab = 2 * bp.pw + 1;
     bp.nmodes = nth;
@@ -481,7 +482,7 @@ extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int c
     CS_TRY(band_diag_weights(bp, (const double*)c->scal.p, nshift, op->n, (double*)op->wts.p, c->st));
     CS_TRY(band_form_shifted(bp, (const double*)c->scal.p, nshift, op->LU.p, lc, c->st));
     CS_TRY(band_factor(bp, op->LU.p, lc, nshift * bp.nmodes, c->st));
-    g_launches += 1 + 2 * ((bp.n2 + bp.nb - 1) / bp.nb);
+    g_launches += band_factor_launches(bp, lc);
     CS_CUDA(cudaEventRecord(c->ev1, c->st));
     CS_CUDA(cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);

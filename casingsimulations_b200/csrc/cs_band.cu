@@ -18,6 +18,8 @@
 #include <cuda_pipeline.h>
 #include <vector>
 #include <cstdlib>
+#include <cstdio>
+#include <cstring>
 
 namespace cs {
 
@@ -245,15 +247,13 @@ int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long lo
 // then the update kernel (32x32 tiles x systems)  A22 -= L21 U12  (R x R).
 // NB is a compile-time constant so the per-thread row / column solves live in
 // registers; a short last block is padded with an identity.
-static const int NB = 16;
-static const int NBMAX = NB;
 
 // grid = (chunks, systems), 128 threads: every CTA factors the NB x NB diagonal block
 // itself (one warp, ~1 us, redundant across chunks) and then solves 64 rows of A21 and
 // 64 columns of A12.  A11 is NOT overwritten here (other chunks may still read it):
 // chunk 0 parks the factored block in `scratch`, the update kernel copies it in place.
-template <typename T>
-__global__ void __launch_bounds__(128)
+template <typename T, int NB>
+__global__ void __launch_bounds__(160)
 k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, T* __restrict__ scratch) {
     __shared__ T D[NB][NB + 1];                      // D[r][c]
     T* A = LU + (size_t)blockIdx.y * nel + pw;       // dense view base
@@ -261,8 +261,9 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
     int R = (int)min((long long)p, n2 - (t + nbe));
     int tid = threadIdx.x;
     int idx = blockIdx.x * 64 + (tid & 63);          // row / column handled by this thread
-    bool isrow = (tid < 64) && idx < R, iscol = (tid >= 64) && idx < R;
-    // issue this thread's panel loads first: they overlap the A11 factorization
+    bool isrow = (tid < 64) && idx < R, iscol = (tid >= 64 && tid < 128) && idx < R;
+    // threads 0..127: 64 rows of A21 + 64 columns of A12; warp 4: the LU of the diagonal block.
+    // The panel loads are issued first so that they overlap the A11 factorisation.
     T v[NB];
     long long row = t + nbe + idx, col = t + nbe + idx;
     if (isrow) {
@@ -280,26 +281,27 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
         D[r][c] = val;
     }
     __syncthreads();
-    // unblocked LU of the NB x NB diagonal block by the first warp (lane r owns row r)
-    if (tid < 32) {
-        int r = tid & 15;
-        T rowv[NB];
+    // unblocked LU of the NB x NB diagonal block by one warp (lane r owns row r)
+    // (the LU warp reuses v[] for its row: it holds no panel data)
+    if (tid >= 128) {
+        int lane = tid - 128;
+        int r = lane & (NB - 1);
 #pragma unroll
-        for (int c = 0; c < NB; ++c) rowv[c] = D[r][c];
+        for (int c = 0; c < NB; ++c) v[c] = D[r][c];
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-            T piv = Sc<T>::inv(shfl_row(rowv[c], c));       // pivot row c is final now
-            T l = rowv[c] * piv;
-            if (r > c) rowv[c] = l;
+            T piv = Sc<T>::inv(shfl_row(v[c], c));       // pivot row c is final now
+            T l = v[c] * piv;
+            if (r > c) v[c] = l;
 #pragma unroll
             for (int cc = c + 1; cc < NB; ++cc) {
-                T u = shfl_row(rowv[cc], c);
-                if (r > c) rowv[cc] -= l * u;
+                T u = shfl_row(v[cc], c);
+                if (r > c) v[cc] -= l * u;
             }
         }
-        if (tid < NB) {
+        if (lane < NB) {
 #pragma unroll
-            for (int c = 0; c < NB; ++c) D[r][c] = rowv[c];
+            for (int c = 0; c < NB; ++c) D[r][c] = v[c];
         }
     }
     __syncthreads();
@@ -308,13 +310,13 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
         for (int e = tid; e < NB * NB; e += blockDim.x) S[e] = D[e % NB][e / NB];
     }
     if (isrow) {
-        // row a of A21:  v U11 = row
+        // row a of A21:  v U11 = row   (two interleaved accumulators shorten the fp64 dependency chain)
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-            T acc = v[c];
+            T acc0 = v[c], acc1 = Sc<T>::zero();
 #pragma unroll
-            for (int c2 = 0; c2 < c; ++c2) acc -= v[c2] * D[c2][c];
-            v[c] = acc * Sc<T>::inv(D[c][c]);
+            for (int c2 = 0; c2 < c; ++c2) { if (c2 & 1) acc1 -= v[c2] * D[c2][c]; else acc0 -= v[c2] * D[c2][c]; }
+            v[c] = (acc0 + acc1) * Sc<T>::inv(D[c][c]);
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) if (c < nbe) A[row + (t + c) * (long long)ld] = v[c];
@@ -322,10 +324,10 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
         // column b of A12:  L11 w = col (unit lower)
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
-            T acc = v[r];
+            T acc0 = v[r], acc1 = Sc<T>::zero();
 #pragma unroll
-            for (int r2 = 0; r2 < r; ++r2) acc -= D[r][r2] * v[r2];
-            v[r] = acc;
+            for (int r2 = 0; r2 < r; ++r2) { if (r2 & 1) acc1 -= D[r][r2] * v[r2]; else acc0 -= D[r][r2] * v[r2]; }
+            v[r] = acc0 + acc1;
         }
         T* cp = A + col * (long long)ld + t;
 #pragma unroll
@@ -333,7 +335,7 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
     }
 }
 
-template <typename T>
+template <typename T, int NB>
 __global__ void __launch_bounds__(256)
 k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, const T* __restrict__ scratch) {
     __shared__ T Ls[NB][32];
@@ -382,221 +384,12 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     if (m1 && n1) c01[16] = old11 - acc11;
 }
 
-// ---------------------------------------------------- two-level blocking -----
-// The NB = 16 scheme above is a chain of 2 * n2 / 16 dependent launches whose length, not
-// the flops, sets the factorisation time.  For panels that fit shared memory the outer block
-// is NBB = 64 columns: k_panel64 factors a whole 64-column panel inside ONE CTA per 64-row
-// chunk (four 16-column sub-steps with the panel resident in shared memory: no global
-// round trips, no launches), k_update64 applies the rank-64 update.  Column chunks hold rows
-// of A21 and the block A11; row chunks hold columns of A12 TRANSPOSED together with A11^T:
-// running the same Doolittle code on the transposed view yields U' = D L11^T, so
-// U12^T = (A12^T U'^-1) D -- both panel kinds share one code path.
-static const int NBB = 64;
-static const int GS = NBB + 1;      // shared-memory row pitch (elements)
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_panel64(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t0, T* __restrict__ scratch, int chunks) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* G = reinterpret_cast<T*>(smem_raw);            // [NBB][GS]  view of A11 (row chunk: transposed)
-    T* Q = G + NBB * GS;                              // [NBB][GS]  64 panel rows x 64 panel columns
-    T* A = LU + (size_t)blockIdx.y * nel + pw;        // dense view base
-    const int tid = threadIdx.x;
-    const bool rowpanel = (int)blockIdx.x >= chunks;
-    const int ch = rowpanel ? blockIdx.x - chunks : blockIdx.x;
-    const int nbb = (int)min((long long)NBB, n2 - t0);
-    const int R = (int)min((long long)p, n2 - (t0 + nbb));
-    const long long pbase = t0 + nbb + 64LL * ch;     // first global row (column) of this chunk
-    const int nq = (int)max(0LL, min(64LL, (long long)R - 64LL * ch));   // valid panel rows in this chunk
-    const T zero = Sc<T>::zero(), one = Sc<T>::one();
-    // ---- load (band-masked: entries farther than pw from the diagonal are not stored = zero)
-    for (int e = tid; e < NBB * NBB; e += 256) {
-        int r = e % NBB, c = e / NBB;                  // consecutive threads -> consecutive global rows
-        T g = (r == c) ? one : zero;
-        if (r < nbb && c < nbb) g = (abs(r - c) <= pw) ? A[(t0 + r) + (t0 + c) * (long long)ld] : zero;
-        if (!rowpanel) G[r * GS + c] = g; else G[c * GS + r] = g;
-        T q = zero;
-        if (r < nq && c < nbb) {
-            long long gr = pbase + r, gc = t0 + c;
-            if (gr - gc <= pw) q = rowpanel ? A[gc + gr * (long long)ld] : A[gr + gc * (long long)ld];
-        }
-        Q[r * GS + c] = q;
-    }
-    __syncthreads();
-    for (int o = 0; o < NBB; o += NB) {
-        // ---- a. unblocked LU of the 16 x 16 diagonal sub-block by warp 0 (lane r owns row r)
-        if (tid < 32) {
-            int r = tid & 15;
-            T rowv[NB];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) rowv[c] = G[(o + r) * GS + o + c];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                T piv = Sc<T>::inv(shfl_row(rowv[c], c));
-                T l = rowv[c] * piv;
-                if (r > c) rowv[c] = l;
-#pragma unroll
-                for (int cc = c + 1; cc < NB; ++cc) {
-                    T u = shfl_row(rowv[cc], c);
-                    if (r > c) rowv[cc] -= l * u;
-                }
-            }
-            if (tid < NB) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c) G[(o + r) * GS + o + c] = rowv[c];
-            }
-        }
-        __syncthreads();
-        // ---- b. triangular solves against the sub-block
-        //   threads   0.. 63 : panel rows      q U^-1
-        //   threads  64..127 : rows of G below the sub-block   g U^-1   (L part)
-        //   threads 128..191 : columns of G right of the sub-block   L^-1 g   (U part)
-        {
-            T v[NB];
-            const int grp = tid >> 6, idx = tid & 63;
-            if (grp == 0 || (grp == 1 && idx >= o + NB)) {
-                T* rowp = (grp == 0 ? Q : G) + idx * GS + o;
-#pragma unroll
-                for (int c = 0; c < NB; ++c) v[c] = rowp[c];
-#pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    T acc = v[c];
-#pragma unroll
-                    for (int c2 = 0; c2 < c; ++c2) acc -= v[c2] * G[(o + c2) * GS + o + c];
-                    v[c] = acc * Sc<T>::inv(G[(o + c) * GS + o + c]);
-                }
-#pragma unroll
-                for (int c = 0; c < NB; ++c) rowp[c] = v[c];
-            } else if (grp == 2 && idx >= o + NB) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r) v[r] = G[(o + r) * GS + idx];
-#pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    T acc = v[r];
-#pragma unroll
-                    for (int r2 = 0; r2 < r; ++r2) acc -= G[(o + r) * GS + o + r2] * v[r2];
-                    v[r] = acc;
-                }
-#pragma unroll
-                for (int r = 0; r < NB; ++r) G[(o + r) * GS + idx] = v[r];
-            }
-        }
-        __syncthreads();
-        // ---- c. trailing update inside the panel: rows (64 panel rows + rows of G below) x later columns
-        if (o + NB < NBB) {
-            const int rr = tid & 127, cg = tid >> 7;     // row task, column parity
-            const bool isq = rr < 64;
-            const int gr = isq ? rr : (o + NB + (rr - 64));           // G row for rr >= 64
-            if (isq || gr < NBB) {
-                T* rowp = (isq ? Q : G) + (isq ? rr : gr) * GS;
-                T l[NB];
-#pragma unroll
-                for (int k = 0; k < NB; ++k) l[k] = rowp[o + k];
-                // four independent accumulator chains per thread (fp64 FMA latency, not rate, is the limit)
-                for (int c = o + NB + cg; c < NBB; c += 8) {
-                    T a0 = rowp[c], a1 = (c + 2 < NBB) ? rowp[c + 2] : zero, a2 = (c + 4 < NBB) ? rowp[c + 4] : zero, a3 = (c + 6 < NBB) ? rowp[c + 6] : zero;
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        const T* gk = G + (o + k) * GS + c;
-                        a0 -= l[k] * gk[0];
-                        if (c + 2 < NBB) a1 -= l[k] * gk[2];
-                        if (c + 4 < NBB) a2 -= l[k] * gk[4];
-                        if (c + 6 < NBB) a3 -= l[k] * gk[6];
-                    }
-                    rowp[c] = a0;
-                    if (c + 2 < NBB) rowp[c + 2] = a1;
-                    if (c + 4 < NBB) rowp[c + 4] = a2;
-                    if (c + 6 < NBB) rowp[c + 6] = a3;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    // ---- store
-    if (rowpanel) {
-        // U12^T = (A12^T U'^-1) D, D = diag(U') ; transposed store
-        for (int e = tid; e < NBB * NBB; e += 256) {
-            int c = e % NBB, r = e / NBB;               // consecutive threads -> consecutive global rows (= panel col c)
-            if (r < nq && c < nbb) {
-                long long gr = pbase + r, gc = t0 + c;
-                if (gr - gc <= pw) A[gc + gr * (long long)ld] = Q[r * GS + c] * G[c * GS + c];
-            }
-        }
-    } else {
-        for (int e = tid; e < NBB * NBB; e += 256) {
-            int r = e % NBB, c = e / NBB;
-            if (r < nq && c < nbb) {
-                long long gr = pbase + r, gc = t0 + c;
-                if (gr - gc <= pw) A[gr + gc * (long long)ld] = Q[r * GS + c];
-            }
-        }
-        if (ch == 0) {
-            // park the factored diagonal block (other CTAs may still be reading A11)
-            T* S = scratch + (size_t)blockIdx.y * NBB * NBB;
-            for (int e = tid; e < NBB * NBB; e += 256) S[e] = G[(e % NBB) * GS + e / NBB];
-        }
-    }
-}
-
-// A22 -= L21 (R x 64) U12 (64 x R) on 32 x 32 tiles; tile (0,0) also copies the parked diagonal block in place
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_update64(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t0, const T* __restrict__ scratch) {
-    __shared__ T Ls[NB][32];
-    __shared__ T Us[NB][33];
-    T* A = LU + (size_t)blockIdx.z * nel + pw;
-    const int nbb = (int)min((long long)NBB, n2 - t0);
-    const int R = (int)min((long long)p, n2 - (t0 + nbb));
-    const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
-    const int tid = threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
-        const T* S = scratch + (size_t)blockIdx.z * NBB * NBB;
-        for (int e = tid; e < NBB * NBB; e += 256) {
-            int r = e % NBB, c = e / NBB;
-            if (r < nbb && c < nbb && abs(r - c) <= pw) A[(t0 + r) + (t0 + c) * (long long)ld] = S[e];
-        }
-    }
-    if (a0 >= R || b0 >= R) return;
-    const long long r0 = t0 + nbb + a0, c0 = t0 + nbb + b0;
-    const int ta = tid % 16, tb = tid / 16;
-    const bool m0 = (a0 + ta < R), m1 = (a0 + ta + 16 < R), n0 = (b0 + tb < R), n1 = (b0 + tb + 16 < R);
-    T* c00 = A + (r0 + ta) + (c0 + tb) * (long long)ld;
-    T* c01 = A + (r0 + ta) + (c0 + tb + 16) * (long long)ld;
-    T old00 = (m0 && n0) ? c00[0] : Sc<T>::zero(), old10 = (m1 && n0) ? c00[16] : Sc<T>::zero();
-    T old01 = (m0 && n1) ? c01[0] : Sc<T>::zero(), old11 = (m1 && n1) ? c01[16] : Sc<T>::zero();
-    T acc00 = Sc<T>::zero(), acc01 = Sc<T>::zero(), acc10 = Sc<T>::zero(), acc11 = Sc<T>::zero();
-    for (int k0 = 0; k0 < nbb; k0 += NB) {
-        for (int e = tid; e < NB * 32; e += 256) {
-            int a = e % 32, c = e / 32;
-            long long gr = r0 + a, gc = t0 + k0 + c;
-            Ls[c][a] = (a0 + a < R && k0 + c < nbb && gr - gc <= pw) ? A[gr + gc * (long long)ld] : Sc<T>::zero();
-        }
-        for (int e = tid; e < NB * 32; e += 256) {
-            int c = e % NB, bq = e / NB;
-            long long gr = t0 + k0 + c, gc = c0 + bq;
-            Us[c][bq] = (b0 + bq < R && k0 + c < nbb && gc - gr <= pw) ? A[gr + gc * (long long)ld] : Sc<T>::zero();
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < NB; ++c) {
-            T l0 = Ls[c][ta], l1 = Ls[c][ta + 16];
-            T u0 = Us[c][tb], u1 = Us[c][tb + 16];
-            acc00 += l0 * u0; acc01 += l0 * u1; acc10 += l1 * u0; acc11 += l1 * u1;
-        }
-        __syncthreads();
-    }
-    if (m0 && n0) c00[0] = old00 - acc00;
-    if (m1 && n0) c00[16] = old10 - acc10;
-    if (m0 && n1) c01[0] = old01 - acc01;
-    if (m1 && n1) c01[16] = old11 - acc11;
-}
-
 // After the factorisation every NB x NB diagonal block holds L11 \ U11.  The triangular solves
 // with those blocks are the sequential heart of the substitution kernels, so they are replaced
 // once, here (fully parallel: one warp per block), by the explicit inverses
 //   strictly lower part <- inv(L11) (unit diagonal implicit),  upper part <- inv(U11),
 // which turns every block step of k_band_solve into two small dependency-free mat-vecs.
-template <typename T>
+template <typename T, int NB>
 __global__ void k_invert_diag(T* __restrict__ LU, size_t nel, long long n2, int pw, int ld) {
     __shared__ T D[NB][NB + 1];
     T* A = LU + (size_t)blockIdx.y * nel + pw;
@@ -610,32 +403,34 @@ __global__ void k_invert_diag(T* __restrict__ LU, size_t nel, long long n2, int 
         D[r][c] = val;
     }
     __syncwarp();
-    T xl[NB], xu[NB];
-    int j = lane & 15;
-    // column j of inv(L), L unit lower
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-        T acc = (r == j) ? Sc<T>::one() : Sc<T>::zero();
-#pragma unroll
-        for (int k = 0; k < r; ++k) if (k >= j) acc -= D[r][k] * xl[k];
-        xl[r] = (r >= j) ? acc : Sc<T>::zero();
-    }
-    // column j of inv(U), U upper with diagonal
-#pragma unroll
-    for (int r = NB - 1; r >= 0; --r) {
-        T acc = (r == j) ? Sc<T>::one() : Sc<T>::zero();
-#pragma unroll
-        for (int k = r + 1; k < NB; ++k) if (k <= j) acc -= D[r][k] * xu[k];
-        xu[r] = (r <= j) ? acc * Sc<T>::inv(D[r][r]) : Sc<T>::zero();
-    }
-    __syncwarp();
-    if (lane < NB && j < nbe) {
+    int j = lane & (NB - 1);
+    const bool wr = lane < NB && j < nbe;
+    {   // column j of inv(L), L unit lower  -> strictly lower part
+        T xl[NB];
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
-            if (r < nbe) {
-                if (r > j) A[(t + r) + (t + j) * (long long)ld] = xl[r];
-                else A[(t + r) + (t + j) * (long long)ld] = xu[r];
-            }
+            T acc = (r == j) ? Sc<T>::one() : Sc<T>::zero();
+#pragma unroll
+            for (int k = 0; k < r; ++k) if (k >= j) acc -= D[r][k] * xl[k];
+            xl[r] = (r >= j) ? acc : Sc<T>::zero();
+        }
+        if (wr) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) if (r < nbe && r > j) A[(t + r) + (t + j) * (long long)ld] = xl[r];
+        }
+    }
+    {   // column j of inv(U), U upper with diagonal -> upper part (D still holds the factors)
+        T xu[NB];
+#pragma unroll
+        for (int r = NB - 1; r >= 0; --r) {
+            T acc = (r == j) ? Sc<T>::one() : Sc<T>::zero();
+#pragma unroll
+            for (int k = r + 1; k < NB; ++k) if (k <= j) acc -= D[r][k] * xu[k];
+            xu[r] = (r <= j) ? acc * Sc<T>::inv(D[r][r]) : Sc<T>::zero();
+        }
+        if (wr) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) if (r < nbe && r <= j) A[(t + r) + (t + j) * (long long)ld] = xu[r];
         }
     }
 }
@@ -653,62 +448,36 @@ struct FactorGraph { FactorGraphKey key; cudaGraphExec_t exec; unsigned long lon
 static std::vector<FactorGraph> g_graphs;
 static unsigned long long g_stamp = 0;
 
-// 16 = single-level blocking (default); 64 = two-level blocking (env CS_FACTOR_BLOCK=64).  The
-// two-level path is bit-for-bit tested but measured slower on B200 for p = 109 (113 ms vs 92 ms
-// for the C2 sweep): the 64-column panel kernel is a long chain of dependent fp64 operations in
-// one CTA.  Kept selectable for wider bands / future tuning.
-static int g_factor_block = -1;
-
-template <typename T>
+template <typename T, int NB>
 static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, cudaStream_t st) {
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
     int tiles = (bp.p + 31) / 32;
     int chunks = (bp.p + 63) / 64;
-    if (g_factor_block == 64) {
-        size_t smb = 2 * (size_t)NBB * GS * sizeof(T);
-        for (long long t = 0; t < bp.n2; t += NBB) {
-            dim3 gp(2 * chunks, nsys);
-            k_panel64<T><<<gp, 256, smb, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, chunks);
-            dim3 g(tiles, tiles, nsys);
-            k_update64<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
-        }
-        dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
-        k_invert_diag<T><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
-        return CS_OK;
-    }
     for (long long t = 0; t < bp.n2; t += NB) {
         dim3 gp(chunks, nsys);
-        k_lu_panel<T><<<gp, 128, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch);
+        k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch);
         dim3 g(tiles, tiles, nsys);
-        k_lu_update<T><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
+        k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
     }
     dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
-    k_invert_diag<T><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
+    k_invert_diag<T, NB><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
     return CS_OK;
 }
 
-template <typename T>
+template <typename T, int NB>
 static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
-    CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
-    if (g_factor_block < 0) {
-        const char* e = getenv("CS_FACTOR_BLOCK");
-        g_factor_block = (e && atoi(e) == 64) ? 64 : 16;
-    }
-    {
-        static bool attr = false;                // per instantiation
-        if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_panel64<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NBB * GS * sizeof(T)))); attr = true; }
-    }
+    CS_CHECK(bp.nb == NB, "band plan block size must equal the instantiated NB");
     static void* scratch = nullptr;
     static size_t scratch_bytes = 0;
-    size_t need = (size_t)nsys * NBB * NBB * sizeof(T);
+    size_t need = (size_t)nsys * NB * NB * sizeof(T);
     if (need > scratch_bytes) {
         if (scratch) cudaFree(scratch);
         if (need < (1u << 20)) need = 1u << 20;
         CS_CUDA(cudaMalloc(&scratch, need));
         scratch_bytes = need;
     }
-    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * g_factor_block};
+    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB};
     for (auto& g : g_graphs)
         if (g.key == key) {
             g.stamp = ++g_stamp;
@@ -737,7 +506,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
         for (int g = 0; g < groups && okq; ++g) {
             int s0 = (int)((long long)nsys * g / groups), s1 = (int)((long long)nsys * (g + 1) / groups);
             cudaStream_t sg = (g == 0) ? st : aux[g - 1];
-            okq = okq && band_factor_enqueue<T>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NBB * NBB, sg) == CS_OK;
+            okq = okq && band_factor_enqueue<T, NB>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NB * NB, sg) == CS_OK;
         }
         for (int g = 1; g < groups; ++g) {
             okq = okq && cudaEventRecord(ev_join[g - 1], aux[g - 1]) == cudaSuccess;
@@ -749,7 +518,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     }
     if (!captured) {
         cudaGetLastError();                 // capture unavailable: plain launches (same kernels)
-        CS_TRY(band_factor_enqueue<T>(bp, LU, nsys, (T*)scratch, st));
+        CS_TRY((band_factor_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st)));
         CS_CUDA(cudaGetLastError());
         return CS_OK;
     }
@@ -763,9 +532,359 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_CUDA(cudaGraphLaunch(exec, st));
     return CS_OK;
 }
+// ------------------------------------------------- cluster-resident LU ------
+// The step-per-launch chain above is bound by launch boundaries and cold global round trips
+// (~17 us per 16-column block step).  When the active window fits, the whole factorisation of
+// one system is instead done by ONE thread-block cluster that keeps the window in (distributed)
+// shared memory for the entire sweep:
+//   * block column jb (NB columns = one contiguous NB*ldab chunk of the band array) is owned by
+//     CTA jb % C; it is loaded ONCE (cp.async) when it enters the window, updated in shared
+//     memory by the ~p/NB panels that touch it, factored by its owner and stored ONCE;
+//   * the factorisation is the block LDU variant: the NB x NB pivot block is replaced by its full
+//     inverse (in-place Gauss-Jordan, one element per thread), L21 = A21 inv(D), U12 = A12 stays
+//     as it is -- so no triangular solves sit on the critical path and the trailing update reads
+//     the pivot rows in place (BandPlan::diag_full tells k_band_solve about the format);
+//   * the factored panel L21 is published through a small global (L2) buffer and a split cluster
+//     barrier (arrive.release after publishing / wait.acquire after the CTA's own updates), so
+//     the next owner's  update -> invert -> publish  chain is the only critical path and the
+//     other CTAs' trailing updates overlap it (look-ahead).
+// HBM traffic: the band array is read once and written once.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cp_async16_cg(void* dst_smem, const void* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_ca(void* dst_smem, const void* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(cplx* d, const cplx* s) { cp_async16_cg(d, s); }
+__device__ __forceinline__ void cp_async_elem(double* d, const double* s) { cp_async8_ca(d, s); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+static const int CL_THREADS = 256;
+// optional phase timers (CS_BAND_PROF=1): thread 0 of every CTA accumulates clock64 deltas
+#define CL_TICK(i) do { if (prof && threadIdx.x == 0) { long long t_ = clock64(); prof_s[i] += t_ - *tprev; *tprev = t_; } } while (0)
+
+struct ClusterLuGeom {
+    long long n2; int p, pw, ldab;
+    int nblk;     // number of NB-column blocks
+    int nbw;      // blocks a panel reaches to its right: ceil(p / NB)
+    int sl;       // chunk slots per CTA: ceil((nbw + 1) / C)
+    int prs;      // panel leading dimension: roundup(p, 4)
+};
+
+// trailing update of the own blocks first, first + C, ... by panel kb:  A[i][j] -= L21[i][:] A12[:][j]
+// TR x 4 register tile per thread.  Lanes run along rows and a thread's TR rows are `ngr` apart, so
+// every L / accumulator access of a warp is one contiguous run (no bank conflicts); the A12 rows are
+// read in place from the chunk (same address across the warp: broadcast).
+template <typename T, int NB, int TR>
+__device__ __forceinline__ void cl_trailing(const ClusterLuGeom& g, T* chunks, const T* Lb,
+                                            int kb, int R, int first, int nown, int C) {
+    const int ld = g.ldab - 1;
+    const size_t CH = (size_t)NB * g.ldab;
+    const int ngr = (R + TR - 1) / TR, ngc = nown * (NB / 4);
+    const long long lim = (long long)(kb + 1) * NB + R;     // first column the panel does not reach
+    for (int it = threadIdx.x; it < ngr * ngc; it += CL_THREADS) {
+        int rg = it % ngr, cg = it / ngr;
+        int ci0 = cg * 4, b = ci0 / NB, c0 = ci0 % NB;
+        int jb = first + C * b;
+        T* blk = chunks + (size_t)((jb / C) % g.sl) * CH + g.pw + (long long)c0 * ld;
+        T* q = blk + (kb + 1 - jb) * NB + rg;               // rows below the pivot block
+        const T* uq = blk + (kb - jb) * NB;                 // the pivot block's rows of these columns
+        long long gc0 = (long long)jb * NB + c0;
+        bool cv[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) cv[cc] = gc0 + cc < lim;
+        T acc[TR][4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < TR; ++rr)
+                acc[rr][cc] = (rg + rr * ngr < R && cv[cc]) ? q[rr * ngr + cc * ld] : Sc<T>::zero();
+        const T* lp = Lb + rg;
+#pragma unroll 4
+        for (int k = 0; k < NB; ++k) {
+            T l[TR], u[4];
+#pragma unroll
+            for (int rr = 0; rr < TR; ++rr) l[rr] = lp[rr * ngr + k * g.prs];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) u[cc] = cv[cc] ? uq[k + cc * ld] : Sc<T>::zero();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int rr = 0; rr < TR; ++rr) acc[rr][cc] -= l[rr] * u[cc];
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < TR; ++rr)
+                if (rg + rr * ngr < R && cv[cc]) q[rr * ngr + cc * ld] = acc[rr][cc];
+    }
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void cl_process(const ClusterLuGeom& g, T* chunks, const T* Lb,
+                                           int kb, int R, int first, int nown, int C) {
+    if (nown <= 0) return;                                   // (uniform per CTA)
+    // few work items: the narrower register tile keeps all warps busy
+    int items4 = ((R + 3) / 4) * (nown * NB / 4);
+    if (items4 <= CL_THREADS / 2) cl_trailing<T, NB, 2>(g, chunks, Lb, kb, R, first, nown, C);
+    else cl_trailing<T, NB, 4>(g, chunks, Lb, kb, R, first, nown, C);
+}
+
+// factor block column kb (resident in `chunk`): D <- inv(D) by an in-place Gauss-Jordan sweep without
+// pivoting (one element per thread, one barrier per pivot), L21 <- A21 inv(D); publish L21 to P
+template <typename T, int NB>
+__device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunk, T* __restrict__ P, T (*Di)[NB + 1], T (*rowb)[NB],
+                                          T (*colb)[NB], int kb, long long* prof, long long* prof_s, long long* tprev) {
+    static_assert(NB * NB == CL_THREADS, "one thread per element of the diagonal block");
+    const int ld = g.ldab - 1;
+    T* sv = chunk + g.pw;
+    const int tid = threadIdx.x;
+    const int nbe = (int)min((long long)NB, g.n2 - (long long)kb * NB);
+    const int R = (int)min((long long)g.p, g.n2 - ((long long)kb * NB + nbe));
+    const int r = tid % NB, c = tid / NB;
+    T a = (r == c) ? Sc<T>::one() : Sc<T>::zero();           // a short last block is padded with the identity
+    if (r < nbe && c < nbe) a = sv[r + (long long)c * ld];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const int buf = k & 1;
+        if (r == k) rowb[buf][c] = a;
+        if (c == k) colb[buf][r] = a;
+        __syncthreads();
+        T pv = Sc<T>::inv(rowb[buf][k]);
+        T rk = rowb[buf][c] * pv;                            // a[k][c] / pivot
+        T ck = colb[buf][r];                                 // a[r][k]
+        if (r == k) a = (c == k) ? pv : rk;
+        else a = (c == k) ? Sc<T>::zero() - ck * pv : a - ck * rk;
+    }
+    Di[r][c] = a;
+    if (r < nbe && c < nbe) sv[r + (long long)c * ld] = a;
+    __syncthreads();
+    CL_TICK(2);
+    // L21 = A21 inv(D): thread -> (row a, half of the columns); read everything, barrier, write in place
+    const int HALF = NB / 2;
+    for (int a0 = 0; a0 < R; a0 += CL_THREADS / 2) {
+        int ar = a0 + (tid % (CL_THREADS / 2)), h = tid / (CL_THREADS / 2);
+        T out[HALF];
+        if (ar < R) {
+            T row[NB];
+#pragma unroll
+            for (int c2 = 0; c2 < NB; ++c2) row[c2] = sv[NB + ar + (long long)c2 * ld];
+#pragma unroll
+            for (int cc = 0; cc < HALF; ++cc) {
+                T acc = Sc<T>::zero();
+#pragma unroll
+                for (int c2 = 0; c2 < NB; ++c2) acc += row[c2] * Di[c2][h * HALF + cc];
+                out[cc] = acc;
+            }
+        }
+        __syncthreads();
+        if (ar < R) {
+#pragma unroll
+            for (int cc = 0; cc < HALF; ++cc) {
+                int cq = h * HALF + cc;
+                sv[NB + ar + (long long)cq * ld] = out[cc];
+                P[ar + cq * g.prs] = out[cc];
+            }
+        }
+    }
+    __syncthreads();
+    CL_TICK(4);
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void cl_load_chunk(const ClusterLuGeom& g, T* chunk, const T* __restrict__ AB, int jb) {
+    if (jb >= g.nblk) return;
+    int ncols = (int)min((long long)NB, g.n2 - (long long)jb * NB);
+    const T* src = AB + (size_t)jb * NB * g.ldab;
+    for (int e = threadIdx.x; e < ncols * g.ldab; e += CL_THREADS) cp_async_elem(chunk + e, src + e);
+}
+template <typename T, int NB>
+__device__ __forceinline__ void cl_store_chunk(const ClusterLuGeom& g, const T* chunk, T* __restrict__ AB, int jb) {
+    int ncols = (int)min((long long)NB, g.n2 - (long long)jb * NB);
+    T* dst = AB + (size_t)jb * NB * g.ldab;
+    for (int e = threadIdx.x; e < ncols * g.ldab; e += CL_THREADS) dst[e] = chunk[e];
+}
+
+// grid = C * nsys CTAs in clusters of C; panels: per system 2 slots of prs * NB elements
+template <typename T, int NB>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict__ panels, long long* prof) {
+    __shared__ long long prof_s[12];
+    __shared__ long long tprev_s;
+    long long* tprev = &tprev_s;
+    if (threadIdx.x == 0) { for (int i = 0; i < 12; ++i) prof_s[i] = 0; tprev_s = clock64(); }
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+    const int sys = blockIdx.x / C;
+    T* AB = LU + (size_t)sys * nel;
+    const size_t CH = (size_t)NB * g.ldab;
+    T* chunks = reinterpret_cast<T*>(cl_smem);               // sl chunks (NB * ldab elements: 16-byte multiples)
+    T* Lb = chunks + (size_t)g.sl * CH;                      // panel L21: prs x NB
+    T (*Di)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(Lb + (size_t)g.prs * NB);
+    T (*rowb)[NB] = reinterpret_cast<T (*)[NB]>(Di + NB);
+    T (*colb)[NB] = rowb + 2;
+    T* P = panels + (size_t)sys * 2 * g.prs * NB;
+    const int psz16 = (int)((size_t)g.prs * NB * sizeof(T) / 16);
+
+    // prologue: the first window
+    for (int jb = rank; jb < g.sl * C && jb < g.nblk; jb += C) cl_load_chunk<T, NB>(g, chunks + (size_t)((jb / C) % g.sl) * CH, AB, jb);
+    cp_async_wait_all();
+    __syncthreads();
+    if (rank == 0) {
+        cl_factor<T, NB>(g, chunks, P, Di, rowb, colb, 0, nullptr, prof_s, tprev);
+        cl_store_chunk<T, NB>(g, chunks, AB, 0);
+        __syncthreads();
+        cl_load_chunk<T, NB>(g, chunks, AB, g.sl * C);
+    }
+    cluster_arrive();
+    cluster_wait();
+    if (threadIdx.x == 0) tprev_s = clock64();
+
+    for (int kb = 0; kb + 1 < g.nblk; ++kb) {
+        // panel kb -> shared (L2 only: it was written by another SM)
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(P + (size_t)(kb & 1) * g.prs * NB);
+            uint4* dst = reinterpret_cast<uint4*>(Lb);
+            for (int e = threadIdx.x; e < psz16; e += CL_THREADS) cp_async16_cg(dst + e, src + e);
+        }
+        cp_async_wait_all();                                 // also the chunk that entered during the previous step
+        __syncthreads();
+        CL_TICK(0);
+        const int R = (int)min((long long)g.p, g.n2 - (long long)(kb + 1) * NB);
+        const int last = min(kb + g.nbw, g.nblk - 1);        // right-most block panel kb reaches
+        int first = kb + 1 + (((rank - (kb + 1)) % C) + C) % C;
+        int nown = (first <= last) ? (last - first) / C + 1 : 0;
+        if (rank == (kb + 1) % C) {
+            // look-ahead: bring block kb+1 up to date, factor and publish it, then do the rest
+            cl_process<T, NB>(g, chunks, Lb, kb, R, first, 1, C);
+            __syncthreads();
+            CL_TICK(1);
+            T* chunk = chunks + (size_t)(((kb + 1) / C) % g.sl) * CH;
+            cl_factor<T, NB>(g, chunk, P + (size_t)((kb + 1) & 1) * g.prs * NB, Di, rowb, colb, kb + 1, prof, prof_s, tprev);
+            cluster_arrive();
+            cl_process<T, NB>(g, chunks, Lb, kb, R, first + C, nown - 1, C);
+            __syncthreads();
+            CL_TICK(5);
+            cl_store_chunk<T, NB>(g, chunk, AB, kb + 1);
+            __syncthreads();
+            cl_load_chunk<T, NB>(g, chunk, AB, kb + 1 + g.sl * C);
+            CL_TICK(6);
+        } else {
+            cluster_arrive();
+            cl_process<T, NB>(g, chunks, Lb, kb, R, first, nown, C);
+            __syncthreads();
+            CL_TICK(7);
+        }
+        __syncthreads();
+        cluster_wait();
+        CL_TICK(8);
+    }
+    if (prof && threadIdx.x == 0) for (int i = 0; i < 12; ++i) prof[(size_t)blockIdx.x * 12 + i] = prof_s[i];
+}
+
+struct ClusterLuPlan { bool ok; int C; ClusterLuGeom g; size_t smem; };
+template <typename T, int NB>
+static ClusterLuPlan cluster_lu_plan(const BandPlan& bp) {
+    ClusterLuPlan pl{};
+    pl.ok = false;
+    const char* e = getenv("CS_BAND_LU");
+    if (e && !strcmp(e, "steps")) return pl;
+    // block LDU with explicitly inverted pivot blocks is only as accurate as those blocks are well
+    // conditioned (3-D FDEM-h test: cond ~ 1e10 curl-curl blocks -> backward error 3e-8): scalar fields only
+    if (!bp.scalar_field) return pl;
+    ClusterLuGeom& g = pl.g;
+    g.n2 = bp.n2; g.p = bp.p; g.pw = bp.pw; g.ldab = bp.ldab;
+    g.nblk = (int)((bp.n2 + NB - 1) / NB);
+    g.nbw = (bp.p + NB - 1) / NB;
+    g.prs = ((bp.p + 3) / 4) * 4;
+    if (bp.pw < g.nbw * NB || bp.p < 1) return pl;
+    const int cands[3] = {4, 8, 2};
+    for (int ci = 0; ci < 3; ++ci) {
+        int C = cands[ci];
+        if (C == 2 && g.nbw + 1 > 2) continue;
+        if (C != 2 && g.nbw + 1 <= 2) continue;
+        int sl = (g.nbw + 1 + C - 1) / C;
+        if (sl > 4) continue;
+        size_t CH = (size_t)NB * bp.ldab;
+        size_t el = (size_t)sl * CH + (size_t)g.prs * NB + (size_t)NB * (NB + 1) + 4 * (size_t)NB;
+        size_t bytes = el * sizeof(T);
+        if (bytes > 200 * 1024) continue;
+        pl.ok = true; pl.C = C; g.sl = sl; pl.smem = bytes;
+        return pl;
+    }
+    return pl;
+}
+
+template <typename T, int NB>
+static int band_factor_cluster(const BandPlan& bp, const ClusterLuPlan& pl, T* LU, int nsys, cudaStream_t st) {
+    static void* panels = nullptr;
+    static size_t panel_bytes = 0;
+    size_t need = (size_t)nsys * 2 * pl.g.prs * NB * sizeof(T);
+    if (need > panel_bytes) {
+        if (panels) cudaFree(panels);
+        if (need < (4u << 20)) need = 4u << 20;
+        CS_CUDA(cudaMalloc(&panels, need));
+        CS_CUDA(cudaMemset(panels, 0, need));
+        panel_bytes = need;
+    }
+    CS_CUDA(cudaFuncSetAttribute(k_band_lu_cluster<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nsys * pl.C));
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    long long* prof = nullptr;
+    const char* pe = getenv("CS_BAND_PROF");
+    if (pe && atoi(pe) > 0) CS_CUDA(cudaMalloc(&prof, (size_t)nsys * pl.C * 12 * sizeof(long long)));
+    CS_CUDA(cudaLaunchKernelEx(&cfg, k_band_lu_cluster<T, NB>, LU, bp.band_elems(), pl.g, (T*)panels, prof));
+    if (prof) {
+        // debugging aid: average cycles per block step and phase (0 panel load, 1 look-ahead update, 2 block inverse,
+        // 3 -, 4 L21 + publish, 5 owner's remaining update, 6 chunk store/load, 7 non-owner update, 8 barrier wait)
+        std::vector<long long> h((size_t)nsys * pl.C * 12);
+        CS_CUDA(cudaStreamSynchronize(st));
+        CS_CUDA(cudaMemcpy(h.data(), prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(prof);
+        double acc[12] = {0};
+        for (size_t i = 0; i < h.size(); ++i) acc[i % 12] += (double)h[i];
+        fprintf(stderr, "[cluster LU] C=%d sl=%d nblk=%d cycles/step (summed over the cluster's CTAs):", pl.C, pl.g.sl, pl.g.nblk);
+        for (int i = 0; i < 9; ++i) fprintf(stderr, " p%d=%.0f", i, acc[i] / nsys / pl.g.nblk);
+        fprintf(stderr, "\n");
+    }
+    return CS_OK;
+}
+
+template <typename T>
+static int band_factor_any(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
+    if (bp.nb == 16) {
+        ClusterLuPlan pl = cluster_lu_plan<T, 16>(bp);
+        if (pl.ok) { bp.diag_full = 1; return band_factor_cluster<T, 16>(bp, pl, LU, nsys, st); }
+        bp.diag_full = 0;
+        return band_factor_t<T, 16>(bp, LU, nsys, st);
+    }
+    CS_CHECK(bp.nb == 32, "band plan block size must be 16 or 32");
+    bp.diag_full = 0;
+    return band_factor_t<T, 32>(bp, LU, nsys, st);
+}
+int band_factor_launches(const BandPlan& bp, bool lu_cplx) {
+    if (bp.nb == 16) {
+        bool ok = lu_cplx ? cluster_lu_plan<cplx, 16>(bp).ok : cluster_lu_plan<double, 16>(bp).ok;
+        if (ok) return 1;
+    }
+    return 1 + 2 * (int)((bp.n2 + bp.nb - 1) / bp.nb);
+}
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st) {
-    if (lu_cplx) return band_factor_t<cplx>(bp, (cplx*)LU, nsys_tot, st);
-    return band_factor_t<double>(bp, (double*)LU, nsys_tot, st);
+    if (lu_cplx) return band_factor_any<cplx>(bp, (cplx*)LU, nsys_tot, st);
+    return band_factor_any<double>(bp, (double*)LU, nsys_tot, st);
 }
 
 // ---------------------------------------------------------- banded solve ----
@@ -777,7 +896,7 @@ int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaSt
 // Thread layout of k_band_solve: 4 threads per staged row (quarter q = tid & 3 owns block
 // columns q, q+4, q+8, q+12), so a block step is 4 cp.async + 4 complex FMAs + a 2-stage
 // shuffle reduction per thread instead of 16 + 16 sequential ones, and ~14 warps share the SM.
-template <typename TL, int TPR>
+template <typename TL, int TPR, int NB>
 __device__ __forceinline__ void prefetch_cols(TL* __restrict__ dst, int ldd, const TL* __restrict__ A, int ld,
                                               long long row0, int nrows, long long col0, int ncols) {
     // dst[r + c*ldd] = A[(row0 + r) + (col0 + c)*ld]
@@ -799,10 +918,10 @@ template <> __device__ __forceinline__ cplx shfl_xor_t<cplx>(cplx v, int m) {
     return mk(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
-template <typename TL, typename TV, int TPR>
-__global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 512))
+template <typename TL, typename TV, int TPR, int NB>
+__global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst) {
+                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int v = blockIdx.y, m = blockIdx.x;
     int f = shift_of_vec ? shift_of_vec[v] : 0;
@@ -814,7 +933,8 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     TV* win = reinterpret_cast<TV*>(ring + (size_t)nst * ssz);   // circular window, wsz = power of two >= p + 5 NB
     __shared__ TV yw[32][NB];                                 // per-warp copy of the block solution
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r16 = lane & 15, half = lane >> 4;              // block mat-vec: lane <-> (row, column parity)
+    constexpr int HALVES = 32 / NB;                           // NB = 16: two lanes share a row (column parity)
+    const int r16 = lane % NB, half = lane / NB;              // block mat-vec: lane <-> (row, column parity)
     const int urow = tid / TPR, uq = tid % TPR;               // window update: thread <-> (row, column group)
     const int wm = wsz - 1;
     const long long nsteps = (n2 + NB - 1) / NB;
@@ -826,7 +946,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             long long t2 = (long long)s * NB;
             int nbe2 = (int)min((long long)NB, n2 - t2);
             int R2 = (int)min((long long)p, n2 - (t2 + nbe2));
-            prefetch_cols<TL, TPR>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
+            prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
         }
         __pipeline_commit();
     };
@@ -855,13 +975,16 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
                 if (pe < n2) pend = b[pe];
             }
             // every warp computes y1 = inv(L11) b1 for itself: lane (r, half) sums the columns of its parity
+            // (block LDU factors have a unit block diagonal in L: nothing to apply)
             TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
+            if (!diag_full) {
 #pragma unroll
-            for (int i = 0; i < NB / 2; ++i) {
-                int c = 2 * i + half;
-                if (c < r16) yr += cur[r16 + c * ldd] * win[(t + c) & wm];
+                for (int i = 0; i < NB / HALVES; ++i) {
+                    int c = HALVES * i + half;
+                    if (c < r16) yr += cur[r16 + c * ldd] * win[(t + c) & wm];
+                }
             }
-            yr += shfl_xor_t<TV>(yr, 16);
+            if (HALVES == 2) yr += shfl_xor_t<TV>(yr, 16);
             if (lane < NB) yw[warp][lane] = yr;
             __syncwarp();
             if (warp == 0 && lane < nbe) b[t + lane] = yr;
@@ -889,7 +1012,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             long long t2 = tlast - (long long)s * NB;
             int nbe2 = (int)min((long long)NB, n2 - t2);
             int Ra2 = (int)min((long long)p, t2);
-            prefetch_cols<TL, TPR>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2);
+            prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2);
         }
         __pipeline_commit();
     };
@@ -918,11 +1041,11 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             }
             TV xr = zero;
 #pragma unroll
-            for (int i = 0; i < NB / 2; ++i) {
-                int c = 2 * i + half;
-                if (c >= r16 && c < nbe && r16 < nbe) xr += cur[(Ra + r16) + c * ldd] * win[(t + c) & wm];
+            for (int i = 0; i < NB / HALVES; ++i) {
+                int c = HALVES * i + half;
+                if ((diag_full || c >= r16) && c < nbe && r16 < nbe) xr += cur[(Ra + r16) + c * ldd] * win[(t + c) & wm];
             }
-            xr += shfl_xor_t<TV>(xr, 16);
+            if (HALVES == 2) xr += shfl_xor_t<TV>(xr, 16);
             if (lane < NB) yw[warp][lane] = xr;
             __syncwarp();
             if (warp == 0 && lane < nbe) b[t + lane] = xr;
@@ -942,23 +1065,23 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     __pipeline_wait_prior(0);
 }
 
-template <typename T, int TPR>
+template <typename T, int TPR, int NB>
 static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, int th, size_t sm, int wsz, int nst, cudaStream_t st) {
     static bool attr = false;                    // one flag per instantiation
-    if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024)); attr = true; }
+    if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024)); attr = true; }
     dim3 g(bp.nmodes, nvec);
-    k_band_solve<T, T, TPR><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst);
+    k_band_solve<T, T, TPR, NB><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
 
-template <typename T>
+template <typename T, int NB>
 static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, cudaStream_t st) {
     int rowsn = bp.p + NB;
-    int tpr = (4 * rowsn <= 512) ? 4 : (2 * rowsn <= 768 ? 2 : 1);
+    int tpr = (4 * rowsn <= 640) ? 4 : (2 * rowsn <= 768 ? 2 : 1);
     int th = ((tpr * rowsn + 31) / 32) * 32;
     if (th < 64) th = 64;
-    CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel (p + 16 <= 1024)");
+    CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel (p + NB <= 1024)");
     int wsz = 64;
     while (wsz < bp.p + 7 * NB) wsz <<= 1;
     size_t stage_b = (size_t)rowsn * NB * sizeof(T);
@@ -966,16 +1089,31 @@ static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const 
     if (nst > 6) nst = 6;
     CS_CHECK(nst >= 2, "half bandwidth too large for the shared-memory staged solve");
     size_t sm = (size_t)nst * stage_b + (size_t)wsz * sizeof(T);
-    if (tpr == 4) return band_solve_launch<T, 4>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
-    if (tpr == 2) return band_solve_launch<T, 2>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
-    return band_solve_launch<T, 1>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+    if (tpr == 4) return band_solve_launch<T, 4, NB>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+    if (tpr == 2) return band_solve_launch<T, 2, NB>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+    return band_solve_launch<T, 1, NB>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+}
+
+// block size of a plan: 32 halves the length of the dependent step chains, but the staged block
+// column (p + NB) x NB x 16 B must fit the shared-memory ring at least twice
+int band_choose_nb(int p) {
+    const char* e = getenv("CS_BAND_NB");
+    // 32-column block steps halve the chain length but each step costs 3x (measured on C2:
+    // factor 137 ms vs 84 ms, solve 25 vs 22 ms), so 16 is the default; CS_BAND_NB=32 opts in.
+    size_t stage32 = (size_t)(p + 32) * 32 * sizeof(cplx);
+    if (e && atoi(e) == 32 && 2 * stage32 + 16 * 1024 <= 200 * 1024) return 32;
+    return 16;
 }
 
 int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st) {
-    CS_CHECK(bp.nb == NB, "band plan block size must equal the compiled NB");
     CS_CHECK(lu_cplx == xm_cplx, "LU and mode vectors must have the same scalar type");
-    if (lu_cplx) return band_solve_t<cplx>(bp, (const cplx*)LU, (cplx*)xm, nvec, shift_of_vec_d, st);
-    return band_solve_t<double>(bp, (const double*)LU, (double*)xm, nvec, shift_of_vec_d, st);
+    if (bp.nb == 32) {
+        if (lu_cplx) return band_solve_t<cplx, 32>(bp, (const cplx*)LU, (cplx*)xm, nvec, shift_of_vec_d, st);
+        return band_solve_t<double, 32>(bp, (const double*)LU, (double*)xm, nvec, shift_of_vec_d, st);
+    }
+    CS_CHECK(bp.nb == 16, "band plan block size must be 16 or 32");
+    if (lu_cplx) return band_solve_t<cplx, 16>(bp, (const cplx*)LU, (cplx*)xm, nvec, shift_of_vec_d, st);
+    return band_solve_t<double, 16>(bp, (const double*)LU, (double*)xm, nvec, shift_of_vec_d, st);
 }
 
 }  // namespace cs

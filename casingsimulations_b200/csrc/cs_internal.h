@@ -61,9 +61,19 @@ struct BandPlan {
     int* jstr = nullptr;         // [n2] stride per theta step (0 = axis unknown)
     double* mdiag = nullptr;     // [n2] diagonal "mass" part multiplied by the shift s
     void* Kband = nullptr;       // [nmodes][n2*ldab] band of the s-independent part
+    // format of the factored diagonal blocks, set by band_factor: 0 = inv(L11) \ inv(U11) of the
+    // scalar LU, 1 = full inverse of the block pivot (block LDU: L21 = A21 inv(D), U12 = A12)
+    mutable int diag_full = 0;
+    // one unknown per (r, z) node (cell potentials, azimuthal edges): the NB x NB pivot blocks are
+    // well conditioned and may be inverted explicitly; curl-curl systems with several components
+    // per node have nearly singular pivot blocks and need the scalar LU
+    bool scalar_field = false;
     size_t band_elems() const { return (size_t)n2 * ldab; }
 };
 
+// block size (16 or 32) for a plan with half bandwidth p
+int band_choose_nb(int p);
+int band_factor_launches(const BandPlan& bp, bool lu_cplx);
 int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm /*[nvec][nmodes][n2]*/, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
 int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
 int band_probe_fill(const BandPlan& bp, int color, void* x3d, long long n3d, bool x_cplx, cudaStream_t st);
