@@ -376,7 +376,7 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     for (int c = 0; c < NB; ++c) {
         T l0 = Ls[c][ta], l1 = Ls[c][ta + 16];
         T u0 = Us[c][tb], u1 = Us[c][tb + 16];
-        acc00 += l0 * u0; acc01 += l0 * u1; acc10 += l1 * u0; acc11 += l1 * u1;
+        fmacc(acc00, l0, u0); fmacc(acc01, l0, u1); fmacc(acc10, l1, u0); fmacc(acc11, l1, u1);
     }
     if (m0 && n0) c00[0] = old00 - acc00;
     if (m1 && n0) c00[16] = old10 - acc10;
@@ -566,6 +566,9 @@ __device__ __forceinline__ void cp_async_elem(double* d, const double* s) { cp_a
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 static const int CL_THREADS = 256;
+#ifndef CL_INV
+#define CL_INV fast_inv
+#endif
 // optional phase timers (CS_BAND_PROF=1): thread 0 of every CTA accumulates clock64 deltas
 #define CL_TICK(i) do { if (prof && threadIdx.x == 0) { long long t_ = clock64(); prof_s[i] += t_ - *tprev; *tprev = t_; } } while (0)
 
@@ -575,54 +578,73 @@ struct ClusterLuGeom {
     int nbw;      // blocks a panel reaches to its right: ceil(p / NB)
     int sl;       // chunk slots per CTA: ceil((nbw + 1) / C)
     int prs;      // panel leading dimension: roundup(p, 4)
+    int split;    // row update of the look-ahead step on sub-partitions 2, 3 only
 };
 
-// trailing update of the own blocks first, first + C, ... by panel kb:  A[i][j] -= L21[i][:] A12[:][j]
-// TR x 4 register tile per thread.  Lanes run along rows and a thread's TR rows are `ngr` apart, so
-// every L / accumulator access of a warp is one contiguous run (no bank conflicts); the A12 rows are
-// read in place from the chunk (same address across the warp: broadcast).
+// One thread's TR x 4 register tile of the trailing update  A[i][j] -= L21[i][:] A12[:][j]  by panel kb.
+// Lanes run along rows and a thread's TR rows are `ngr` apart, so every L / accumulator access of a
+// warp is one contiguous run (no bank conflicts); the A12 rows are read in place from the chunk
+// (same address across the warp: broadcast).
 template <typename T, int NB, int TR>
-__device__ __forceinline__ void cl_trailing(const ClusterLuGeom& g, T* chunks, const T* Lb,
-                                            int kb, int R, int first, int nown, int C) {
-    const int ld = g.ldab - 1;
-    const size_t CH = (size_t)NB * g.ldab;
-    const int ngr = (R + TR - 1) / TR, ngc = nown * (NB / 4);
-    const long long lim = (long long)(kb + 1) * NB + R;     // first column the panel does not reach
-    for (int it = threadIdx.x; it < ngr * ngc; it += CL_THREADS) {
+struct ClTile {
+    T* q; const T* uq; const T* lp;
+    int ngr, ld, prs, rleft;      // rleft: rows left below this thread's first row
+    bool cv[4];
+    T acc[TR][4];
+    // item `it` of the update of rows [rbeg, R) of the own blocks first, first + C, ...
+    __device__ __forceinline__ void setup(const ClusterLuGeom& g, T* chunks, const T* Lb, int kb, int R, int rbeg,
+                                          int first, int C, int it) {
+        ld = g.ldab - 1; prs = g.prs;
+        const size_t CH = (size_t)NB * g.ldab;
+        ngr = (R - rbeg + TR - 1) / TR;
         int rg = it % ngr, cg = it / ngr;
         int ci0 = cg * 4, b = ci0 / NB, c0 = ci0 % NB;
         int jb = first + C * b;
         T* blk = chunks + (size_t)((jb / C) % g.sl) * CH + g.pw + (long long)c0 * ld;
-        T* q = blk + (kb + 1 - jb) * NB + rg;               // rows below the pivot block
-        const T* uq = blk + (kb - jb) * NB;                 // the pivot block's rows of these columns
-        long long gc0 = (long long)jb * NB + c0;
-        bool cv[4];
+        q = blk + (kb + 1 - jb) * NB + rbeg + rg;           // rows below the pivot block
+        uq = blk + (kb - jb) * NB;                          // the pivot block's rows of these columns
+        lp = Lb + rbeg + rg;
+        rleft = R - rbeg - rg;
+        long long gc0 = (long long)jb * NB + c0, lim = (long long)(kb + 1) * NB + R;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) cv[cc] = gc0 + cc < lim;
-        T acc[TR][4];
+        for (int cc = 0; cc < 4; ++cc) cv[cc] = gc0 + cc < lim;   // columns the panel reaches
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
             for (int rr = 0; rr < TR; ++rr)
-                acc[rr][cc] = (rg + rr * ngr < R && cv[cc]) ? q[rr * ngr + cc * ld] : Sc<T>::zero();
-        const T* lp = Lb + rg;
+                acc[rr][cc] = (rr * ngr < rleft && cv[cc]) ? q[rr * ngr + cc * ld] : Sc<T>::zero();
+    }
+    __device__ __forceinline__ void step(int k) {
+        T l[TR], u[4];
+#pragma unroll
+        for (int rr = 0; rr < TR; ++rr) l[rr] = lp[rr * ngr + k * prs];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) u[cc] = cv[cc] ? uq[k + cc * ld] : Sc<T>::zero();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < TR; ++rr) fmsub(acc[rr][cc], l[rr], u[cc]);
+    }
+    __device__ __forceinline__ void store() {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < TR; ++rr)
+                if (rr * ngr < rleft && cv[cc]) q[rr * ngr + cc * ld] = acc[rr][cc];
+    }
+};
+
+// rows [rbeg, R) of `nown` own blocks by the thread group (tix of nthr)
+template <typename T, int NB, int TR>
+__device__ __forceinline__ void cl_trailing(const ClusterLuGeom& g, T* chunks, const T* Lb,
+                                            int kb, int R, int rbeg, int first, int nown, int C, int tix, int nthr) {
+    const int ngr = (R - rbeg + TR - 1) / TR, ngc = nown * (NB / 4);
+    for (int it = tix; it < ngr * ngc; it += nthr) {
+        ClTile<T, NB, TR> t;
+        t.setup(g, chunks, Lb, kb, R, rbeg, first, C, it);
 #pragma unroll 4
-        for (int k = 0; k < NB; ++k) {
-            T l[TR], u[4];
-#pragma unroll
-            for (int rr = 0; rr < TR; ++rr) l[rr] = lp[rr * ngr + k * g.prs];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) u[cc] = cv[cc] ? uq[k + cc * ld] : Sc<T>::zero();
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-                for (int rr = 0; rr < TR; ++rr) acc[rr][cc] -= l[rr] * u[cc];
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-            for (int rr = 0; rr < TR; ++rr)
-                if (rg + rr * ngr < R && cv[cc]) q[rr * ngr + cc * ld] = acc[rr][cc];
+        for (int k = 0; k < NB; ++k) t.step(k);
+        t.store();
     }
 }
 
@@ -632,41 +654,100 @@ __device__ __forceinline__ void cl_process(const ClusterLuGeom& g, T* chunks, co
     if (nown <= 0) return;                                   // (uniform per CTA)
     // few work items: the narrower register tile keeps all warps busy
     int items4 = ((R + 3) / 4) * (nown * NB / 4);
-    if (items4 <= CL_THREADS / 2) cl_trailing<T, NB, 2>(g, chunks, Lb, kb, R, first, nown, C);
-    else cl_trailing<T, NB, 4>(g, chunks, Lb, kb, R, first, nown, C);
+    if (items4 <= CL_THREADS / 2) cl_trailing<T, NB, 2>(g, chunks, Lb, kb, R, 0, first, nown, C, threadIdx.x, CL_THREADS);
+    else cl_trailing<T, NB, 4>(g, chunks, Lb, kb, R, 0, first, nown, C, threadIdx.x, CL_THREADS);
 }
 
-// factor block column kb (resident in `chunk`): D <- inv(D) by an in-place Gauss-Jordan sweep without
-// pivoting (one element per thread, one barrier per pivot), L21 <- A21 inv(D); publish L21 to P
+// Factor block column kb (resident in `chunk`), optionally bringing it up to date with panel kb-1
+// (in Lb) first -- the look-ahead step that is the critical path of the whole sweep:
+//   1. the NB x NB pivot block gets its panel update (one element per thread);
+//   2. warps 0-1: D <- inv(D) by an in-place Gauss-Jordan sweep without pivoting (4 elements per
+//      thread, one 64-thread named barrier per pivot).  The sweep is a pure latency chain
+//      (reciprocal -> scale -> eliminate per pivot), so meanwhile the other warps apply the panel
+//      update to the rows BELOW the pivot block;
+//   3. L21 <- A21 inv(D), written in place and published to P.
 template <typename T, int NB>
-__device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunk, T* __restrict__ P, T (*Di)[NB + 1], T (*rowb)[NB],
-                                          T (*colb)[NB], int kb, long long* prof, long long* prof_s, long long* tprev) {
-    static_assert(NB * NB == CL_THREADS, "one thread per element of the diagonal block");
+__device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunks, T* chunk, const T* Lb, bool update,
+                                          T* __restrict__ P, T (*Di)[NB + 1], T (*rowb)[NB],
+                                          T (*colb)[NB], int kb, int C, int split, long long* prof, long long* prof_s, long long* tprev) {
+    static_assert(NB == 16 && CL_THREADS == 256, "thread <-> element mappings below");
     const int ld = g.ldab - 1;
     T* sv = chunk + g.pw;
     const int tid = threadIdx.x;
     const int nbe = (int)min((long long)NB, g.n2 - (long long)kb * NB);
     const int R = (int)min((long long)g.p, g.n2 - ((long long)kb * NB + nbe));
-    const int r = tid % NB, c = tid / NB;
-    T a = (r == c) ? Sc<T>::one() : Sc<T>::zero();           // a short last block is padded with the identity
-    if (r < nbe && c < nbe) a = sv[r + (long long)c * ld];
+    // rows of panel kb-1 that reach this block: its own NB rows + Rp - NB below
+    const int Rp = update ? (int)min((long long)g.p, g.n2 - (long long)kb * NB) : 0;
+    {
+        const int r = tid % NB, c = tid / NB;
+        T a = (r == c) ? Sc<T>::one() : Sc<T>::zero();       // a short last block is padded with the identity
+        if (r < nbe && c < nbe) {
+            a = sv[r + (long long)c * ld];
+            if (update) {
+                const T* uq = sv - NB + (long long)c * ld;   // rows of pivot block kb-1 in this column
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-        const int buf = k & 1;
-        if (r == k) rowb[buf][c] = a;
-        if (c == k) colb[buf][r] = a;
-        __syncthreads();
-        T pv = Sc<T>::inv(rowb[buf][k]);
-        T rk = rowb[buf][c] * pv;                            // a[k][c] / pivot
-        T ck = colb[buf][r];                                 // a[r][k]
-        if (r == k) a = (c == k) ? pv : rk;
-        else a = (c == k) ? Sc<T>::zero() - ck * pv : a - ck * rk;
+                for (int k = 0; k < NB; ++k) fmsub(a, Lb[r + k * g.prs], uq[k]);
+            }
+        }
+        Di[r][c] = a;
     }
-    Di[r][c] = a;
-    if (r < nbe && c < nbe) sv[r + (long long)c * ld] = a;
+    __syncthreads();
+    CL_TICK(1);
+    if (tid < 64) {
+        // in-place Gauss-Jordan, thread (r, cq) holds row r, columns 4 cq .. 4 cq + 3.  Pivot k:
+        //   a_kc <- a_kc / p;  a_rc -= (a_rk / p) a_kc;  a_rk <- -a_rk / p;  a_kk <- 1 / p
+        // (a 2 x 2 block-pivot variant was tried: 8 instead of 16 dependent steps, but each step
+        //  is so much longer for a lone warp that the sweep only went from 7.7k to 6.9k cycles.)
+        const int r = tid % NB, cq = tid / NB;
+        T a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = Di[r][cq * 4 + j];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const int buf = k & 1, kq = k / 4, kj = k % 4;
+            if (r == k) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rowb[buf][cq * 4 + j] = a[j];
+            }
+            if (cq == kq) colb[buf][r] = a[kj];
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            T pv = CL_INV(rowb[buf][k]);
+            // multiplier of the (unscaled) pivot row: rows != k eliminate with -a_rk / p, row k scales with 1 / p
+            T t = (r == k) ? pv : Sc<T>::zero() - colb[buf][r] * pv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = cq * 4 + j;
+                if (col == k) a[j] = t;
+                else {
+                    T v = (r == k) ? Sc<T>::zero() : a[j];
+                    fmacc(v, t, rowb[buf][col]);
+                    a[j] = v;
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");        // all reads of Di (pivot values) are long done; publish
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = cq * 4 + j;
+            Di[r][col] = a[j];
+            if (r < nbe && col < nbe) sv[r + (long long)col * ld] = a[j];
+        }
+        CL_TICK(3);
+    } else if (Rp > NB) {
+        // the Gauss-Jordan warps 0 and 1 sit on SM sub-partitions 0 and 1 (warp id mod 4).  With
+        // CS_BAND_SPLIT=1 the row update runs on warps 2, 3, 6, 7 (sub-partitions 2, 3) only, so that
+        // the latency chain does not queue behind their FP64 / LSU traffic: the sweep then takes 5.5k
+        // instead of 6.6k cycles, but the update needs two passes (7.2k vs 4.6k) -- off by default
+        const int w = tid >> 5;
+        long long tt0 = 0;
+        if (prof && tid == 64) tt0 = clock64();
+        if (!split) cl_trailing<T, NB, 2>(g, chunks, Lb, kb - 1, Rp, NB, kb, 1, C, tid - 64, CL_THREADS - 64);
+        else if ((w & 3) >= 2) cl_trailing<T, NB, 2>(g, chunks, Lb, kb - 1, Rp, NB, kb, 1, C, ((w >> 2) * 2 + (w & 1)) * 32 + (tid & 31), 128);
+        if (prof && tid == 64) prof_s[9] += clock64() - tt0;
+    }
     __syncthreads();
     CL_TICK(2);
-    // L21 = A21 inv(D): thread -> (row a, half of the columns); read everything, barrier, write in place
+    // L21 = A21 inv(D): thread -> (row, half of the columns); read everything, barrier, write in place
     const int HALF = NB / 2;
     for (int a0 = 0; a0 < R; a0 += CL_THREADS / 2) {
         int ar = a0 + (tid % (CL_THREADS / 2)), h = tid / (CL_THREADS / 2);
@@ -679,7 +760,7 @@ __device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunk, T* _
             for (int cc = 0; cc < HALF; ++cc) {
                 T acc = Sc<T>::zero();
 #pragma unroll
-                for (int c2 = 0; c2 < NB; ++c2) acc += row[c2] * Di[c2][h * HALF + cc];
+                for (int c2 = 0; c2 < NB; ++c2) fmacc(acc, row[c2], Di[c2][h * HALF + cc]);
                 out[cc] = acc;
             }
         }
@@ -737,7 +818,7 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
     cp_async_wait_all();
     __syncthreads();
     if (rank == 0) {
-        cl_factor<T, NB>(g, chunks, P, Di, rowb, colb, 0, nullptr, prof_s, tprev);
+        cl_factor<T, NB>(g, chunks, chunks, Lb, false, P, Di, rowb, colb, 0, C, g.split, nullptr, prof_s, tprev);
         cl_store_chunk<T, NB>(g, chunks, AB, 0);
         __syncthreads();
         cl_load_chunk<T, NB>(g, chunks, AB, g.sl * C);
@@ -762,11 +843,8 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
         int nown = (first <= last) ? (last - first) / C + 1 : 0;
         if (rank == (kb + 1) % C) {
             // look-ahead: bring block kb+1 up to date, factor and publish it, then do the rest
-            cl_process<T, NB>(g, chunks, Lb, kb, R, first, 1, C);
-            __syncthreads();
-            CL_TICK(1);
             T* chunk = chunks + (size_t)(((kb + 1) / C) % g.sl) * CH;
-            cl_factor<T, NB>(g, chunk, P + (size_t)((kb + 1) & 1) * g.prs * NB, Di, rowb, colb, kb + 1, prof, prof_s, tprev);
+            cl_factor<T, NB>(g, chunks, chunk, Lb, true, P + (size_t)((kb + 1) & 1) * g.prs * NB, Di, rowb, colb, kb + 1, C, g.split, prof, prof_s, tprev);
             cluster_arrive();
             cl_process<T, NB>(g, chunks, Lb, kb, R, first + C, nown - 1, C);
             __syncthreads();
@@ -803,6 +881,7 @@ static ClusterLuPlan cluster_lu_plan(const BandPlan& bp) {
     g.nblk = (int)((bp.n2 + NB - 1) / NB);
     g.nbw = (bp.p + NB - 1) / NB;
     g.prs = ((bp.p + 3) / 4) * 4;
+    { const char* se = getenv("CS_BAND_SPLIT"); g.split = se ? atoi(se) : 0; }
     if (bp.pw < g.nbw * NB || bp.p < 1) return pl;
     const int cands[3] = {4, 8, 2};
     for (int ci = 0; ci < 3; ++ci) {
@@ -848,8 +927,8 @@ static int band_factor_cluster(const BandPlan& bp, const ClusterLuPlan& pl, T* L
     if (pe && atoi(pe) > 0) CS_CUDA(cudaMalloc(&prof, (size_t)nsys * pl.C * 12 * sizeof(long long)));
     CS_CUDA(cudaLaunchKernelEx(&cfg, k_band_lu_cluster<T, NB>, LU, bp.band_elems(), pl.g, (T*)panels, prof));
     if (prof) {
-        // debugging aid: average cycles per block step and phase (0 panel load, 1 look-ahead update, 2 block inverse,
-        // 3 -, 4 L21 + publish, 5 owner's remaining update, 6 chunk store/load, 7 non-owner update, 8 barrier wait)
+        // debugging aid: average cycles per block step and phase (0 panel load, 1 pivot-block update, 3 Gauss-Jordan,
+        // 2 wait for the row update, 4 L21 + publish, 5 owner's remaining update, 6 chunk store/load, 7 non-owner update, 8 barrier wait)
         std::vector<long long> h((size_t)nsys * pl.C * 12);
         CS_CUDA(cudaStreamSynchronize(st));
         CS_CUDA(cudaMemcpy(h.data(), prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -857,7 +936,7 @@ static int band_factor_cluster(const BandPlan& bp, const ClusterLuPlan& pl, T* L
         double acc[12] = {0};
         for (size_t i = 0; i < h.size(); ++i) acc[i % 12] += (double)h[i];
         fprintf(stderr, "[cluster LU] C=%d sl=%d nblk=%d cycles/step (summed over the cluster's CTAs):", pl.C, pl.g.sl, pl.g.nblk);
-        for (int i = 0; i < 9; ++i) fprintf(stderr, " p%d=%.0f", i, acc[i] / nsys / pl.g.nblk);
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " p%d=%.0f", i, acc[i] / nsys / pl.g.nblk);
         fprintf(stderr, "\n");
     }
     return CS_OK;
@@ -981,7 +1060,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
 #pragma unroll
                 for (int i = 0; i < NB / HALVES; ++i) {
                     int c = HALVES * i + half;
-                    if (c < r16) yr += cur[r16 + c * ldd] * win[(t + c) & wm];
+                    if (c < r16) fmacc(yr, cur[r16 + c * ldd], win[(t + c) & wm]);
                 }
             }
             if (HALVES == 2) yr += shfl_xor_t<TV>(yr, 16);
@@ -994,7 +1073,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
 #pragma unroll
                 for (int i = 0; i < NB / TPR; ++i) {
                     int c = uq + TPR * i;
-                    if (c < nbe) acc += cur[(nbe + urow) + c * ldd] * yw[warp][c];
+                    if (c < nbe) fmacc(acc, cur[(nbe + urow) + c * ldd], yw[warp][c]);
                 }
             }
             if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
@@ -1043,7 +1122,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
 #pragma unroll
             for (int i = 0; i < NB / HALVES; ++i) {
                 int c = HALVES * i + half;
-                if ((diag_full || c >= r16) && c < nbe && r16 < nbe) xr += cur[(Ra + r16) + c * ldd] * win[(t + c) & wm];
+                if ((diag_full || c >= r16) && c < nbe && r16 < nbe) fmacc(xr, cur[(Ra + r16) + c * ldd], win[(t + c) & wm]);
             }
             if (HALVES == 2) xr += shfl_xor_t<TV>(xr, 16);
             if (lane < NB) yw[warp][lane] = xr;
@@ -1054,7 +1133,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
 #pragma unroll
                 for (int i = 0; i < NB / TPR; ++i) {
                     int c = uq + TPR * i;
-                    if (c < nbe) acc += cur[urow + c * ldd] * yw[warp][c];
+                    if (c < nbe) fmacc(acc, cur[urow + c * ldd], yw[warp][c]);
                 }
             }
             if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);

@@ -67,7 +67,35 @@ __host__ __device__ __forceinline__ cplx cinv(cplx a) {
     return mk(a.x * d, -a.y * d);
 }
 __host__ __device__ __forceinline__ cplx operator/(cplx a, cplx b) { return a * cinv(b); }
+// fused multiply-accumulate forms: 4 (complex) / 1 (real) DFMA instead of the mul + sub sequence
+// the operator forms compile to (6 FP64 instructions per complex term)
+__device__ __forceinline__ void fmacc(cplx& acc, cplx a, cplx b) {        // acc += a * b
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void fmsub(cplx& acc, cplx a, cplx b) {        // acc -= a * b
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void fmacc(double& acc, double a, double b) { acc = fma(a, b, acc); }
+__device__ __forceinline__ void fmsub(double& acc, double a, double b) { acc = fma(-a, b, acc); }
 __host__ __device__ __forceinline__ cplx conjc(cplx a) { return mk(a.x, -a.y); }
+
+// 1/d without the IEEE slow path: hardware seed (2^-23) + two Newton steps; d normal and nonzero
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ cplx fast_inv(cplx a) {
+    double d = fast_rcp(fma(a.x, a.x, a.y * a.y));
+    return mk(a.x * d, -a.y * d);
+}
+__device__ __forceinline__ double fast_inv(double a) { return fast_rcp(a); }
 
 // scalar traits so kernels can be written once for double and cplx
 template <typename T> struct Sc;

@@ -245,3 +245,39 @@ def test_apply_matches_oracle_at_size():
     ye = ope.apply(ctx.to_device(xe), shifts=s).cpu().numpy()
     assert rel(ye, P.C.T @ (P.MfRho @ (P.C @ xe)) + s * (P.MeMu @ xe)) < 1e-12
     ctx.close()
+
+
+@pytest.mark.parametrize("nx,nz", [(3, 9), (8, 40), (17, 21), (40, 33), (130, 24)])
+def test_band_factor_paths_agree(nx, nz, monkeypatch):
+    """The cluster-resident band factorisation (scalar fields) against the step-per-launch one and the
+    oracle, over the shapes that select its variants: cluster size 2 / 4 / 8, 1-3 chunk slots per CTA,
+    a short last block, real (DC) and complex (FDEM-h) scalars."""
+    import casingsimulations_b200 as cs
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, OracleFDEM, mesh_tensor, paint_casing_in_halfspace
+    hx = mesh_tensor([(0.01, min(nx, 4)), (0.01, nx - min(nx, 4), 1.3)]) if nx > 4 else np.ones(nx) * 0.02
+    hz = mesh_tensor([(0.5, nz // 3, -1.3), (0.5, nz - 2 * (nz // 3)), (0.5, nz // 3, 1.3)])
+    hy = np.r_[2 * np.pi]
+    z0 = -np.sum(hz) * 0.6
+    om = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    sig, mu = paint_casing_in_halfspace(om, **CASING)
+    q = rnd(om.nC, False, 3)
+    se = rnd(om.nF, False, 5)
+    Pd, Ph = OracleDC(om, sig), OracleFDEM(om, sig, mu, "h")
+    A, Ah, rhs = Pd.getA(), Ph.getA(10.0), Ph.getRHS(10.0, se)
+    out = {}
+    for path in ("cluster", "steps"):
+        monkeypatch.setenv("CS_BAND_LU", path)
+        ctx = cs._lib.Context(0)
+        ctx.set_mesh(hx, hy, hz, z0)
+        ctx.paint(paint_params(CASING))
+        phi = ctx.solve_dc(ctx.to_device(q[None, :])).cpu().numpy()[0]
+        assert ctx.info["relres"] <= 1e-10
+        h = ctx.solve_fdem("h", [10.0], ctx.to_device(se)).cpu().numpy()[0]
+        assert ctx.info["relres"] <= 1e-10
+        out[path] = (phi, h)
+        d = np.sqrt(np.abs(A.diagonal()))
+        assert np.linalg.norm((A @ phi - q) / d) <= 1e-9 * np.linalg.norm(q / d), (path, nx, nz)
+        dh = np.sqrt(np.abs(Ah.diagonal()))
+        assert np.linalg.norm((Ah @ h - rhs) / dh) <= 1e-9 * np.linalg.norm(rhs / dh), (path, nx, nz)
+    assert rel(out["cluster"][0], out["steps"][0]) < 1e-6
+    assert rel(out["cluster"][1], out["steps"][1]) < 1e-6
