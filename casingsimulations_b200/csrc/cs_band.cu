@@ -997,19 +997,101 @@ template <> __device__ __forceinline__ cplx shfl_xor_t<cplx>(cplx v, int m) {
     return mk(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
+// ---- producer warps + mbarrier (block columns of the factors -> shared memory ring) ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+// TMA staging by the producer warp: column c is copied by producer thread c (complex only: 16-byte
+// elements, so every column segment satisfies the alignment / size rules of cp.async.bulk).
+// Measured on C2 (16 copies of 2 KB per step): one warp, one copy per lane 14.6 ms per solve;
+// lane 0 of 2 or 4 warps 16.1 ms; one thread issuing all 16 copies 20.4 ms; cp.async by two
+// producer warps 25 ms; cp.async spread over all compute warps 17.8 ms.
+template <typename TL>
+__device__ __forceinline__ void tma_stage_cols(TL* dst, int ldd, const TL* A, int ld, long long row0, int nrows,
+                                               long long col0, int ncols, unsigned long long* bar, int tix, int nthr) {
+    const unsigned bytes = (unsigned)(nrows * sizeof(TL));
+    if (tix == 0) mbar_expect_tx(bar, bytes * ncols);
+    __syncwarp();
+    for (int c = tix; c < ncols; c += nthr) tma_bulk_g2s(dst + (size_t)c * ldd, A + row0 + (col0 + c) * (long long)ld, bytes, bar);
+}
+// the executing thread arrives on `bar` once all cp.async it has issued so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+}
+// a thread group (tix of nthr) stages ncols columns of nrows contiguous elements: dst[r + c*ldd] = A[(row0 + r) + (col0 + c)*ld]
+template <typename TL>
+__device__ __forceinline__ void stage_cols_group(TL* dst, int ldd, const TL* __restrict__ A, int ld, long long row0, int nrows,
+                                                 long long col0, int ncols, int tix, int nthr) {
+    for (int c = 0; c < ncols; ++c) {
+        const TL* src = A + row0 + (col0 + c) * (long long)ld;
+        TL* d = dst + (size_t)c * ldd;
+        for (int r = tix; r < nrows; r += nthr) cp_async_elem(d + r, src + r);
+    }
+}
+
+__device__ long long g_solve_prof[8];
+#define SV_TICK(i) do { if (prof_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == prof_on - 1) { long long t_ = clock64(); g_solve_prof[i] += t_ - tp; tp = t_; } } while (0)
 template <typename TL, typename TV, int TPR, int NB>
 __global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full) {
+                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0, int nprod, int prof_on) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // Staging of the factors.  When the launch has room, dedicated producer warps (threads prod0 ..
+    // prod0 + nprod - 1, no compute) issue the cp.async copies of stage s + nst - 1 while the other
+    // warps compute step s; each producer thread arrives on the stage's mbarrier when its copies have
+    // landed (cp.async.mbarrier.arrive) and the compute warps wait on that barrier.  With every
+    // thread issuing its share instead, the 64 LDGSTS warp instructions of a stage (8 LSU cycles
+    // each) sit right in front of the latency-critical shared-memory loads of the step.
+    // Complex systems stage with TMA bulk copies (one 2 KB column segment per producer lane, tracked by
+    // expect_tx / complete_tx); real systems (8-byte elements: segments are not 16-byte aligned) with cp.async.
+    constexpr bool USE_TMA = sizeof(TL) == 16;                // complex: TMA bulk copies, real: cp.async
+    const bool has_prod = prod0 > 0;
+    const bool is_prod = has_prod && (int)threadIdx.x >= prod0;
+    __shared__ unsigned long long full_bar[8];
+    unsigned phasebits = 0;
+    if (has_prod) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 8; ++i) mbar_init(&full_bar[i], USE_TMA ? 1u : (unsigned)nprod);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    long long tp = clock64();
     int v = blockIdx.y, m = blockIdx.x;
     int f = shift_of_vec ? shift_of_vec[v] : 0;
     const TL* A = LU + ((size_t)f * nmodes + m) * nel + pw;
     TV* b = xm + ((size_t)v * nmodes + m) * n2;
-    const int ldd = NB + p;                                   // rows per staged block column
+    // rows per staged block column, padded so that the TPR column groups of a quarter warp fall into
+    // distinct shared-memory banks (TPR = 4: ldd = 2 mod 8, TPR = 2: ldd = 4 mod 8)
+    int ldd = NB + p;
+    if (TPR == 4) while ((ldd & 7) != 2) ++ldd;
+    if (TPR == 2) while ((ldd & 7) != 4) ++ldd;
     const size_t ssz = (size_t)ldd * NB;                      // elements per stage
     TL* ring = reinterpret_cast<TL*>(smem_raw);               // [nst][NB][ldd]
-    TV* win = reinterpret_cast<TV*>(ring + (size_t)nst * ssz);   // circular window, wsz = power of two >= p + 5 NB
+    TV* win = reinterpret_cast<TV*>(ring + (size_t)nst * ssz);   // circular window, wsz = power of two >= p + 12 NB
     __shared__ TV yw[32][NB];                                 // per-warp copy of the block solution
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int HALVES = 32 / NB;                           // NB = 16: two lanes share a row (column parity)
@@ -1025,18 +1107,25 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             long long t2 = (long long)s * NB;
             int nbe2 = (int)min((long long)NB, n2 - t2);
             int R2 = (int)min((long long)p, n2 - (t2 + nbe2));
-            prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
+            if (has_prod) {
+                if (is_prod) {
+                    if (USE_TMA) tma_stage_cols<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2, &full_bar[s % nst], tid - prod0, nprod);
+                    else {
+                        stage_cols_group<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2, tid - prod0, nprod);
+                        cp_async_mbar_arrive(&full_bar[s % nst]);
+                    }
+                }
+            } else prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
+            // the NB right-hand-side rows that enter the window at step s (first touched at step s + 2)
+            // travel in the same cp.async group: no register-staged global load on the critical path
+            long long e = t2 + 3 * NB + p + tid;
+            if (tid < NB && e < n2) cp_async_elem(&win[e & wm], &b[e]);
         }
         __pipeline_commit();
     };
     for (int e = tid; e < 3 * NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
     for (int q = 0; q < nst - 1; ++q) fwd_prefetch(q);
     {
-        // entering rows are loaded one step before they are stored (the global-load latency
-        // would otherwise stall warp 0 in front of every barrier)
-        TV pend = zero;
-        long long pe = 3 * NB + p + tid;                      // row loaded into pend (threads < NB)
-        if (tid < NB && pe < n2) pend = b[pe];
         int slot = 0;
         const int ns = (int)nsteps;
         for (int s = 0; s < ns; ++s) {
@@ -1044,15 +1133,16 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             const int nbe = (int)min((long long)NB, n2 - t);
             const int R = (int)min((long long)p, n2 - (t + nbe));
             const TL* cur = ring + (size_t)slot * ssz;
+            if (has_prod && !is_prod) { mbar_wait(&full_bar[slot], (phasebits >> slot) & 1u); phasebits ^= 1u << slot; }
             slot = (slot + 1 == nst) ? 0 : slot + 1;
+            SV_TICK(2);
             __pipeline_wait_prior(nst - 2);                   // stage s has landed
+            SV_TICK(0);
             __syncthreads();                                  // ... and is visible; window of step s-1 complete
+            SV_TICK(1);
             fwd_prefetch(s + nst - 1);                        // refills the slot step s-1 just released
-            if (tid < NB) {
-                if (pe < n2) win[pe & wm] = pend;             // rows t + 3 NB + p .. (first touched at step s + 2)
-                pe += NB;
-                if (pe < n2) pend = b[pe];
-            }
+            SV_TICK(3);
+            if (is_prod) continue;
             // every warp computes y1 = inv(L11) b1 for itself: lane (r, half) sums the columns of its parity
             // (block LDU factors have a unit block diagonal in L: nothing to apply)
             TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
@@ -1091,7 +1181,17 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             long long t2 = tlast - (long long)s * NB;
             int nbe2 = (int)min((long long)NB, n2 - t2);
             int Ra2 = (int)min((long long)p, t2);
-            prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2);
+            if (has_prod) {
+                if (is_prod) {
+                    if (USE_TMA) tma_stage_cols<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2, &full_bar[s % nst], tid - prod0, nprod);
+                    else {
+                        stage_cols_group<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2, tid - prod0, nprod);
+                        cp_async_mbar_arrive(&full_bar[s % nst]);
+                    }
+                }
+            } else prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2);
+            long long e = n2 - (long long)(5 + s) * NB - p + tid;     // rows entering below the window at step s
+            if (tid < NB && e >= 0) cp_async_elem(&win[e & wm], &b[e]);
         }
         __pipeline_commit();
     };
@@ -1099,9 +1199,6 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     for (long long e = max(0LL, n2 - (4 * NB + p)) + tid; e < n2; e += blockDim.x) win[e & wm] = b[e];
     for (int q = 0; q < nst - 1; ++q) bwd_prefetch(q);
     {
-        TV pend = zero;
-        long long pe = n2 - (4 * NB + p) - NB + tid;          // next rows below the loaded window
-        if (tid < NB && pe >= 0) pend = b[pe];
         int slot = 0;
         const int ns = (int)nsteps;
         for (int s = 0; s < ns; ++s) {
@@ -1109,15 +1206,16 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             const int nbe = (int)min((long long)NB, n2 - t);
             const int Ra = (int)min((long long)p, t);
             const TL* cur = ring + (size_t)slot * ssz;        // rows [t - Ra, t + nbe), local row = row - (t - Ra)
+            if (has_prod && !is_prod) { mbar_wait(&full_bar[slot], (phasebits >> slot) & 1u); phasebits ^= 1u << slot; }
             slot = (slot + 1 == nst) ? 0 : slot + 1;
+            SV_TICK(6);
             __pipeline_wait_prior(nst - 2);
+            SV_TICK(4);
             __syncthreads();
+            SV_TICK(5);
             bwd_prefetch(s + nst - 1);
-            if (tid < NB) {
-                if (pe >= 0) win[pe & wm] = pend;
-                pe -= NB;
-                if (pe >= 0) pend = b[pe];
-            }
+            SV_TICK(7);
+            if (is_prod) continue;
             TV xr = zero;
 #pragma unroll
             for (int i = 0; i < NB / HALVES; ++i) {
@@ -1146,11 +1244,33 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
 
 template <typename T, int TPR, int NB>
 static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, int th, size_t sm, int wsz, int nst, cudaStream_t st) {
+    // two (or one) extra warps that only stage the factors, if the launch bounds leave room
+    int prod0 = 0, nprod = 0;
+    const int bound = TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640);
+    {
+        const char* e = getenv("CS_SOLVE_PROD");
+        int want = e ? atoi(e) * 32 : 32;
+        while (want > 0 && th + want > bound) want -= 32;
+        if (want > 0) { prod0 = th; nprod = want; }
+    }
+    th += nprod;
     static bool attr = false;                    // one flag per instantiation
     if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024)); attr = true; }
+    const char* pe = getenv("CS_BAND_PROF");
+    const int prof_on = (pe && atoi(pe) > 0) ? atoi(pe) : 0;      // 1 + index of the profiled thread
     dim3 g(bp.nmodes, nvec);
-    k_band_solve<T, T, TPR, NB><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full);
+    k_band_solve<T, T, TPR, NB><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, prod0, nprod, prof_on);
     CS_CUDA(cudaGetLastError());
+    if (prof_on) {
+        long long h[8];
+        CS_CUDA(cudaStreamSynchronize(st));
+        CS_CUDA(cudaMemcpyFromSymbol(h, g_solve_prof, sizeof(h)));
+        long long z[8] = {0};
+        CS_CUDA(cudaMemcpyToSymbol(g_solve_prof, z, sizeof(z)));
+        double ns = (double)((bp.n2 + NB - 1) / NB);
+        fprintf(stderr, "[band solve] th=%d nst=%d cycles/step fwd: cp-wait %.0f barrier %.0f prefetch %.0f compute %.0f | bwd: %.0f %.0f %.0f %.0f\n",
+                th, nst, h[0] / ns, h[1] / ns, h[3] / ns, h[2] / ns, h[4] / ns, h[5] / ns, h[7] / ns, h[6] / ns);
+    }
     return CS_OK;
 }
 
@@ -1161,9 +1281,13 @@ static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const 
     int th = ((tpr * rowsn + 31) / 32) * 32;
     if (th < 64) th = 64;
     CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel (p + NB <= 1024)");
+    // circular window: p + 4 NB live rows + the rows of up to 6 in-flight stages that land early
     int wsz = 64;
-    while (wsz < bp.p + 7 * NB) wsz <<= 1;
-    size_t stage_b = (size_t)rowsn * NB * sizeof(T);
+    while (wsz < bp.p + 12 * NB) wsz <<= 1;
+    int ldd = rowsn;                             // padded leading dimension of a stage (see k_band_solve)
+    if (tpr == 4) while ((ldd & 7) != 2) ++ldd;
+    if (tpr == 2) while ((ldd & 7) != 4) ++ldd;
+    size_t stage_b = (size_t)ldd * NB * sizeof(T);
     int nst = (int)((200 * 1024 - (size_t)wsz * sizeof(T)) / stage_b);   // ring depth: as deep as shared memory allows
     if (nst > 6) nst = 6;
     CS_CHECK(nst >= 2, "half bandwidth too large for the shared-memory staged solve");
