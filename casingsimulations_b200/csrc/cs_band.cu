@@ -1052,36 +1052,35 @@ __device__ __forceinline__ void stage_cols_group(TL* dst, int ldd, const TL* __r
     }
 }
 
-__device__ long long g_solve_prof[8];
-#define SV_TICK(i) do { if (prof_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == prof_on - 1) { long long t_ = clock64(); g_solve_prof[i] += t_ - tp; tp = t_; } } while (0)
-template <typename TL, typename TV, int TPR, int NB>
+__device__ __forceinline__ void bar_sync0() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// HP: a dedicated producer warp (threads prod0 .. prod0 + 31, no compute) stages the factors.
+//   It issues the copies of stage s + nst - 1 while the other warps compute step s and the compute
+//   warps wait on the stage's mbarrier.  Complex systems stage with TMA bulk copies (one 2 KB column
+//   segment per producer lane, expect_tx / complete_tx); real systems (8-byte elements: segments are
+//   not 16-byte aligned) with cp.async + cp.async.mbarrier.arrive.
+//   The producer runs its own loop; both sides meet at `bar.sync 0` once per block step.
+// !HP: every thread issues its share of the stage with cp.async (commit / wait groups): the 64 LDGSTS
+//   warp instructions of a stage (8 LSU cycles each) then sit right in front of the latency-critical
+//   shared-memory loads of the step.
+template <typename TL, typename TV, int TPR, int NB, bool HP>
 __global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0, int nprod, int prof_on) {
+                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // Staging of the factors.  When the launch has room, dedicated producer warps (threads prod0 ..
-    // prod0 + nprod - 1, no compute) issue the cp.async copies of stage s + nst - 1 while the other
-    // warps compute step s; each producer thread arrives on the stage's mbarrier when its copies have
-    // landed (cp.async.mbarrier.arrive) and the compute warps wait on that barrier.  With every
-    // thread issuing its share instead, the 64 LDGSTS warp instructions of a stage (8 LSU cycles
-    // each) sit right in front of the latency-critical shared-memory loads of the step.
-    // Complex systems stage with TMA bulk copies (one 2 KB column segment per producer lane, tracked by
-    // expect_tx / complete_tx); real systems (8-byte elements: segments are not 16-byte aligned) with cp.async.
     constexpr bool USE_TMA = sizeof(TL) == 16;                // complex: TMA bulk copies, real: cp.async
-    const bool has_prod = prod0 > 0;
-    const bool is_prod = has_prod && (int)threadIdx.x >= prod0;
     __shared__ unsigned long long full_bar[8];
-    unsigned phasebits = 0;
-    if (has_prod) {
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < 8; ++i) mbar_init(&full_bar[i], USE_TMA ? 1u : (unsigned)nprod);
+    __shared__ TV yw[32][NB];                                 // per-warp copy of the block solution
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (HP) {
+        if (tid == 0) {
+            for (int i = 0; i < 8; ++i) mbar_init(&full_bar[i], USE_TMA ? 1u : 32u);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncthreads();
+        bar_sync0();
     }
-    long long tp = clock64();
-    int v = blockIdx.y, m = blockIdx.x;
-    int f = shift_of_vec ? shift_of_vec[v] : 0;
+    const int v = blockIdx.y, m = blockIdx.x;
+    const int f = shift_of_vec ? shift_of_vec[v] : 0;
     const TL* A = LU + ((size_t)f * nmodes + m) * nel + pw;
     TV* b = xm + ((size_t)v * nmodes + m) * n2;
     // rows per staged block column, padded so that the TPR column groups of a quarter warp fall into
@@ -1092,57 +1091,81 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     const size_t ssz = (size_t)ldd * NB;                      // elements per stage
     TL* ring = reinterpret_cast<TL*>(smem_raw);               // [nst][NB][ldd]
     TV* win = reinterpret_cast<TV*>(ring + (size_t)nst * ssz);   // circular window, wsz = power of two >= p + 12 NB
-    __shared__ TV yw[32][NB];                                 // per-warp copy of the block solution
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = wsz - 1;
+    const int ns = (int)((n2 + NB - 1) / NB);
+    const long long tlast = (long long)(ns - 1) * NB;
+
+    // stage of forward step s: rows [t, t + nbe + R) of columns [t, t + nbe);  backward: rows [t - Ra, t + nbe)
+    auto stage_geom = [&](bool fwd, int s, long long& row0, int& nrows, long long& col0, int& ncols) {
+        long long t2 = fwd ? (long long)s * NB : tlast - (long long)s * NB;
+        int nbe2 = (int)min((long long)NB, n2 - t2);
+        col0 = t2; ncols = nbe2;
+        if (fwd) { row0 = t2; nrows = nbe2 + (int)min((long long)p, n2 - (t2 + nbe2)); }
+        else { int Ra2 = (int)min((long long)p, t2); row0 = t2 - Ra2; nrows = Ra2 + nbe2; }
+    };
+
+    if (HP && tid >= prod0) {
+        // ------------------------------ producer warp ------------------------------
+        auto issue = [&](bool fwd, int s) {
+            if (s >= ns) return;
+            long long row0, col0; int nrows, ncols;
+            stage_geom(fwd, s, row0, nrows, col0, ncols);
+            TL* dst = ring + (size_t)(s % nst) * ssz;
+            if (USE_TMA) tma_stage_cols<TL>(dst, ldd, A, ld, row0, nrows, col0, ncols, &full_bar[s % nst], lane, 32);
+            else {
+                stage_cols_group<TL>(dst, ldd, A, ld, row0, nrows, col0, ncols, lane, 32);
+                cp_async_mbar_arrive(&full_bar[s % nst]);
+            }
+        };
+        for (int q = 0; q < nst - 1; ++q) issue(true, q);
+        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(true, s + nst - 1); }
+        bar_sync0();                                          // forward done: every ring slot is free again
+        for (int q = 0; q < nst - 1; ++q) issue(false, q);
+        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(false, s + nst - 1); }
+        return;
+    }
+
+    // ------------------------------ compute warps ------------------------------
     constexpr int HALVES = 32 / NB;                           // NB = 16: two lanes share a row (column parity)
     const int r16 = lane % NB, half = lane / NB;              // block mat-vec: lane <-> (row, column parity)
     const int urow = tid / TPR, uq = tid % TPR;               // window update: thread <-> (row, column group)
-    const int wm = wsz - 1;
-    const long long nsteps = (n2 + NB - 1) / NB;
     const TV zero = Sc<TV>::zero();
-
-    // ================= forward: L y = b (unit lower; diagonal blocks hold inv(L11)) =================
-    auto fwd_prefetch = [&](int s) {
-        if (s < nsteps) {
-            long long t2 = (long long)s * NB;
-            int nbe2 = (int)min((long long)NB, n2 - t2);
-            int R2 = (int)min((long long)p, n2 - (t2 + nbe2));
-            if (has_prod) {
-                if (is_prod) {
-                    if (USE_TMA) tma_stage_cols<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2, &full_bar[s % nst], tid - prod0, nprod);
-                    else {
-                        stage_cols_group<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2, tid - prod0, nprod);
-                        cp_async_mbar_arrive(&full_bar[s % nst]);
-                    }
-                }
-            } else prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2, nbe2 + R2, t2, nbe2);
-            // the NB right-hand-side rows that enter the window at step s (first touched at step s + 2)
-            // travel in the same cp.async group: no register-staged global load on the critical path
-            long long e = t2 + 3 * NB + p + tid;
-            if (tid < NB && e < n2) cp_async_elem(&win[e & wm], &b[e]);
+    unsigned phasebits = 0;
+    // the NB right-hand-side rows that enter the window at step s (first touched at step s + 2) are
+    // fetched with cp.async by warp 0, nst - 1 steps ahead: no register-staged global load on the critical path
+    auto rows_prefetch = [&](bool fwd, int s) {
+        if (s < ns && tid < NB) {
+            long long e = fwd ? (long long)s * NB + 3 * NB + p + tid : n2 - (long long)(5 + s) * NB - p + tid;
+            if (e >= 0 && e < n2) cp_async_elem(&win[e & wm], &b[e]);
         }
-        __pipeline_commit();
     };
-    for (int e = tid; e < 3 * NB + p && e < n2; e += blockDim.x) win[e & wm] = b[e];
-    for (int q = 0; q < nst - 1; ++q) fwd_prefetch(q);
+    auto prefetch = [&](bool fwd, int s) {
+        if (!HP && s < ns) {
+            long long row0, col0; int nrows, ncols;
+            stage_geom(fwd, s, row0, nrows, col0, ncols);
+            prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, row0, nrows, col0, ncols);
+        }
+        if (!HP || warp == 0) { rows_prefetch(fwd, s); __pipeline_commit(); }
+    };
+    auto stage_wait = [&](int slot) {
+        if (HP) { mbar_wait(&full_bar[slot], (phasebits >> slot) & 1u); phasebits ^= 1u << slot; }
+        if (!HP || warp == 0) __pipeline_wait_prior(nst - 2);
+    };
+
+    // ================= forward: L y = b (unit lower; diagonal blocks hold inv(L11), or nothing to apply) ==========
+    for (int e = tid; e < 3 * NB + p && e < n2; e += (HP ? prod0 : blockDim.x)) win[e & wm] = b[e];
+    for (int q = 0; q < nst - 1; ++q) prefetch(true, q);
     {
         int slot = 0;
-        const int ns = (int)nsteps;
         for (int s = 0; s < ns; ++s) {
             const long long t = (long long)s * NB;
             const int nbe = (int)min((long long)NB, n2 - t);
             const int R = (int)min((long long)p, n2 - (t + nbe));
             const TL* cur = ring + (size_t)slot * ssz;
-            if (has_prod && !is_prod) { mbar_wait(&full_bar[slot], (phasebits >> slot) & 1u); phasebits ^= 1u << slot; }
+            stage_wait(slot);                                 // stage s has landed
             slot = (slot + 1 == nst) ? 0 : slot + 1;
-            SV_TICK(2);
-            __pipeline_wait_prior(nst - 2);                   // stage s has landed
-            SV_TICK(0);
-            __syncthreads();                                  // ... and is visible; window of step s-1 complete
-            SV_TICK(1);
-            fwd_prefetch(s + nst - 1);                        // refills the slot step s-1 just released
-            SV_TICK(3);
-            if (is_prod) continue;
+            bar_sync0();                                      // ... and is visible; window of step s-1 complete
+            prefetch(true, s + nst - 1);                      // refills the slot step s-1 just released
             // every warp computes y1 = inv(L11) b1 for itself: lane (r, half) sums the columns of its parity
             // (block LDU factors have a unit block diagonal in L: nothing to apply)
             TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
@@ -1172,50 +1195,23 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
         }
     }
     __pipeline_wait_prior(0);
-    __syncthreads();
+    bar_sync0();
 
-    // ================= backward: U x = y (diagonal blocks hold inv(U11)) =================
-    const long long tlast = (nsteps - 1) * NB;
-    auto bwd_prefetch = [&](int s) {
-        if (s < nsteps) {
-            long long t2 = tlast - (long long)s * NB;
-            int nbe2 = (int)min((long long)NB, n2 - t2);
-            int Ra2 = (int)min((long long)p, t2);
-            if (has_prod) {
-                if (is_prod) {
-                    if (USE_TMA) tma_stage_cols<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2, &full_bar[s % nst], tid - prod0, nprod);
-                    else {
-                        stage_cols_group<TL>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2, tid - prod0, nprod);
-                        cp_async_mbar_arrive(&full_bar[s % nst]);
-                    }
-                }
-            } else prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, t2 - Ra2, Ra2 + nbe2, t2, nbe2);
-            long long e = n2 - (long long)(5 + s) * NB - p + tid;     // rows entering below the window at step s
-            if (tid < NB && e >= 0) cp_async_elem(&win[e & wm], &b[e]);
-        }
-        __pipeline_commit();
-    };
-    // window now slides downwards; (re)load the last p + 3 NB rows of y
-    for (long long e = max(0LL, n2 - (4 * NB + p)) + tid; e < n2; e += blockDim.x) win[e & wm] = b[e];
-    for (int q = 0; q < nst - 1; ++q) bwd_prefetch(q);
+    // ================= backward: U x = y (diagonal blocks hold inv(U11), or the full pivot-block inverse) =========
+    // window now slides downwards; (re)load the last p + 4 NB rows of y
+    for (long long e = max(0LL, n2 - (4 * NB + p)) + tid; e < n2; e += (HP ? prod0 : blockDim.x)) win[e & wm] = b[e];
+    for (int q = 0; q < nst - 1; ++q) prefetch(false, q);
     {
         int slot = 0;
-        const int ns = (int)nsteps;
         for (int s = 0; s < ns; ++s) {
             const long long t = tlast - (long long)s * NB;
             const int nbe = (int)min((long long)NB, n2 - t);
             const int Ra = (int)min((long long)p, t);
             const TL* cur = ring + (size_t)slot * ssz;        // rows [t - Ra, t + nbe), local row = row - (t - Ra)
-            if (has_prod && !is_prod) { mbar_wait(&full_bar[slot], (phasebits >> slot) & 1u); phasebits ^= 1u << slot; }
+            stage_wait(slot);
             slot = (slot + 1 == nst) ? 0 : slot + 1;
-            SV_TICK(6);
-            __pipeline_wait_prior(nst - 2);
-            SV_TICK(4);
-            __syncthreads();
-            SV_TICK(5);
-            bwd_prefetch(s + nst - 1);
-            SV_TICK(7);
-            if (is_prod) continue;
+            bar_sync0();
+            prefetch(false, s + nst - 1);
             TV xr = zero;
 #pragma unroll
             for (int i = 0; i < NB / HALVES; ++i) {
@@ -1244,33 +1240,20 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
 
 template <typename T, int TPR, int NB>
 static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, int th, size_t sm, int wsz, int nst, cudaStream_t st) {
-    // two (or one) extra warps that only stage the factors, if the launch bounds leave room
-    int prod0 = 0, nprod = 0;
+    // one extra warp that only stages the factors, if the launch bounds leave room (CS_SOLVE_PROD=0: never)
     const int bound = TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640);
-    {
-        const char* e = getenv("CS_SOLVE_PROD");
-        int want = e ? atoi(e) * 32 : 32;
-        while (want > 0 && th + want > bound) want -= 32;
-        if (want > 0) { prod0 = th; nprod = want; }
-    }
-    th += nprod;
+    const char* e = getenv("CS_SOLVE_PROD");
+    const bool hp = (th + 32 <= bound) && !(e && atoi(e) == 0);
     static bool attr = false;                    // one flag per instantiation
-    if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024)); attr = true; }
-    const char* pe = getenv("CS_BAND_PROF");
-    const int prof_on = (pe && atoi(pe) > 0) ? atoi(pe) : 0;      // 1 + index of the profiled thread
-    dim3 g(bp.nmodes, nvec);
-    k_band_solve<T, T, TPR, NB><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, prod0, nprod, prof_on);
-    CS_CUDA(cudaGetLastError());
-    if (prof_on) {
-        long long h[8];
-        CS_CUDA(cudaStreamSynchronize(st));
-        CS_CUDA(cudaMemcpyFromSymbol(h, g_solve_prof, sizeof(h)));
-        long long z[8] = {0};
-        CS_CUDA(cudaMemcpyToSymbol(g_solve_prof, z, sizeof(z)));
-        double ns = (double)((bp.n2 + NB - 1) / NB);
-        fprintf(stderr, "[band solve] th=%d nst=%d cycles/step fwd: cp-wait %.0f barrier %.0f prefetch %.0f compute %.0f | bwd: %.0f %.0f %.0f %.0f\n",
-                th, nst, h[0] / ns, h[1] / ns, h[3] / ns, h[2] / ns, h[4] / ns, h[5] / ns, h[7] / ns, h[6] / ns);
+    if (!attr) {
+        CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+        CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+        attr = true;
     }
+    dim3 g(bp.nmodes, nvec);
+    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, th);
+    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, 0);
+    CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
 
