@@ -697,7 +697,10 @@ __device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunks, T* 
         // in-place Gauss-Jordan, thread (r, cq) holds row r, columns 4 cq .. 4 cq + 3.  Pivot k:
         //   a_kc <- a_kc / p;  a_rc -= (a_rk / p) a_kc;  a_rk <- -a_rk / p;  a_kk <- 1 / p
         // (a 2 x 2 block-pivot variant was tried: 8 instead of 16 dependent steps, but each step
-        //  is so much longer for a lone warp that the sweep only went from 7.7k to 6.9k cycles.)
+        //  is so much longer for a lone warp that the sweep only went from 7.7k to 6.9k cycles.
+        //  Also tried: L21 = A21 inv(D) by replaying the sweep's column operations on the A21 rows in
+        //  warps 2..7 while the sweep runs -- the sweep slowed to 8.7k cycles and the replay still
+        //  finished 4.1k cycles after it: the shadow of the sweep is too short for tile update + L21.)
         const int r = tid % NB, cq = tid / NB;
         T a[4];
 #pragma unroll
@@ -1260,7 +1263,8 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
 template <typename T, int NB>
 static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, cudaStream_t st) {
     int rowsn = bp.p + NB;
-    int tpr = (4 * rowsn <= 640) ? 4 : (2 * rowsn <= 768 ? 2 : 1);
+    int tpr = (4 * rowsn <= 640) ? 4 : (2 * rowsn <= 768 ? 2 : 1);   // C2: 4 -> 11.2 ms, 2 -> 11.4 ms, 1 -> 13.8 ms per solve
+    { const char* e = getenv("CS_SOLVE_TPR"); if (e && (atoi(e) == 1 || atoi(e) == 2) && atoi(e) * rowsn <= 768) tpr = atoi(e); }
     int th = ((tpr * rowsn + 31) / 32) * 32;
     if (th < 64) th = 64;
     CS_CHECK(th <= 1024, "half bandwidth too large for the solve kernel (p + NB <= 1024)");
