@@ -5,6 +5,7 @@
 #include <complex>
 #include <map>
 #include <vector>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -12,7 +13,7 @@
 namespace cs {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide (all contexts)
 }  // namespace cs
 
 using namespace cs;

@@ -17,6 +17,9 @@
 #include "cs_internal.h"
 #include <cuda_pipeline.h>
 #include <vector>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -32,6 +35,28 @@ template <> __device__ __forceinline__ cplx shfl_t<cplx>(cplx v, int src) {
 template <typename T> __device__ __forceinline__ T shfl_row(T v, int src) { return shfl_t<T>(v, src); }
 
 static const int TPB = 128;
+
+// Host-side state shared by all contexts (graph cache, capture streams, scratch buffers) is guarded
+// by one mutex; the small device scratch buffers are per (purpose, device, stream), so independent
+// contexts (one stream each) never share one.
+static std::mutex g_band_mu;
+static int band_scratch(int which, cudaStream_t st, size_t need, bool zero_new, void** out) {
+    struct Buf { void* p = nullptr; size_t bytes = 0; };
+    static std::map<std::tuple<int, int, cudaStream_t>, Buf> bufs;
+    int dev = 0;
+    CS_CUDA(cudaGetDevice(&dev));
+    Buf& b = bufs[std::make_tuple(which, dev, st)];
+    if (need > b.bytes) {
+        if (b.p) cudaFree(b.p);                  // (synchronises with everything still using it)
+        b.p = nullptr; b.bytes = 0;
+        if (need < (4u << 20)) need = 4u << 20;
+        CS_CUDA(cudaMalloc(&b.p, need));
+        if (zero_new) CS_CUDA(cudaMemset(b.p, 0, need));
+        b.bytes = need;
+    }
+    *out = b.p;
+    return CS_OK;
+}
 #define TWO_PI 6.28318530717958647692
 
 // ------------------------------------------------------------------ DFT -----
@@ -468,15 +493,9 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
 template <typename T, int NB>
 static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_CHECK(bp.nb == NB, "band plan block size must equal the instantiated NB");
-    static void* scratch = nullptr;
-    static size_t scratch_bytes = 0;
-    size_t need = (size_t)nsys * NB * NB * sizeof(T);
-    if (need > scratch_bytes) {
-        if (scratch) cudaFree(scratch);
-        if (need < (1u << 20)) need = 1u << 20;
-        CS_CUDA(cudaMalloc(&scratch, need));
-        scratch_bytes = need;
-    }
+    std::lock_guard<std::mutex> lock(g_band_mu);
+    void* scratch = nullptr;
+    CS_TRY(band_scratch(0, st, (size_t)nsys * NB * NB * sizeof(T), false, &scratch));
     FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB};
     for (auto& g : g_graphs)
         if (g.key == key) {
@@ -905,16 +924,9 @@ static ClusterLuPlan cluster_lu_plan(const BandPlan& bp) {
 
 template <typename T, int NB>
 static int band_factor_cluster(const BandPlan& bp, const ClusterLuPlan& pl, T* LU, int nsys, cudaStream_t st) {
-    static void* panels = nullptr;
-    static size_t panel_bytes = 0;
-    size_t need = (size_t)nsys * 2 * pl.g.prs * NB * sizeof(T);
-    if (need > panel_bytes) {
-        if (panels) cudaFree(panels);
-        if (need < (4u << 20)) need = 4u << 20;
-        CS_CUDA(cudaMalloc(&panels, need));
-        CS_CUDA(cudaMemset(panels, 0, need));
-        panel_bytes = need;
-    }
+    std::lock_guard<std::mutex> lock(g_band_mu);
+    void* panels = nullptr;
+    CS_TRY(band_scratch(1, st, (size_t)nsys * 2 * pl.g.prs * NB * sizeof(T), true, &panels));
     CS_CUDA(cudaFuncSetAttribute(k_band_lu_cluster<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nsys * pl.C));
@@ -1247,12 +1259,8 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
     const int bound = TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640);
     const char* e = getenv("CS_SOLVE_PROD");
     const bool hp = (th + 32 <= bound) && !(e && atoi(e) == 0);
-    static bool attr = false;                    // one flag per instantiation
-    if (!attr) {
-        CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
-        CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
-        attr = true;
-    }
+    if (hp) CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    else CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     dim3 g(bp.nmodes, nvec);
     if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, th);
     else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, 0);

@@ -367,3 +367,48 @@ def test_against_committed_golden_vectors(nth):
     F = ctx.tdem_run("j", np.r_[np.ones(3) * 1e-5, np.ones(3) * 1e-4], se).cpu().numpy().T
     assert rel(F, g[tag + "tdem_j"]) < 1e-6
     ctx.close()
+
+
+def test_two_contexts_on_two_host_threads():
+    """include/casing_b200.h: 'a cs_ctx is not thread safe, independent contexts are'.  Two host threads, each with
+    its own context (own stream), run the DC + FDEM-h solves of different meshes at the same time; every result
+    must equal the one obtained alone."""
+    import threading
+    from casingsimulations_b200 import _lib
+    from conftest import CASING, paint_params
+    from oracle.cyl_oracle import mesh_tensor
+
+    def problem(nx, nz):
+        hx = mesh_tensor([(0.01, 4), (0.01, nx - 4, 1.3)])
+        hz = mesh_tensor([(0.5, nz // 3, -1.3), (0.5, nz - 2 * (nz // 3)), (0.5, nz // 3, 1.3)])
+        return hx, np.r_[2 * np.pi], hz, -np.sum(hz) * 0.6
+
+    def run(args, out, key, reps):
+        hx, hy, hz, z0 = args
+        ctx = _lib.Context(0)
+        ctx.set_mesh(hx, hy, hz, z0)
+        ctx.paint(paint_params(CASING))
+        rng = np.random.default_rng(7)
+        q = rng.standard_normal(ctx.nC)
+        se = rng.standard_normal(ctx.nF)
+        res = None
+        for _ in range(reps):
+            phi = ctx.solve_dc(ctx.to_device(q[None, :])).cpu().numpy()[0]
+            h = ctx.solve_fdem("h", [3.0, 30.0], ctx.to_device(se)).cpu().numpy()
+            res = (phi, h)
+        out[key] = res
+        ctx.close()
+
+    probs = {"a": problem(40, 60), "b": problem(24, 90)}
+    alone, both = {}, {}
+    for k, a in probs.items():
+        run(a, alone, k, 1)
+    ths = [threading.Thread(target=run, args=(a, both, k, 4)) for k, a in probs.items()]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for k in probs:
+        assert k in both, "worker thread failed"
+        for x, y in zip(alone[k], both[k]):
+            assert rel(x, y) < 1e-9
