@@ -481,8 +481,7 @@ extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int c
     CS_CUDA(cudaMemcpyAsync(c->scal.p, shifts_h, 2 * nshift * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CS_TRY(op->wts.ensure((size_t)nshift * op->n * sizeof(double)));
     CS_TRY(band_diag_weights(bp, (const double*)c->scal.p, nshift, op->n, (double*)op->wts.p, c->st));
-    CS_TRY(band_form_shifted(bp, (const double*)c->scal.p, nshift, op->LU.p, lc, c->st));
-    CS_TRY(band_factor(bp, op->LU.p, lc, nshift * bp.nmodes, c->st));
+    CS_TRY(band_form_and_factor(bp, (const double*)c->scal.p, nshift, op->LU.p, lc, c->st));
     g_launches += band_factor_launches(bp, lc);
     CS_CUDA(cudaEventRecord(c->ev1, c->st));
     CS_CUDA(cudaStreamSynchronize(c->st));

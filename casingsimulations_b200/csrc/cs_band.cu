@@ -800,12 +800,70 @@ __device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunks, T* 
     CL_TICK(4);
 }
 
-template <typename T, int NB>
-__device__ __forceinline__ void cl_load_chunk(const ClusterLuGeom& g, T* chunk, const T* __restrict__ AB, int jb) {
+// where block columns come from: the already formed A(s) in the LU buffer (K == nullptr), or -- fused
+// assembly -- the shift-independent band K[m] plus s_f * diag(mdiag) on the fly (k_form_shifted's rule),
+// which saves writing and re-reading the nshift * nmodes shifted copies (10 GB each way for C2)
+struct ClusterLuSource {
+    const void* K; const double* s_d; const long long* map3d; const int* jstr; const double* mdiag; int nmodes;
+};
+template <typename T, typename TB, int NB>
+__device__ __forceinline__ void cl_load_chunk(const ClusterLuGeom& g, T* chunk, const T* __restrict__ AB,
+                                              const ClusterLuSource& src, int sys, int jb) {
     if (jb >= g.nblk) return;
     int ncols = (int)min((long long)NB, g.n2 - (long long)jb * NB);
-    const T* src = AB + (size_t)jb * NB * g.ldab;
-    for (int e = threadIdx.x; e < ncols * g.ldab; e += CL_THREADS) cp_async_elem(chunk + e, src + e);
+    if (!src.K) {
+        const T* a = AB + (size_t)jb * NB * g.ldab;
+        for (int e = threadIdx.x; e < ncols * g.ldab; e += CL_THREADS) cp_async_elem(chunk + e, a + e);
+        return;
+    }
+    const int m = sys % src.nmodes, f = sys / src.nmodes;
+    const TB* kb = reinterpret_cast<const TB*>(src.K) + (size_t)m * g.n2 * g.ldab + (size_t)jb * NB * g.ldab;
+    const T sv = Sc<T>::from(src.s_d[2 * f], src.s_d[2 * f + 1]);
+    // all NB loads of a thread (one band offset d, every column) are issued before the first use
+    for (int d = threadIdx.x; d < g.ldab; d += CL_THREADS) {
+        TB kv[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (c < ncols) kv[c] = kb[(size_t)c * g.ldab + d];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            if (c < ncols) {
+                T v = Sc<T>::from(Sc<TB>::re(kv[c]), Sc<TB>::im(kv[c]));
+                if (d == g.pw) {
+                    long long q = (long long)jb * NB + c;
+                    bool dummy = (src.map3d[q] < 0) || (src.jstr[q] == 0 && m > 0);
+                    v = dummy ? Sc<T>::one() : v + sv * Sc<T>::from(src.mdiag[q], 0.0);
+                }
+                chunk[(size_t)c * g.ldab + d] = v;
+            }
+        }
+    }
+}
+// fused source, asynchronous: the raw K chunk travels with cp.async into `stg` (into the chunk itself when
+// K already has the factor's scalar type); cl_finish_chunk converts it and adds the shift once it has landed
+template <typename T, typename TB, int NB>
+__device__ __forceinline__ void cl_load_chunk_async(const ClusterLuGeom& g, T* chunk, TB* stg, const ClusterLuSource& src, int sys, int jb) {
+    int ncols = (int)min((long long)NB, g.n2 - (long long)jb * NB);
+    const int m = sys % src.nmodes;
+    const TB* kb = reinterpret_cast<const TB*>(src.K) + (size_t)m * g.n2 * g.ldab + (size_t)jb * NB * g.ldab;
+    TB* dst = (sizeof(TB) == sizeof(T)) ? reinterpret_cast<TB*>(chunk) : stg;
+    for (int e = threadIdx.x; e < ncols * g.ldab; e += CL_THREADS) cp_async_elem(dst + e, kb + e);
+}
+template <typename T, typename TB, int NB>
+__device__ __forceinline__ void cl_finish_chunk(const ClusterLuGeom& g, T* chunk, const TB* stg, const ClusterLuSource& src, int sys, int jb) {
+    int ncols = (int)min((long long)NB, g.n2 - (long long)jb * NB);
+    const int m = sys % src.nmodes, f = sys / src.nmodes;
+    const T sv = Sc<T>::from(src.s_d[2 * f], src.s_d[2 * f + 1]);
+    if (sizeof(TB) != sizeof(T)) {
+        for (int e = threadIdx.x; e < ncols * g.ldab; e += CL_THREADS) chunk[e] = Sc<T>::from(Sc<TB>::re(stg[e]), Sc<TB>::im(stg[e]));
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < ncols) {
+        const int c = threadIdx.x;
+        long long q = (long long)jb * NB + c;
+        bool dummy = (src.map3d[q] < 0) || (src.jstr[q] == 0 && m > 0);
+        T* dg = chunk + (size_t)c * g.ldab + g.pw;
+        *dg = dummy ? Sc<T>::one() : *dg + sv * Sc<T>::from(src.mdiag[q], 0.0);
+    }
 }
 template <typename T, int NB>
 __device__ __forceinline__ void cl_store_chunk(const ClusterLuGeom& g, const T* chunk, T* __restrict__ AB, int jb) {
@@ -815,9 +873,9 @@ __device__ __forceinline__ void cl_store_chunk(const ClusterLuGeom& g, const T* 
 }
 
 // grid = C * nsys CTAs in clusters of C; panels: per system 2 slots of prs * NB elements
-template <typename T, int NB>
+template <typename T, typename TB, int NB>
 __global__ void __launch_bounds__(CL_THREADS, 1)
-k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict__ panels, long long* prof) {
+k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict__ panels, ClusterLuSource src, long long* prof) {
     __shared__ long long prof_s[12];
     __shared__ long long tprev_s;
     long long* tprev = &tprev_s;
@@ -832,18 +890,22 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
     T (*Di)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(Lb + (size_t)g.prs * NB);
     T (*rowb)[NB] = reinterpret_cast<T (*)[NB]>(Di + NB);
     T (*colb)[NB] = rowb + 2;
+    TB* stg = reinterpret_cast<TB*>(colb + 2);               // raw K chunk in flight (fused source with TB != T only)
+    int pend_jb = -1;                                        // block column whose fused load still needs cl_finish_chunk
+    T* pend_chunk = nullptr;
     T* P = panels + (size_t)sys * 2 * g.prs * NB;
     const int psz16 = (int)((size_t)g.prs * NB * sizeof(T) / 16);
 
     // prologue: the first window
-    for (int jb = rank; jb < g.sl * C && jb < g.nblk; jb += C) cl_load_chunk<T, NB>(g, chunks + (size_t)((jb / C) % g.sl) * CH, AB, jb);
+    for (int jb = rank; jb < g.sl * C && jb < g.nblk; jb += C) cl_load_chunk<T, TB, NB>(g, chunks + (size_t)((jb / C) % g.sl) * CH, AB, src, sys, jb);
     cp_async_wait_all();
     __syncthreads();
     if (rank == 0) {
         cl_factor<T, NB>(g, chunks, chunks, Lb, false, P, Di, rowb, colb, 0, C, g.split, nullptr, prof_s, tprev);
         cl_store_chunk<T, NB>(g, chunks, AB, 0);
         __syncthreads();
-        cl_load_chunk<T, NB>(g, chunks, AB, g.sl * C);
+        if (src.K) { if (g.sl * C < g.nblk) { cl_load_chunk_async<T, TB, NB>(g, chunks, stg, src, sys, g.sl * C); pend_jb = g.sl * C; pend_chunk = chunks; } }
+        else cl_load_chunk<T, TB, NB>(g, chunks, AB, src, sys, g.sl * C);
     }
     cluster_arrive();
     cluster_wait();
@@ -858,6 +920,11 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
         }
         cp_async_wait_all();                                 // also the chunk that entered during the previous step
         __syncthreads();
+        if (pend_jb >= 0) {                                  // (uniform per CTA)
+            cl_finish_chunk<T, TB, NB>(g, pend_chunk, stg, src, sys, pend_jb);
+            pend_jb = -1;
+            __syncthreads();
+        }
         CL_TICK(0);
         const int R = (int)min((long long)g.p, g.n2 - (long long)(kb + 1) * NB);
         const int last = min(kb + g.nbw, g.nblk - 1);        // right-most block panel kb reaches
@@ -873,7 +940,8 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
             CL_TICK(5);
             cl_store_chunk<T, NB>(g, chunk, AB, kb + 1);
             __syncthreads();
-            cl_load_chunk<T, NB>(g, chunk, AB, kb + 1 + g.sl * C);
+            if (src.K) { if (kb + 1 + g.sl * C < g.nblk) { cl_load_chunk_async<T, TB, NB>(g, chunk, stg, src, sys, kb + 1 + g.sl * C); pend_jb = kb + 1 + g.sl * C; pend_chunk = chunk; } }
+            else cl_load_chunk<T, TB, NB>(g, chunk, AB, src, sys, kb + 1 + g.sl * C);
             CL_TICK(6);
         } else {
             cluster_arrive();
@@ -889,8 +957,9 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
 }
 
 struct ClusterLuPlan { bool ok; int C; ClusterLuGeom g; size_t smem; };
+// stage_bytes: size of one element of the raw K band if the fused source needs a conversion buffer, else 0
 template <typename T, int NB>
-static ClusterLuPlan cluster_lu_plan(const BandPlan& bp) {
+static ClusterLuPlan cluster_lu_plan(const BandPlan& bp, size_t stage_bytes = 0) {
     ClusterLuPlan pl{};
     pl.ok = false;
     const char* e = getenv("CS_BAND_LU");
@@ -914,20 +983,20 @@ static ClusterLuPlan cluster_lu_plan(const BandPlan& bp) {
         if (sl > 4) continue;
         size_t CH = (size_t)NB * bp.ldab;
         size_t el = (size_t)sl * CH + (size_t)g.prs * NB + (size_t)NB * (NB + 1) + 4 * (size_t)NB;
-        size_t bytes = el * sizeof(T);
-        if (bytes > 200 * 1024) continue;
+        size_t bytes = el * sizeof(T) + CH * stage_bytes;
+        if (bytes > 216 * 1024) continue;
         pl.ok = true; pl.C = C; g.sl = sl; pl.smem = bytes;
         return pl;
     }
     return pl;
 }
 
-template <typename T, int NB>
-static int band_factor_cluster(const BandPlan& bp, const ClusterLuPlan& pl, T* LU, int nsys, cudaStream_t st) {
+template <typename T, typename TB, int NB>
+static int band_factor_cluster(const BandPlan& bp, const ClusterLuPlan& pl, T* LU, int nsys, const ClusterLuSource& src, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_band_mu);
     void* panels = nullptr;
     CS_TRY(band_scratch(1, st, (size_t)nsys * 2 * pl.g.prs * NB * sizeof(T), true, &panels));
-    CS_CUDA(cudaFuncSetAttribute(k_band_lu_cluster<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    CS_CUDA(cudaFuncSetAttribute(k_band_lu_cluster<T, TB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nsys * pl.C));
     cfg.blockDim = dim3(CL_THREADS);
@@ -940,7 +1009,7 @@ static int band_factor_cluster(const BandPlan& bp, const ClusterLuPlan& pl, T* L
     long long* prof = nullptr;
     const char* pe = getenv("CS_BAND_PROF");
     if (pe && atoi(pe) > 0) CS_CUDA(cudaMalloc(&prof, (size_t)nsys * pl.C * 12 * sizeof(long long)));
-    CS_CUDA(cudaLaunchKernelEx(&cfg, k_band_lu_cluster<T, NB>, LU, bp.band_elems(), pl.g, (T*)panels, prof));
+    CS_CUDA(cudaLaunchKernelEx(&cfg, k_band_lu_cluster<T, TB, NB>, LU, bp.band_elems(), pl.g, (T*)panels, src, prof));
     if (prof) {
         // debugging aid: average cycles per block step and phase (0 panel load, 1 pivot-block update, 3 Gauss-Jordan,
         // 2 wait for the row update, 4 L21 + publish, 5 owner's remaining update, 6 chunk store/load, 7 non-owner update, 8 barrier wait)
@@ -961,13 +1030,36 @@ template <typename T>
 static int band_factor_any(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     if (bp.nb == 16) {
         ClusterLuPlan pl = cluster_lu_plan<T, 16>(bp);
-        if (pl.ok) { bp.diag_full = 1; return band_factor_cluster<T, 16>(bp, pl, LU, nsys, st); }
+        if (pl.ok) { bp.diag_full = 1; ClusterLuSource none{}; return band_factor_cluster<T, T, 16>(bp, pl, LU, nsys, none, st); }
         bp.diag_full = 0;
         return band_factor_t<T, 16>(bp, LU, nsys, st);
     }
     CS_CHECK(bp.nb == 32, "band plan block size must be 16 or 32");
     bp.diag_full = 0;
     return band_factor_t<T, 32>(bp, LU, nsys, st);
+}
+// A(s_f) = K + s_f diag(mdiag) formed and factored for nshift shifts.  Scalar fields: fused into the cluster
+// kernel's chunk loads (no shifted copies in HBM); otherwise k_form_shifted + the step kernels.
+int band_form_and_factor(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st) {
+    const char* e = getenv("CS_BAND_FUSE");
+    bool fuse = !(e && atoi(e) == 0) && bp.nb == 16;
+    if (fuse) {
+        ClusterLuSource src{bp.Kband, s_d, bp.map3d, bp.jstr, bp.mdiag, bp.nmodes};
+        const int nsys = nshift * bp.nmodes;
+        if (lu_cplx) {
+            ClusterLuPlan pl = cluster_lu_plan<cplx, 16>(bp, bp.cplx_band ? 0 : sizeof(double));
+            if (pl.ok) {
+                bp.diag_full = 1;
+                if (bp.cplx_band) return band_factor_cluster<cplx, cplx, 16>(bp, pl, (cplx*)LU, nsys, src, st);
+                return band_factor_cluster<cplx, double, 16>(bp, pl, (cplx*)LU, nsys, src, st);
+            }
+        } else if (!bp.cplx_band) {
+            ClusterLuPlan pl = cluster_lu_plan<double, 16>(bp);
+            if (pl.ok) { bp.diag_full = 1; return band_factor_cluster<double, double, 16>(bp, pl, (double*)LU, nsys, src, st); }
+        }
+    }
+    CS_TRY(band_form_shifted(bp, s_d, nshift, LU, lu_cplx, st));
+    return band_factor(bp, LU, lu_cplx, nshift * bp.nmodes, st);
 }
 int band_factor_launches(const BandPlan& bp, bool lu_cplx) {
     if (bp.nb == 16) {

@@ -84,6 +84,7 @@ int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long lo
 int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shift*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
 // in-place blocked LU without pivoting of nsys_tot = nshift*nmodes band matrices
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st);
+int band_form_and_factor(const BandPlan& bp, const double* s_d /*device*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
 // solve: rhs/solution xm [nvec][nmodes][n2]; vector v uses factor shift_of_vec[v]
 int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st);
 
