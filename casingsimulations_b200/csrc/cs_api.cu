@@ -292,28 +292,32 @@ static int probe_plan(cs_op* op) {
     cs_ctx* c = op->ctx;
     BandPlan& bp = op->bp;
     bool cv = bp.cplx_band;
-    CS_TRY(c->tmp1.ensure((size_t)op->n * esz(cv)));
-    CS_TRY(c->tmp2.ensure((size_t)op->n * esz(cv)));
-    CS_TRY(c->modes.ensure((size_t)bp.nmodes * bp.n2 * esz(cv)));
-    CS_TRY(c->scal.ensure(4096));
-    CS_CUDA(cudaMemsetAsync(c->scal.p, 0, 4096, c->st));     // shift 0
     int ncol = 2 * bp.p + 1;
+    // several colours per launch (one probing vector each): 5 graph nodes per batch instead of per colour
+    int pb = (int)std::min<size_t>(16, std::max<size_t>(1, ((size_t)192 << 20) / ((size_t)std::max<long long>(op->n, bp.nmodes * bp.n2) * esz(cv))));
+    pb = std::min(pb, ncol);
+    CS_TRY(c->tmp1.ensure((size_t)pb * op->n * esz(cv)));
+    CS_TRY(c->tmp2.ensure((size_t)pb * op->n * esz(cv)));
+    CS_TRY(c->modes.ensure((size_t)pb * bp.nmodes * bp.n2 * esz(cv)));
+    CS_TRY(c->scal.ensure(4096));
+    CS_CUDA(cudaMemsetAsync(c->scal.p, 0, 4096, c->st));     // shift 0 for every probing vector
     // ~4 * (2p+1) tiny launches: replay them as one cached CUDA graph (keyed by every pointer
     // and size baked into the launches) so that host jitter cannot stretch the assembly
     std::vector<unsigned long long> key = {(unsigned long long)c->tmp1.p, (unsigned long long)c->tmp2.p, (unsigned long long)c->modes.p,
         (unsigned long long)c->scal.p, (unsigned long long)bp.Kband, (unsigned long long)bp.map3d, (unsigned long long)bp.jstr,
         (unsigned long long)op->w1, (unsigned long long)op->w2, (unsigned long long)op->csr_vals, (unsigned long long)op->kind,
         (unsigned long long)bp.n2, (unsigned long long)bp.p, (unsigned long long)bp.nmodes, (unsigned long long)op->n,
-        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables};
-    g_launches += 4LL * ncol;
+        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables, (unsigned long long)pb};
+    g_launches += 4LL * ((ncol + pb - 1) / pb);
     for (auto& g : c->probe_graphs)
         if (g.first == key) { CS_CUDA(cudaGraphLaunch(g.second, c->st)); return CS_OK; }
     auto enqueue = [&]() -> int {
-        for (int col = 0; col < ncol; ++col) {
-            CS_TRY(band_probe_fill(bp, col, c->tmp1.p, op->n, cv, c->st));
-            CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, 1, cv));
-            CS_TRY(band_dft_gather(bp, c->tmp2.p, cv, c->modes.p, cv, bp.nmodes, op->n, 1, c->st));
-            CS_TRY(band_probe_store(bp, col, c->modes.p, c->st));
+        for (int col = 0; col < ncol; col += pb) {
+            int nb = std::min(pb, ncol - col);
+            CS_TRY(band_probe_fill(bp, col, nb, c->tmp1.p, op->n, cv, c->st));
+            CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, nb, cv));
+            CS_TRY(band_dft_gather(bp, c->tmp2.p, cv, c->modes.p, cv, bp.nmodes, op->n, nb, c->st));
+            CS_TRY(band_probe_store(bp, col, nb, c->modes.p, c->st));
         }
         return CS_OK;
     };

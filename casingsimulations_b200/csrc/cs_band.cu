@@ -156,27 +156,32 @@ int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d
 // (ones at j = 0 for every band index q == color mod (2p+1)); the DFT of the
 // response holds column q of every mode matrix at once.
 template <typename TX>
-__global__ void k_probe_fill(const long long* __restrict__ map3d, long long n2, int ncol, int color, TX* __restrict__ x3d) {
-    long long q = color + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * ncol;
+__global__ void k_probe_fill(const long long* __restrict__ map3d, long long n2, int ncol, int color0, long long n3d, TX* __restrict__ x3d) {
+    // probing vector blockIdx.y carries colour color0 + blockIdx.y
+    long long q = color0 + blockIdx.y + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * ncol;
     if (q >= n2) return;
     long long b = map3d[q];
-    if (b >= 0) x3d[b] = Sc<TX>::one();
+    if (b >= 0) x3d[(size_t)blockIdx.y * n3d + b] = Sc<TX>::one();
 }
-int band_probe_fill(const BandPlan& bp, int color, void* x3d, long long n3d, bool x_cplx, cudaStream_t st) {
+// nb probing vectors (colours color .. color + nb - 1) at once
+int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d, long long n3d, bool x_cplx, cudaStream_t st) {
     int ncol = 2 * bp.p + 1;
-    CS_CUDA(cudaMemsetAsync(x3d, 0, (size_t)n3d * (x_cplx ? sizeof(cplx) : sizeof(double)), st));
+    CS_CUDA(cudaMemsetAsync(x3d, 0, (size_t)nb * n3d * (x_cplx ? sizeof(cplx) : sizeof(double)), st));
     long long cnt = (bp.n2 + ncol - 1) / ncol;
-    if (x_cplx) k_probe_fill<cplx><<<cdiv(cnt, TPB), TPB, 0, st>>>(bp.map3d, bp.n2, ncol, color, (cplx*)x3d);
-    else k_probe_fill<double><<<cdiv(cnt, TPB), TPB, 0, st>>>(bp.map3d, bp.n2, ncol, color, (double*)x3d);
+    dim3 g((unsigned)cdiv(cnt, TPB), nb);
+    if (x_cplx) k_probe_fill<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.n2, ncol, color, n3d, (cplx*)x3d);
+    else k_probe_fill<double><<<g, TPB, 0, st>>>(bp.map3d, bp.n2, ncol, color, n3d, (double*)x3d);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
 
 template <typename TB>
 __global__ void k_probe_store(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int p, int pw, int ldab,
-                              int color, const TB* __restrict__ ym, TB* __restrict__ K) {
+                              int color0, int nmodes, const TB* __restrict__ ym, TB* __restrict__ K) {
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int m = blockIdx.y;
+    const int color = color0 + blockIdx.z;                   // response of probing vector blockIdx.z
+    ym += (size_t)blockIdx.z * nmodes * n2;
     if (r >= n2) return;
     if (map3d[r] < 0) return;
     if (jstr[r] == 0 && m > 0) return;
@@ -189,10 +194,10 @@ __global__ void k_probe_store(const long long* __restrict__ map3d, const int* __
     if (jstr[q] == 0 && m > 0) return;
     K[(size_t)m * n2 * ldab + (size_t)(pw + r - q) + (size_t)q * ldab] = ym[(size_t)m * n2 + r];
 }
-int band_probe_store(const BandPlan& bp, int color, const void* ym, cudaStream_t st) {
-    dim3 g((unsigned)cdiv(bp.n2, TPB), bp.nmodes);
-    if (bp.cplx_band) k_probe_store<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, bp.p, bp.pw, bp.ldab, color, (const cplx*)ym, (cplx*)bp.Kband);
-    else k_probe_store<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, bp.p, bp.pw, bp.ldab, color, (const double*)ym, (double*)bp.Kband);
+int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, cudaStream_t st) {
+    dim3 g((unsigned)cdiv(bp.n2, TPB), bp.nmodes, nb);
+    if (bp.cplx_band) k_probe_store<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, (const cplx*)ym, (cplx*)bp.Kband);
+    else k_probe_store<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, (const double*)ym, (double*)bp.Kband);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

@@ -76,8 +76,8 @@ int band_choose_nb(int p);
 int band_factor_launches(const BandPlan& bp, bool lu_cplx);
 int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm /*[nvec][nmodes][n2]*/, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
 int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
-int band_probe_fill(const BandPlan& bp, int color, void* x3d, long long n3d, bool x_cplx, cudaStream_t st);
-int band_probe_store(const BandPlan& bp, int color, const void* ym /*[nmodes][n2]*/, cudaStream_t st);
+int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]*/, long long n3d, bool x_cplx, cudaStream_t st);
+int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym /*[nb][nmodes][n2]*/, cudaStream_t st);
 // w[f][3-D index] = 1 / |diag(A(s_f))| recovered from the mode matrices (mean over modes of K_m[q,q]) + s_f * mass
 int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long long n3d, double* w, cudaStream_t st);
 // LU[f][mode] = Kband[mode] + s[f] * diag(mdiag)   (f = 0..nshift-1)
