@@ -12,5 +12,6 @@ from .physics import casing_currents, casing_charges
 from . import sources
 from . import run
 from .solver import Solver
-from .utils import load_properties, edge3DthetaSlice, face3DthetaSlice, ccv3DthetaSlice, mesh2d_from_3d
+from .utils import (load_properties, edge3DthetaSlice, face3DthetaSlice, ccv3DthetaSlice, mesh2d_from_3d,
+                    writeSimulationPy, loadSimulationResults)
 from .info import __version__, __author__, __license__

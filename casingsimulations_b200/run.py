@@ -123,6 +123,25 @@ class _Problem(object):
         if self._ctx is not None:
             self._ctx.close()
             self._ctx = None
+        self._model_on_device = False
+
+    # ---- fields rebuilt from a saved solution (utils.loadSimulationResults) ----
+    def load_fields(self, solution, m=None, paint_params=None):
+        """Fields object around a solution array read from ``fields.npy`` (run.py:208-212).  Nothing touches the GPU
+        until a derived field (j, e, ...) is asked for; then the model is set and the solution uploaded once."""
+        self._pending_model = (m, paint_params)
+        self._model_on_device = False
+        f = self._fields_from_array(np.asarray(solution))
+        f._loaded = True
+        return f
+
+    def _ensure_model(self):
+        if not getattr(self, "_model_on_device", False) and getattr(self, "_pending_model", None) is not None:
+            m, pp = self._pending_model
+            if pp is not None:
+                self.paint_params = pp
+            self._set_model(m)
+            self._model_on_device = True
 
 
 class Problem3D_CC(_Problem):
@@ -146,10 +165,19 @@ class Problem3D_CC(_Problem):
         f._phi_d = phi
         return f
 
+    def _fields_from_array(self, sol):
+        srcs = self.survey.srcList
+        assert sol.size == self.mesh.nC * len(srcs), "fields file does not match mesh / number of sources"
+        sol = sol.reshape(self.mesh.nC, -1)
+        return Fields(self, sol, srcs)
+
     def _field(self, f, name, idx):
         if name in ("phiSolution", "phi"):
             return f._sol[:, idx]
         ctx = self.ctx
+        if getattr(f, "_phi_d", None) is None:                    # loaded from disk: upload once
+            self._ensure_model()
+            f._phi_d = ctx.to_device(np.ascontiguousarray(np.real(f._sol).T))
         phi = f._phi_d[idx].contiguous()
         if name in ("j", "e", "charge"):
             return ctx.fields_dc(name, phi).cpu().numpy().T.copy()
@@ -195,10 +223,24 @@ class _ProblemFDEM(_Problem):
         self.info = info
         return Fields(self, sol, srcs)
 
+    def _fields_from_array(self, sol):
+        srcs = self.survey.srcList
+        n = self.mesh.nE if self.form == "h" else self.mesh.nF
+        assert sol.size == n * len(srcs), "fields file does not match mesh / number of sources"
+        sol = sol.reshape(n, -1).astype(complex)
+        self._se_d, self._u_d = {}, {}
+        return Fields(self, sol, srcs)
+
     def _field(self, f, name, idx):
         if name == self._solution_name or name == self.form:
             return f._sol[:, idx]
         ctx = self.ctx
+        if getattr(f, "_loaded", False):                          # loaded from disk: upload what is asked for
+            self._ensure_model()
+            for i in idx:
+                if i not in self._u_d:
+                    self._u_d[i] = ctx.to_device(np.ascontiguousarray(f._sol[:, i]), complex_=True)
+                    self._se_d[i] = ctx.to_device(np.real(f.srcList[i].s_e), complex_=False)
         cols = [ctx.fields_fdem(self.form, name, f.srcList[i].freq, self._u_d[i], self._se_d[i]).cpu().numpy() for i in idx]
         return np.stack(cols, axis=1)
 
@@ -240,11 +282,20 @@ class _ProblemTDEM(_Problem):
         self.info = info
         return Fields(self, sol, srcs, times=self.times)
 
+    def _fields_from_array(self, sol):
+        srcs = self.survey.srcList
+        nT = len(self.timeSteps) + 1
+        if sol.ndim == 2:                                         # one source: Fields.__getitem__ dropped the source axis
+            sol = sol[:, None, :]
+        assert sol.shape == (self.mesh.nF, len(srcs), nT), "fields file does not match sources / time steps"
+        return Fields(self, np.real(sol), srcs, times=self.times)
+
     def _field(self, f, name, idx):
         if name in ("jSolution", "j"):
             return f._sol[:, idx, :]
         if name == "e":      # e = Mf^-1 MfRho j
             ctx = self.ctx
+            self._ensure_model()
             w = (ctx.face_inner_product(self._sigma_d, True, False) / ctx.face_inner_product()).cpu().numpy()
             return f._sol[:, idx, :] * w[:, None, None]
         raise KeyError(name)

@@ -412,3 +412,44 @@ def test_two_contexts_on_two_host_threads():
         assert k in both, "worker thread failed"
         for x, y in zip(alone[k], both[k]):
             assert rel(x, y) < 1e-9
+
+
+def test_load_simulation_results_rebuilds_derived_fields(tmp_path):
+    """utils.py:210-253: a saved study re-read with loadSimulationResults gives the same solution and the same
+    derived fields (j, e, b; DC j / e / charge; TDEM e) as the run that wrote it."""
+    tmp = str(tmp_path / "study")
+    mp, mg = _casing_sim(tmp)
+    src = sources.TopCasingSrc(directory=tmp, modelParameters=mp, meshGenerator=mg)
+    sim = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src)
+    f = sim.run()
+    want = {name: f[:, name] for name in ("hSolution", "j", "e", "b")}
+    sim.prob.clean()
+    back = cs.loadSimulationResults(directory=tmp)
+    fb = back.fields()
+    for name, val in want.items():
+        assert np.array_equal(fb[:, name], val), name
+    s1 = back.survey.srcList[1]
+    assert np.array_equal(fb[s1, "j"][:, 0], want["j"][:, 1])
+    back.prob.clean()
+    # DC
+    tmpd = str(tmp_path / "dc")
+    simd = run.SimulationDC(directory=tmpd, modelParameters=mp, meshGenerator=mg, src_a=np.array([[0.05125, 0.0, -2.5]]),
+                            src_b=np.array([[1000.0, 0.0, -2.5]]))
+    fd = simd.run()
+    wantd = {name: fd[:, name] for name in ("phi", "j", "e", "charge")}
+    simd.prob.clean()
+    backd = cs.loadSimulationResults(directory=tmpd, fields="fieldsDC.npy")
+    for name, val in wantd.items():
+        assert np.array_equal(backd.fields()[:, name], val), name
+    backd.prob.clean()
+    # TDEM (one source: the saved array has no source axis)
+    tmpt = str(tmp_path / "tdem")
+    mpt, mgt = _casing_sim(tmpt, 1, npadx=4, npadz=5, csz=10.0)
+    srct = sources.TopCasingSrc(directory=tmpt, modelParameters=mpt, meshGenerator=mgt)
+    simt = run.SimulationTDEM(directory=tmpt, modelParameters=mpt, meshGenerator=mgt, src=srct)
+    ft = simt.run()
+    jt, et = ft[:, "j", :], ft[:, "e", :]
+    simt.prob.clean()
+    backt = cs.loadSimulationResults(directory=tmpt)
+    assert np.array_equal(backt.fields()[:, "j", :], jt) and np.array_equal(backt.fields()[:, "e", :], et)
+    backt.prob.clean()

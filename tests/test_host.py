@@ -207,3 +207,60 @@ def test_no_cpu_fallback():
     import scipy.sparse as sp
     with pytest.raises(_lib.CasingB200Error):
         cs.Solver(sp.identity(4, format="csr"))                # no mesh hint -> raises, never falls back
+
+
+def test_load_simulation_results_and_write_simulation_py(tmp_path):
+    """utils.py:98-253 (SURVEY 8f row 3): a study directory written by Simulation*.save() / np.save can be re-read;
+    loading needs no GPU."""
+    mp, mg = _casing_setup(npadx=3, npadz=4, csz=50.0)
+    d = str(tmp_path / "study")
+    src = cs.sources.TopCasingSrc(modelParameters=mp, meshGenerator=mg, directory=d)
+    rng = np.random.default_rng(3)
+    # FDEM: (nE, nFreq) complex
+    sim = cs.run.SimulationFDEM(modelParameters=mp, meshGenerator=mg, src=src, directory=d)
+    sim.save()
+    sol = rng.standard_normal((mg.mesh.nE, 2)) + 1j * rng.standard_normal((mg.mesh.nE, 2))
+    np.save(os.path.join(d, sim.fields_filename), sol)
+    back = cs.loadSimulationResults(directory=d)
+    assert type(back) is cs.run.SimulationFDEM and back.formulation == "h"
+    assert np.array_equal(back.meshGenerator.mesh.hx, mg.mesh.hx) and back.modelParameters.sigma_casing == mp.sigma_casing
+    f = back.fields()
+    assert np.array_equal(f[:, "hSolution"], sol)
+    assert np.array_equal(f[back.survey.srcList[1], "hSolution"][:, 0], sol[:, 1])
+    # TDEM: one source -> (nF, nT + 1) as written by run.py:208-212
+    mpt = cs.model.CasingInHalfspace(src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0],
+                                     timeSteps=[(1e-6, 3), (1e-5, 2)])
+    mgt = cs.CasingMeshGenerator(modelParameters=mpt, npadx=3, npadz=4, csz=50.0)
+    dt_ = str(tmp_path / "tdem")
+    srct = cs.sources.TopCasingSrc(modelParameters=mpt, meshGenerator=mgt, directory=dt_)
+    simt = cs.run.SimulationTDEM(modelParameters=mpt, meshGenerator=mgt, src=srct, directory=dt_)
+    simt.save()
+    solt = rng.standard_normal((mgt.mesh.nF, 6))
+    np.save(os.path.join(dt_, simt.fields_filename), solt)
+    backt = cs.loadSimulationResults(directory=dt_)
+    assert np.array_equal(backt.fields()[:, "jSolution", :], solt)
+    assert np.array_equal(backt.fields()[:, "jSolution", 2][:, 0], solt[:, 2])
+    # DC
+    dd = str(tmp_path / "dc")
+    simd = cs.run.SimulationDC(modelParameters=mp, meshGenerator=mg, directory=dd, src_a=np.r_[0.05, 0.0, -10.0],
+                               src_b=np.r_[500.0, 0.0, -10.0])
+    simd.save()
+    sold = rng.standard_normal((mg.mesh.nC, 1))
+    np.save(os.path.join(dd, simd.fields_filename), sold)
+    backd = cs.loadSimulationResults(directory=dd, fields=simd.fields_filename)
+    assert np.array_equal(backd.fields()[:, "phiSolution"], sold)
+    with pytest.raises(AssertionError):
+        np.save(os.path.join(dd, simd.fields_filename), rng.standard_normal((mg.mesh.nC + 1, 1)))
+        cs.loadSimulationResults(directory=dd, fields=simd.fields_filename)
+    # writeSimulationPy: same script layout as the reference
+    mp.directory = mg.directory = src.directory = d
+    mp.save(); mg.save(); src.save()
+    cs.writeSimulationPy(modelParameters=mp.filename, meshGenerator=mg.filename, src=src.filename, physics="FDEM", directory=d)
+    text = open(os.path.join(d, "simulation.py")).read()
+    compile(text, "simulation.py", "exec")
+    for needle in ("casingSimulations.run.SimulationFDEM(", "fields = sim.run()", "mesh2D.hy = np.r_[2*np.pi]",
+                   "casingSimulations.run.SimulationDC(", "src_a = sim.src.src_a_closest - np.r_[0., 0., csz/2.]"):
+        assert needle in text
+    cs.writeSimulationPy(physics="TDEM", directory=d, simulation_filename="s2.py", includeDC=False, include2D=False)
+    t2 = open(os.path.join(d, "s2.py")).read()
+    assert "SimulationTDEM" in t2 and "SimulationDC" not in t2 and "sim2D" not in t2
