@@ -453,3 +453,48 @@ def test_load_simulation_results_rebuilds_derived_fields(tmp_path):
     backt = cs.loadSimulationResults(directory=tmpt)
     assert np.array_equal(backt.fields()[:, "j", :], jt) and np.array_equal(backt.fields()[:, "e", :], et)
     backt.prob.clean()
+
+
+def test_full_size_c2_fdem_sweep():
+    """BASELINE config 2 (the bench workload) at full size: FDEM-h on the 109 x 1 x 717 casing mesh, TopCasingSrc,
+    32 frequencies 0.1 Hz - 1 kHz in one batched solve.  Oracle parity at both ends of the sweep (rel-L2 <= 1e-6,
+    BASELINE.json north_star), plus size-independent properties for all 32: Krylov residual, residual through the
+    oracle's assembled matrix, D~ (j + s_e) = D~ C h = 0, linearity in s_e, ~1 A down the casing at 0.1 Hz."""
+    import torch
+    from oracle.cyl_oracle import OracleCylMesh, OracleFDEM, _sdiag
+    freqs = np.logspace(-1, 3, 32)
+    mp = cs.model.CasingInHalfspace(src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0], freqs=freqs)
+    mg = cs.CasingMeshGenerator(modelParameters=mp, npadx=10, npadz=20, csz=1.5)
+    m = mg.mesh
+    assert tuple(m.vnC) == (109, 1, 717)
+    src = sources.TopCasingSrc(modelParameters=mp, meshGenerator=mg, directory="/tmp/cs_b200_c2")
+    sim = run.SimulationFDEM(directory="/tmp/cs_b200_c2", modelParameters=mp, meshGenerator=mg, src=src)
+    f = sim.run(save=False)
+    info = sim.prob.info
+    print("C2 info", info)
+    assert info["relres"] <= 1e-10
+    h = f[:, "hSolution"]
+    assert h.shape == (m.nE, 32)
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    P = OracleFDEM(om, mp.sigma(m), mp.mu(m), "h")
+    se = np.real(sim.survey.srcList[0].s_e)
+    for k in (0, 31):
+        href = P.solve(freqs[k], se, refine=True)
+        print("C2 f = %g Hz: rel-L2 vs oracle" % freqs[k], rel(h[:, k], href))
+        assert rel(h[:, k], href) < 1e-6
+    Dt = om._Dtopo() @ _sdiag(om.area)
+    j = f[:, "j"]
+    for k in range(0, 32, 5):
+        A, rhs = P.getA(freqs[k]), P.getRHS(freqs[k], se)
+        d = np.sqrt(np.abs(A.diagonal()))
+        assert np.linalg.norm((A @ h[:, k] - rhs) / d) <= 1e-9 * np.linalg.norm(rhs / d), freqs[k]
+        div = Dt @ (j[:, k] + se)
+        assert np.linalg.norm(div) <= 1e-9 * np.linalg.norm(np.abs(Dt) @ np.abs(j[:, k])), freqs[k]
+    # linearity: the batched solve of 2.5 s_e is 2.5 h (two frequencies, straight through the C ABI)
+    ctx = sim.prob.ctx
+    u = ctx.solve_fdem("h", freqs[[3, 20]], ctx.to_device(2.5 * se, complex_=False)).cpu().numpy().T
+    assert rel(u, 2.5 * h[:, [3, 20]]) < 1e-8
+    cur = cs.casing_currents(np.real(j[:, [0]]), m, mp)
+    assert 0.9 < -cur["z"][1][-1, 0] <= 1.0 + 1e-6                     # ~1 A enters the casing top at 0.1 Hz
+    sim.prob.clean()
+    shutil.rmtree("/tmp/cs_b200_c2", ignore_errors=True)
