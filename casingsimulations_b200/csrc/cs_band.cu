@@ -1352,10 +1352,13 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
 
 template <typename T, int TPR, int NB>
 static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, int th, size_t sm, int wsz, int nst, cudaStream_t st) {
-    // one extra warp that only stages the factors, if the launch bounds leave room (CS_SOLVE_PROD=0: never)
+    // one extra warp that only stages the factors, if the launch bounds leave room (CS_SOLVE_PROD=0: never).
+    // Complex systems only: the producer of a real system has to use cp.async (no 16-byte alignment for TMA),
+    // and one warp issuing all of a stage's cp.async is much slower than all warps sharing them
+    // (C1 DC, 4 band solves: 141 ms with a producer warp vs 54 ms without).
     const int bound = TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640);
     const char* e = getenv("CS_SOLVE_PROD");
-    const bool hp = (th + 32 <= bound) && !(e && atoi(e) == 0);
+    const bool hp = (sizeof(T) == 16 || (e && atoi(e) > 0)) && (th + 32 <= bound) && !(e && atoi(e) == 0);
     if (hp) CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     else CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     dim3 g(bp.nmodes, nvec);
