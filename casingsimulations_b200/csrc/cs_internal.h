@@ -29,7 +29,7 @@ int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const d
                    const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
 // K4 face form: y = alpha .* (C diag(gamma) C^T (alpha .* x) + s[sys] x), uF = alpha/area, gE = len^2 gamma
 int launch_face_op(const MeshD& m, const double* uF, const double* gE, const double* s_d,
-                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
+                   const void* x, void* y, int nsys, bool cplx_vec, void* ework /*nsys*nE workspace or nullptr*/, cudaStream_t st);
 
 int launch_csr_spmv(long long n, const long long* indptr, const int* indices, const void* vals, bool a_cplx,
                     const void* x, void* y, int nsys, bool x_cplx, cudaStream_t st);
