@@ -602,7 +602,6 @@ struct ClusterLuGeom {
     int nbw;      // blocks a panel reaches to its right: ceil(p / NB)
     int sl;       // chunk slots per CTA: ceil((nbw + 1) / C)
     int prs;      // panel leading dimension: roundup(p, 4)
-    int split;    // row update of the look-ahead step on sub-partitions 2, 3 only
 };
 
 // One thread's TR x 4 register tile of the trailing update  A[i][j] -= L21[i][:] A12[:][j]  by panel kb.
@@ -693,7 +692,7 @@ __device__ __forceinline__ void cl_process(const ClusterLuGeom& g, T* chunks, co
 template <typename T, int NB>
 __device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunks, T* chunk, const T* Lb, bool update,
                                           T* __restrict__ P, T (*Di)[NB + 1], T (*rowb)[NB],
-                                          T (*colb)[NB], int kb, int C, int split, long long* prof, long long* prof_s, long long* tprev) {
+                                          T (*colb)[NB], int kb, int C, long long* prof, long long* prof_s, long long* tprev) {
     static_assert(NB == 16 && CL_THREADS == 256, "thread <-> element mappings below");
     const int ld = g.ldab - 1;
     T* sv = chunk + g.pw;
@@ -761,15 +760,12 @@ __device__ __forceinline__ void cl_factor(const ClusterLuGeom& g, T* chunks, T* 
         }
         CL_TICK(3);
     } else if (Rp > NB) {
-        // the Gauss-Jordan warps 0 and 1 sit on SM sub-partitions 0 and 1 (warp id mod 4).  With
-        // CS_BAND_SPLIT=1 the row update runs on warps 2, 3, 6, 7 (sub-partitions 2, 3) only, so that
-        // the latency chain does not queue behind their FP64 / LSU traffic: the sweep then takes 5.5k
-        // instead of 6.6k cycles, but the update needs two passes (7.2k vs 4.6k) -- off by default
-        const int w = tid >> 5;
+        // (the Gauss-Jordan warps 0 and 1 sit on SM sub-partitions 0 and 1; restricting this update to warps
+        //  2, 3, 6, 7 -- sub-partitions 2, 3 -- made the sweep 5.5k instead of 6.6k cycles but the update
+        //  7.2k instead of 4.6k: all six warps it is)
         long long tt0 = 0;
         if (prof && tid == 64) tt0 = clock64();
-        if (!split) cl_trailing<T, NB, 2>(g, chunks, Lb, kb - 1, Rp, NB, kb, 1, C, tid - 64, CL_THREADS - 64);
-        else if ((w & 3) >= 2) cl_trailing<T, NB, 2>(g, chunks, Lb, kb - 1, Rp, NB, kb, 1, C, ((w >> 2) * 2 + (w & 1)) * 32 + (tid & 31), 128);
+        cl_trailing<T, NB, 2>(g, chunks, Lb, kb - 1, Rp, NB, kb, 1, C, tid - 64, CL_THREADS - 64);
         if (prof && tid == 64) prof_s[9] += clock64() - tt0;
     }
     __syncthreads();
@@ -906,7 +902,7 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
     cp_async_wait_all();
     __syncthreads();
     if (rank == 0) {
-        cl_factor<T, NB>(g, chunks, chunks, Lb, false, P, Di, rowb, colb, 0, C, g.split, nullptr, prof_s, tprev);
+        cl_factor<T, NB>(g, chunks, chunks, Lb, false, P, Di, rowb, colb, 0, C, nullptr, prof_s, tprev);
         cl_store_chunk<T, NB>(g, chunks, AB, 0);
         __syncthreads();
         if (src.K) { if (g.sl * C < g.nblk) { cl_load_chunk_async<T, TB, NB>(g, chunks, stg, src, sys, g.sl * C); pend_jb = g.sl * C; pend_chunk = chunks; } }
@@ -938,7 +934,7 @@ k_band_lu_cluster(T* __restrict__ LU, size_t nel, ClusterLuGeom g, T* __restrict
         if (rank == (kb + 1) % C) {
             // look-ahead: bring block kb+1 up to date, factor and publish it, then do the rest
             T* chunk = chunks + (size_t)(((kb + 1) / C) % g.sl) * CH;
-            cl_factor<T, NB>(g, chunks, chunk, Lb, true, P + (size_t)((kb + 1) & 1) * g.prs * NB, Di, rowb, colb, kb + 1, C, g.split, prof, prof_s, tprev);
+            cl_factor<T, NB>(g, chunks, chunk, Lb, true, P + (size_t)((kb + 1) & 1) * g.prs * NB, Di, rowb, colb, kb + 1, C, prof, prof_s, tprev);
             cluster_arrive();
             cl_process<T, NB>(g, chunks, Lb, kb, R, first + C, nown - 1, C);
             __syncthreads();
@@ -977,7 +973,6 @@ static ClusterLuPlan cluster_lu_plan(const BandPlan& bp, size_t stage_bytes = 0)
     g.nblk = (int)((bp.n2 + NB - 1) / NB);
     g.nbw = (bp.p + NB - 1) / NB;
     g.prs = ((bp.p + 3) / 4) * 4;
-    { const char* se = getenv("CS_BAND_SPLIT"); g.split = se ? atoi(se) : 0; }
     if (bp.pw < g.nbw * NB || bp.p < 1) return pl;
     const int cands[3] = {4, 8, 2};
     for (int ci = 0; ci < 3; ++ci) {
