@@ -9,7 +9,9 @@ PARITY UNPINNED: the reference ships no golden vectors and its dependencies
 (SimPEG 0.14.x, discretize ~0.6, pymatsolver) are not installable here, so
 this restatement is pinned only by (i) the reference's own self-consistency
 tests (tests/test_cyl2D3D.py:202-359, re-run in tests/test_oracle.py),
-(ii) discrete identities and (iii) analytic solutions.  Every [3P-recall]
+(ii) discrete identities and (iii) closed-form solutions (DC dipole and the
+complex field of a vertical electric dipole in a wholespace, tests/test_oracle.py).
+Every [3P-recall]
 convention below is anchored to the reference call site that triggers it.
 
 Reference anchors

@@ -498,3 +498,26 @@ def test_full_size_c2_fdem_sweep():
     assert 0.9 < -cur["z"][1][-1, 0] <= 1.0 + 1e-6                     # ~1 A enters the casing top at 0.1 Hz
     sim.prob.clean()
     shutil.rmtree("/tmp/cs_b200_c2", ignore_errors=True)
+
+
+def test_fdem_vertical_dipole_wholespace_analytic_gpu():
+    """The GPU FDEM-h path against the closed-form wholespace field of a vertical electric dipole (Ward & Hohmann
+    1988, eq. 2.40): a known answer that does not go through the oracle at all (SURVEY 8c iii)."""
+    from casingsimulations_b200 import _lib
+    from test_oracle import ved_check, ved_problem
+    hx, hz, m, se, zsrc = ved_problem()
+    sigma = 0.1
+    ctx = _lib.Context(0)
+    ctx.set_mesh(hx, np.r_[2 * np.pi], hz, m.x0[2])
+    ctx.set_model(ctx.to_device(sigma * np.ones(m.nC)), ctx.to_device(4e-7 * np.pi * np.ones(m.nC)))
+    freqs = np.r_[1e3, 1e4]
+    se_d = ctx.to_device(se, complex_=False)
+    u = ctx.solve_fdem("h", freqs, se_d)
+    assert ctx.info["relres"] <= 1e-10
+    for k, (freq, imag_min) in enumerate(((1e3, 0.08), (1e4, 0.35))):
+        e = ctx.fields_fdem("h", "e", freq, u[k], se_d).cpu().numpy()
+        rz, rx, imag_share = ved_check(m, e, zsrc, sigma, freq)
+        print("VED", freq, rz, rx, imag_share)
+        assert rz < 0.015 and rx < 0.015, (freq, rz, rx)
+        assert imag_share > imag_min
+    ctx.close()
