@@ -521,3 +521,25 @@ def test_fdem_vertical_dipole_wholespace_analytic_gpu():
         assert rz < 0.015 and rx < 0.015, (freq, rz, rx)
         assert imag_share > imag_min
     ctx.close()
+
+
+def test_tdem_vertical_dipole_stepoff_analytic_gpu():
+    """The GPU TDEM-j path (DC initial state, backward Euler, divergence cleaning) against the closed-form step-off
+    response of a vertical electric dipole in a wholespace (Ward & Hohmann 1988, eq. 2.50), without the oracle."""
+    from casingsimulations_b200 import _lib
+    from oracle.cyl_oracle import mesh_tensor
+    from test_oracle import VED_DTS, ved_problem, ved_stepoff_errors
+    hx, hz, m, se, zsrc = ved_problem()
+    sigma = 0.1
+    ctx = _lib.Context(0)
+    ctx.set_mesh(hx, np.r_[2 * np.pi], hz, m.x0[2])
+    ctx.set_model(ctx.to_device(sigma * np.ones(m.nC)), ctx.to_device(4e-7 * np.pi * np.ones(m.nC)))
+    dts = mesh_tensor(VED_DTS)
+    times = np.r_[0.0, np.cumsum(dts)]
+    J = ctx.tdem_run("j", dts, ctx.to_device(se, complex_=False)).cpu().numpy().T
+    errs = ved_stepoff_errors(m, J, times, zsrc, sigma, [0, 10, 25, 35, 45])
+    print("VED step-off", errs)
+    assert errs[0][0] < 0.015 and errs[0][1] < 0.015
+    for ez, ex in errs[1:]:
+        assert ez < 0.05 and ex < 0.09
+    ctx.close()

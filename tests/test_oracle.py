@@ -211,3 +211,53 @@ def test_fdem_vertical_dipole_wholespace_analytic():
         rz, rx, imag_share = ved_check(m, e, zsrc, sigma, freq)
         assert rz < 0.015 and rx < 0.015, (freq, rz, rx)
         assert imag_share > imag_min
+
+
+def ved_stepoff(rho, z, zs, sigma, t):
+    """E of a unit-moment vertical electric dipole in a wholespace whose DC current is switched off at t = 0:
+    e_DC - e_step-on(t), Ward & Hohmann (1988) eq. 2.50 rotated to z.  Returns (E_z, E_rho); t = 0 gives the DC field."""
+    from scipy.special import erfc
+    zz = z - zs
+    r = np.sqrt(rho ** 2 + zz ** 2)
+    pre = 1.0 / (4 * np.pi * sigma * r ** 3)
+    ez, er = pre * (3 * zz ** 2 / r ** 2 - 1), pre * (3 * rho * zz / r ** 2)
+    if t > 0:
+        x = np.sqrt(MU_0 * sigma / (4 * t)) * r
+        g1 = (4 / np.sqrt(np.pi) * x ** 3 + 6 / np.sqrt(np.pi) * x) * np.exp(-x ** 2) + 3 * erfc(x)
+        g2 = (4 / np.sqrt(np.pi) * x ** 3 + 2 / np.sqrt(np.pi) * x) * np.exp(-x ** 2) + erfc(x)
+        ez, er = ez - pre * (zz ** 2 / r ** 2 * g1 - g2), er - pre * (rho * zz / r ** 2 * g1)
+    return ez, er
+
+
+def ved_stepoff_errors(m, J, times, zsrc, sigma, steps):
+    gz, gx = m.gridFz, m.gridFx
+    Rz, Rx = np.hypot(gz[:, 0], gz[:, 2]), np.hypot(gx[:, 0], gx[:, 2])
+    sz, sx = (Rz > 12) & (Rz < 40), (Rx > 12) & (Rx < 40)
+    out = []
+    for n in steps:
+        e = J[:, n] / sigma
+        Ez = sum(ved_stepoff(gz[:, 0], gz[:, 2], zs, sigma, times[n])[0] for zs in zsrc)
+        Ex = sum(ved_stepoff(gx[:, 0], gx[:, 2], zs, sigma, times[n])[1] for zs in zsrc)
+        ez, ex = e[m.nFx + m.nFy:], e[:m.nFx]
+        out.append((np.linalg.norm(ez[sz] - Ez[sz]) / np.linalg.norm(Ez[sz]), np.linalg.norm(ex[sx] - Ex[sx]) / np.linalg.norm(Ex[sx])))
+    return out
+
+
+VED_DTS = [(2e-7, 25), (1e-6, 20), (5e-6, 16)]          # 61 steps to t = 1.05e-4 s
+
+
+def test_tdem_vertical_dipole_stepoff_analytic():
+    """the TDEM-j oracle (DC initial state + backward Euler) against the closed-form step-off
+    response of a vertical electric dipole in a wholespace; halving the time steps halves the error (first order)."""
+    hx, hz, m, se, zsrc = ved_problem()
+    sigma = 0.1
+    errs = {}
+    for tag, scale in (("coarse", 1), ("fine", 2)):
+        dts = mesh_tensor([(dt / scale, n * scale) for dt, n in VED_DTS])
+        times = np.r_[0.0, np.cumsum(dts)]
+        J = OracleTDEM(m, sigma * np.ones(m.nC), MU_0 * np.ones(m.nC), dts).fields(se)
+        errs[tag] = ved_stepoff_errors(m, J, times, zsrc, sigma, [0, 10 * scale, 25 * scale, 35 * scale, 45 * scale])
+    assert errs["coarse"][0][0] < 0.015 and errs["coarse"][0][1] < 0.015        # t = 0: the DC dipole
+    for (cz, cx), (fz, fx) in zip(errs["coarse"][1:], errs["fine"][1:]):
+        assert cz < 0.05 and cx < 0.09, errs
+        assert fz < 0.7 * cz and fx < 0.7 * cx, errs                           # first-order convergence in dt
