@@ -562,3 +562,40 @@ def test_3d_off_axis_dipole_wholespace_analytic_gpu():
     for freq in (1e3, 1e4):
         assert dflt[(freq, "axis")] < 0.03 and dflt[(freq, "shell")] < 0.09
         assert alt[(freq, "axis")] > 1.8 * dflt[(freq, "axis")]
+
+
+def test_dc_3d_off_axis_dipole_analytic_gpu():
+    """3-D DC known answer on the GPU path: current dipole 8.5 m off the axis of a 109 k-cell mesh in a wholespace
+    against phi = I / (4 pi sigma) (1/Ra - 1/Rb), incl. the cells around the axis."""
+    from casingsimulations_b200 import _lib
+    from casingsimulations_b200.mesh import closestPoints
+    from oracle.cyl_oracle import OracleCylMesh, mesh_tensor
+    nth = 32
+    hx = mesh_tensor([(1.0, 24), (1.0, 14, 1.4)])
+    hz = mesh_tensor([(1.0, 14, -1.4), (1.0, 48), (1.0, 14, 1.4)])
+    hy = np.ones(nth) * 2 * np.pi / nth
+    sigma = 0.1
+    m = OracleCylMesh([hx, hy, hz], [0, 0, -hz.sum() / 2])
+    th0 = (nth // 4 + 0.5) * 2 * np.pi / nth
+    cc = m.gridCC
+    X = np.c_[cc[:, 0] * np.cos(cc[:, 1]), cc[:, 0] * np.sin(cc[:, 1]), cc[:, 2]]
+
+    def closest(pt):
+        return int(np.argmin((cc[:, 0] - pt[0]) ** 2 + (np.angle(np.exp(1j * (cc[:, 1] - pt[1])))) ** 2 * pt[0] ** 2 + (cc[:, 2] - pt[2]) ** 2))
+    ia, ib = closest((8.5, th0, 6.5)), closest((8.5, th0, -6.5))
+    q = np.zeros((1, m.nC))
+    q[0, ia], q[0, ib] = 1.0, -1.0
+    ctx = _lib.Context(0)
+    ctx.set_mesh(hx, hy, hz, m.x0[2])
+    ctx.set_model(ctx.to_device(sigma * np.ones(m.nC)), ctx.to_device(4e-7 * np.pi * np.ones(m.nC)))
+    phi = ctx.solve_dc(ctx.to_device(q)).cpu().numpy()[0]
+    assert ctx.info["relres"] <= 1e-10 or ctx.info["backward_err"] <= 2e-15
+    Ra = np.maximum(np.linalg.norm(X - X[ia], axis=1), 1e-9)
+    Rb = np.maximum(np.linalg.norm(X - X[ib], axis=1), 1e-9)
+    ana = (1 / Ra - 1 / Rb) / (4 * np.pi * sigma)
+    axis = (cc[:, 0] < 3) & (np.abs(cc[:, 2]) < 12) & (Ra > 4) & (Rb > 4)
+    shell = (Ra > 4) & (Rb > 4) & (Ra < 18) & (Rb < 18)
+    ea, es = rel(phi[axis], ana[axis]), rel(phi[shell], ana[shell])
+    print("DC 3-D off-axis dipole: axis", ea, "shell", es)
+    assert ea < 0.01 and es < 0.04
+    ctx.close()

@@ -261,3 +261,33 @@ def test_tdem_vertical_dipole_stepoff_analytic():
     for (cz, cx), (fz, fx) in zip(errs["coarse"][1:], errs["fine"][1:]):
         assert cz < 0.05 and cx < 0.09, errs
         assert fz < 0.7 * cz and fx < 0.7 * cx, errs                           # first-order convergence in dt
+
+
+def test_dc_3d_off_axis_dipole_analytic():
+    """3-D known answer for the DC oracle: a current dipole 8.5 m OFF the mesh axis in a wholespace against
+    phi = I / (4 pi sigma) (1/Ra - 1/Rb).  The region around the axis is where the axis conventions act
+    (SURVEY A.4 OQ1): axis_weight_face = 0.5 (default) is closer to the closed form than 1.0."""
+    nth = 16
+    hx = mesh_tensor([(1.0, 24), (1.0, 14, 1.4)])
+    hz = mesh_tensor([(1.0, 14, -1.4), (1.0, 48), (1.0, 14, 1.4)])
+    hy = np.ones(nth) * 2 * np.pi / nth
+    sigma = 0.1
+    th0 = (nth // 4 + 0.5) * 2 * np.pi / nth
+    a, b = np.array([[8.5, th0, 6.5]]), np.array([[8.5, th0, -6.5]])
+    err = {}
+    for awf in (0.5, 1.0):
+        m = OracleCylMesh([hx, hy, hz], [0, 0, -hz.sum() / 2], axis_weight_face=awf)
+        P = OracleDC(m, sigma * np.ones(m.nC))
+        phi = P.fields(a, b)[:, 0]
+        q = P.getRHS(a, b)[:, 0]
+        cc = m.gridCC
+        X = np.c_[cc[:, 0] * np.cos(cc[:, 1]), cc[:, 0] * np.sin(cc[:, 1]), cc[:, 2]]
+        Ra = np.maximum(np.linalg.norm(X - X[np.argmax(q)], axis=1), 1e-9)
+        Rb = np.maximum(np.linalg.norm(X - X[np.argmin(q)], axis=1), 1e-9)
+        ana = (1 / Ra - 1 / Rb) / (4 * np.pi * sigma)
+        axis = (cc[:, 0] < 3) & (np.abs(cc[:, 2]) < 12) & (Ra > 4) & (Rb > 4)
+        shell = (Ra > 4) & (Rb > 4) & (Ra < 18) & (Rb < 18)
+        err[awf] = (np.linalg.norm(phi[axis] - ana[axis]) / np.linalg.norm(ana[axis]),
+                    np.linalg.norm(phi[shell] - ana[shell]) / np.linalg.norm(ana[shell]))
+    assert err[0.5][0] < 0.01 and err[0.5][1] < 0.06, err
+    assert err[1.0][0] > 1.3 * err[0.5][0], err
