@@ -14,7 +14,7 @@ from casingsimulations_b200 import _lib
 from oracle.cyl_oracle import OracleCylMesh, mesh_tensor
 from test_oracle import ved_wholespace
 
-def run(nth=32, conventions=((1.0, 0.5), (0.5, 0.5), (1.0, 1.0), (0.5, 1.0)), freqs=(1e3, 1e4), verbose=True):
+def run(nth=32, conventions=((1.0, 0.5), (0.5, 0.5), (1.0, 1.0), (0.5, 1.0)), freqs=(1e3, 1e4), verbose=True, mur=1.0):
     """returns {(awe, awf): {(freq, region): relative L2 error over all three components}}"""
     hx = mesh_tensor([(1.0, 40), (1.0, 18, 1.35)])
     hz = mesh_tensor([(1.0, 18, -1.35), (1.0, 80), (1.0, 18, 1.35)])
@@ -35,8 +35,9 @@ def run(nth=32, conventions=((1.0, 0.5), (0.5, 0.5), (1.0, 1.0), (0.5, 1.0)), fr
         rho, th, z = grid[:, 0], grid[:, 1], grid[:, 2]
         dx, dy = rho * np.cos(th) - x0, rho * np.sin(th) - y0
         rp = np.maximum(np.hypot(dx, dy), 1e-12)
-        ez = sum(ved_wholespace(rp, z, zs, sigma, freq)[0] for zs in zsrc)
-        er = sum(ved_wholespace(rp, z, zs, sigma, freq)[1] for zs in zsrc)
+        # (a permeable wholespace mu_r behaves like sigma -> sigma mu_r in k^2 with the 1/sigma prefactor kept)
+        ez = sum(ved_wholespace(rp, z, zs, sigma * mur, freq)[0] for zs in zsrc) * mur
+        er = sum(ved_wholespace(rp, z, zs, sigma * mur, freq)[1] for zs in zsrc) * mur
         ex, ey = er * dx / rp, er * dy / rp
         if comp == "z":
             return ez
@@ -48,7 +49,7 @@ def run(nth=32, conventions=((1.0, 0.5), (0.5, 0.5), (1.0, 1.0), (0.5, 1.0)), fr
     for awe, awf in conventions:
         ctx = _lib.Context(0)
         ctx.set_mesh(hx, hy, hz, m.x0[2], axis_weight_edge=awe, axis_weight_face=awf)
-        ctx.set_model(ctx.to_device(sigma * np.ones(m.nC)), ctx.to_device(4e-7 * np.pi * np.ones(m.nC)))
+        ctx.set_model(ctx.to_device(sigma * np.ones(m.nC)), ctx.to_device(mur * 4e-7 * np.pi * np.ones(m.nC)))
         se_d = ctx.to_device(se, complex_=False)
         u = ctx.solve_fdem("h", np.asarray(freqs, dtype=float), se_d)
         res = {"relres": ctx.info["relres"]}
@@ -75,4 +76,5 @@ def run(nth=32, conventions=((1.0, 0.5), (0.5, 0.5), (1.0, 1.0), (0.5, 1.0)), fr
 
 
 if __name__ == "__main__":
-    run(int(sys.argv[1]) if len(sys.argv) > 1 else 32)
+    run(int(sys.argv[1]) if len(sys.argv) > 1 else 32, mur=float(sys.argv[2]) if len(sys.argv) > 2 else 1.0,
+        freqs=tuple(float(f) for f in sys.argv[3:]) or (1e3, 1e4))
