@@ -927,6 +927,7 @@ extern "C" int cs_ctx_destroy(cs_ctx* c) {
     for (auto& g : c->probe_graphs) cudaGraphExecDestroy(g.second);
     cudaFreeHost(c->pin);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    band_release_stream(c->st);
     if (c->own_stream) cudaStreamDestroy(c->st);
     delete c;
     return CS_OK;

@@ -40,12 +40,15 @@ static const int TPB = 128;
 // by one mutex; the small device scratch buffers are per (purpose, device, stream), so independent
 // contexts (one stream each) never share one.
 static std::mutex g_band_mu;
+struct BandScratchBuf { void* p = nullptr; size_t bytes = 0; };
+static std::map<std::tuple<int, int, cudaStream_t>, BandScratchBuf>& band_scratch_map() {
+    static std::map<std::tuple<int, int, cudaStream_t>, BandScratchBuf> bufs;
+    return bufs;
+}
 static int band_scratch(int which, cudaStream_t st, size_t need, bool zero_new, void** out) {
-    struct Buf { void* p = nullptr; size_t bytes = 0; };
-    static std::map<std::tuple<int, int, cudaStream_t>, Buf> bufs;
     int dev = 0;
     CS_CUDA(cudaGetDevice(&dev));
-    Buf& b = bufs[std::make_tuple(which, dev, st)];
+    BandScratchBuf& b = band_scratch_map()[std::make_tuple(which, dev, st)];
     if (need > b.bytes) {
         if (b.p) cudaFree(b.p);                  // (synchronises with everything still using it)
         b.p = nullptr; b.bytes = 0;
@@ -57,7 +60,15 @@ static int band_scratch(int which, cudaStream_t st, size_t need, bool zero_new, 
     *out = b.p;
     return CS_OK;
 }
-#define TWO_PI 6.28318530717958647692
+// a context that goes away takes the scratch buffers of its stream with it
+void band_release_stream(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_band_mu);
+    auto& bufs = band_scratch_map();
+    for (auto it = bufs.begin(); it != bufs.end();) {
+        if (std::get<2>(it->first) == st) { if (it->second.p) cudaFree(it->second.p); it = bufs.erase(it); }
+        else ++it;
+    }
+}
 
 // ------------------------------------------------------------------ DFT -----
 // xm[v][m][q] = sum_j x3d[v][map3d[q] + j*jstr[q]] * exp(-2 pi i j m / nth)

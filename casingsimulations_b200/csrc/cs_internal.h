@@ -73,6 +73,7 @@ struct BandPlan {
 
 // block size (16 or 32) for a plan with half bandwidth p
 int band_choose_nb(int p);
+void band_release_stream(cudaStream_t st);   // frees the band scratch buffers keyed by this stream
 int band_factor_launches(const BandPlan& bp, bool lu_cplx);
 int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm /*[nvec][nmodes][n2]*/, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
 int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
