@@ -599,3 +599,13 @@ def test_dc_3d_off_axis_dipole_analytic_gpu():
     print("DC 3-D off-axis dipole: axis", ea, "shell", es)
     assert ea < 0.01 and es < 0.04
     ctx.close()
+
+
+def test_plain_c_client_of_the_c_abi(tmp_path):
+    """examples/c_abi_dc.c: a DC solve driven from C through include/casing_b200.h (cudaMalloc buffers, no Python)"""
+    import subprocess
+    from test_host import _compile_c_example
+    exe = _compile_c_example(str(tmp_path / "c_abi_dc"))
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(res.stdout, res.stderr)
+    assert res.returncode == 0 and "C ABI OK" in res.stdout

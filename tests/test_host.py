@@ -264,3 +264,23 @@ def test_load_simulation_results_and_write_simulation_py(tmp_path):
     cs.writeSimulationPy(physics="TDEM", directory=d, simulation_filename="s2.py", includeDC=False, include2D=False)
     t2 = open(os.path.join(d, "s2.py")).read()
     assert "SimulationTDEM" in t2 and "SimulationDC" not in t2 and "sim2D" not in t2
+
+
+def _compile_c_example(out):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("gcc or the CUDA headers are not available")
+    libdir = os.path.join(ROOT, "casingsimulations_b200")
+    cmd = ["gcc", "-O2", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(ROOT, "examples", "c_abi_dc.c"), "-L", libdir, "-lcasing_b200", "-L", "/usr/local/cuda/lib64",
+           "-lcudart", "-lm", "-Wl,-rpath," + libdir, "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return out
+
+
+def test_c_abi_header_compiles_and_links_from_plain_c(tmp_path):
+    """the boundary is a C ABI: include/casing_b200.h is valid C and a C client links against the library"""
+    exe = _compile_c_example(str(tmp_path / "c_abi_dc"))
+    assert os.path.exists(exe)
