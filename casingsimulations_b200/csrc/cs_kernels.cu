@@ -558,11 +558,14 @@ static int launch_edge_op_cfg(const MeshD& m, const double* wF, const double* be
     size_t smb = ((size_t)EDGE_NS * ncomp * trows * (TI + 1) + 2 * 3 * (size_t)rows * TI) * sizeof(T);
     CS_CHECK(trows * (TI + 1) <= 2 * TI * rows, "staging descriptor count too small");
     dim3 blk(TI, rows), grd(itiles, jtiles, nchunk * nsys);
-    static bool attr_set = false;                // one flag per template instantiation
-    if (!attr_set) {
+    // the attribute is per device and not capturable into a CUDA graph: set it once per (instantiation, device)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    CS_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
         size_t mx = ((size_t)EDGE_NS * 3 * 6 * (TI + 1) + 2 * 3 * 5 * TI) * sizeof(T);
         CS_CUDA(cudaFuncSetAttribute(k_edge_op<T, SYM, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        attr_set = true;
+        if (dev < 64) attr_set[dev] = true;
     }
     k_edge_op<T, SYM, TI><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, tj, nchunk, kz, istride);
     return CS_OK;
