@@ -35,7 +35,8 @@ for rep in range(2):
     print("GPU rep", rep, "wall s per frequency", (t1 - t0) / len(freqs), {k: round(float(v), 3) for k, v in ctx.info.items()}, flush=True)
 j = ctx.fields_fdem("h", "j", freqs[0], u[0], se_d)
 ix, iz = ctx.casing_currents(j, mp.casing_a, mp.casing_b, mp.casing_z)
-print("casing current just below the source (A):", complex(iz[-2].cpu()))
+kz = int(np.argmin(np.abs(m.vectorNz + 2.0 * csz)))          # node two cells below the casing top
+print("vertical casing current two cells below the casing top (A):", complex(iz[kz].cpu()))
 if do_cpu:
     from oracle.cyl_oracle import OracleCylMesh, OracleFDEM, paint_casing_in_halfspace
     t0 = time.perf_counter()
