@@ -281,3 +281,28 @@ def test_band_factor_paths_agree(nx, nz, monkeypatch):
         assert np.linalg.norm((Ah @ h - rhs) / dh) <= 1e-9 * np.linalg.norm(rhs / dh), (path, nx, nz)
     assert rel(out["cluster"][0], out["steps"][0]) < 1e-6
     assert rel(out["cluster"][1], out["steps"][1]) < 1e-6
+
+
+@pytest.mark.parametrize("nx,nth,nz", [(2, 1, 2), (1, 1, 3), (3, 4, 2), (5, 1, 1), (40, 1, 30)])
+def test_degenerate_inputs(nx, nth, nz):
+    """Edge cases: all-zero right-hand sides (alone and next to a non-zero column) give exact zeros, not NaN;
+    meshes of one or two cells per direction (2-D and 3-D) go through every driver and stay finite."""
+    from casingsimulations_b200 import _lib
+    ctx = _lib.Context(0)
+    hy = np.r_[2 * np.pi] if nth == 1 else np.ones(nth) * 2 * np.pi / nth
+    ctx.set_mesh(np.ones(nx) * 0.5, hy, np.ones(nz) * 0.5, -nz * 0.25)
+    ctx.set_model(ctx.to_device(0.1 * np.ones(ctx.nC)), ctx.to_device(4e-7 * np.pi * np.ones(ctx.nC)))
+    q = np.zeros((2, ctx.nC))
+    q[1, 0], q[1, -1] = 1.0, -1.0
+    phi = ctx.solve_dc(ctx.to_device(q)).cpu().numpy()
+    assert np.all(phi[0] == 0.0) and np.isfinite(phi).all()
+    assert ctx.nC == 1 or np.abs(phi[1]).max() > 0
+    se = np.zeros(ctx.nF)
+    u = ctx.solve_fdem("h", [1.0, 10.0], ctx.to_device(se)).cpu().numpy()
+    assert np.all(u == 0.0)
+    se[ctx.nFx + ctx.nFy] = 1.0
+    u = ctx.solve_fdem("h", [1.0], ctx.to_device(se)).cpu().numpy()
+    assert np.isfinite(u).all() and ctx.info["relres"] <= 1e-10
+    j = ctx.tdem_run("j", np.r_[1e-5, 1e-5, 1e-4], ctx.to_device(se)).cpu().numpy()
+    assert np.isfinite(j).all()
+    ctx.close()
