@@ -74,7 +74,7 @@ void band_release_stream(cudaStream_t st) {
 // xm[v][m][q] = sum_j x3d[v][map3d[q] + j*jstr[q]] * exp(-2 pi i j m / nth)
 template <typename TX, typename TM>
 __global__ void k_dft_gather(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int nth,
-                             const TX* __restrict__ x3d, long long n3d, TM* __restrict__ xm) {
+                             const TX* __restrict__ x3d, long long n3d, TM* __restrict__ xm, int jshift) {
     long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int v = blockIdx.y;
     if (q >= n2) return;
@@ -95,7 +95,9 @@ __global__ void k_dft_gather(const long long* __restrict__ map3d, const int* __r
     for (int m = 0; m < nth; ++m) {
         double re = 0.0, im = 0.0;
         for (int j = 0; j < nth; ++j) {
-            TX val = x3d[b + (long long)j * st];
+            // jshift: theta column that plays the role of column 0 (probing at a column other than 0)
+            int jj = j + jshift; if (jj >= nth) jj -= nth;
+            TX val = x3d[b + (long long)jj * st];
             double sn, cs_;
             sincospi(-2.0 * (double)((j * m) % nth) / (double)nth, &sn, &cs_);
             double vr = Sc<TX>::re(val), vi = Sc<TX>::im(val);
@@ -138,13 +140,13 @@ __global__ void k_dft_scatter(const long long* __restrict__ map3d, const int* __
     }
 }
 
-int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st) {
+int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st, int jshift) {
     dim3 g((unsigned)cdiv(bp.n2, TPB), nvec);
-    if (x_cplx && xm_cplx) k_dft_gather<cplx, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const cplx*)x3d, n3d, (cplx*)xm);
-    else if (!x_cplx && xm_cplx) k_dft_gather<double, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const double*)x3d, n3d, (cplx*)xm);
+    if (x_cplx && xm_cplx) k_dft_gather<cplx, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const cplx*)x3d, n3d, (cplx*)xm, jshift);
+    else if (!x_cplx && xm_cplx) k_dft_gather<double, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const double*)x3d, n3d, (cplx*)xm, jshift);
     else if (!x_cplx && !xm_cplx) {
         CS_CHECK(nth == 1, "real mode vectors need nth == 1");
-        k_dft_gather<double, double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const double*)x3d, n3d, (double*)xm);
+        k_dft_gather<double, double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const double*)x3d, n3d, (double*)xm, jshift);
     } else CS_CHECK(false, "complex vector into real mode storage");
     CS_CUDA(cudaGetLastError());
     return CS_OK;
@@ -167,12 +169,13 @@ int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d
 // (ones at j = 0 for every band index q == color mod (2p+1)); the DFT of the
 // response holds column q of every mode matrix at once.
 template <typename TX>
-__global__ void k_probe_fill(const long long* __restrict__ map3d, long long n2, int ncol, int color0, long long n3d, TX* __restrict__ x3d) {
-    // probing vector blockIdx.y carries colour color0 + blockIdx.y
+__global__ void k_probe_fill(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int ncol, int color0,
+                             long long n3d, int jprobe, TX* __restrict__ x3d) {
+    // probing vector blockIdx.y carries colour color0 + blockIdx.y; the ones sit in theta column jprobe
     long long q = color0 + blockIdx.y + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * ncol;
     if (q >= n2) return;
     long long b = map3d[q];
-    if (b >= 0) x3d[(size_t)blockIdx.y * n3d + b] = Sc<TX>::one();
+    if (b >= 0) x3d[(size_t)blockIdx.y * n3d + b + (long long)jprobe * jstr[q]] = Sc<TX>::one();
 }
 // nb probing vectors (colours color .. color + nb - 1) at once
 int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d, long long n3d, bool x_cplx, cudaStream_t st) {
@@ -180,8 +183,8 @@ int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d, long long 
     CS_CUDA(cudaMemsetAsync(x3d, 0, (size_t)nb * n3d * (x_cplx ? sizeof(cplx) : sizeof(double)), st));
     long long cnt = (bp.n2 + ncol - 1) / ncol;
     dim3 g((unsigned)cdiv(cnt, TPB), nb);
-    if (x_cplx) k_probe_fill<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.n2, ncol, color, n3d, (cplx*)x3d);
-    else k_probe_fill<double><<<g, TPB, 0, st>>>(bp.map3d, bp.n2, ncol, color, n3d, (double*)x3d);
+    if (x_cplx) k_probe_fill<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, ncol, color, n3d, bp.jprobe, (cplx*)x3d);
+    else k_probe_fill<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, ncol, color, n3d, bp.jprobe, (double*)x3d);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

@@ -68,6 +68,9 @@ struct BandPlan {
     // well conditioned and may be inverted explicitly; curl-curl systems with several components
     // per node have nearly singular pivot blocks and need the scalar LU
     bool scalar_field = false;
+    // theta column the band matrices are probed at: 0 for uniform azimuthal widths, otherwise the column whose
+    // width is closest to the mean (the circulant preconditioner then models an "average" column)
+    int jprobe = 0;
     size_t band_elems() const { return (size_t)n2 * ldab; }
 };
 
@@ -75,7 +78,7 @@ struct BandPlan {
 int band_choose_nb(int p);
 void band_release_stream(cudaStream_t st);   // frees the band scratch buffers keyed by this stream
 int band_factor_launches(const BandPlan& bp, bool lu_cplx);
-int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm /*[nvec][nmodes][n2]*/, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
+int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm /*[nvec][nmodes][n2]*/, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st, int jshift = 0);
 int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
 int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]*/, long long n3d, bool x_cplx, cudaStream_t st);
 int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym /*[nb][nmodes][n2]*/, cudaStream_t st);
