@@ -1242,7 +1242,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
         for (int s = 0; s < ns; ++s) { bar_sync0(); issue(true, s + nst - 1); }
         bar_sync0();                                          // forward done: every ring slot is free again
         for (int q = 0; q < nst - 1; ++q) issue(false, q);
-        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(false, s + nst - 1); }
+        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(false, s + nst - 1); bar_sync0(); }   // (two barriers per backward step)
         return;
     }
 
@@ -1333,23 +1333,32 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             slot = (slot + 1 == nst) ? 0 : slot + 1;
             bar_sync0();
             prefetch(false, s + nst - 1);
-            TV xr = zero;
+            // the block solution x1 = inv(U11) w (or inv(D) w) is computed by warp 0 alone and handed over through
+            // shared memory + one more barrier: done redundantly by every warp (as the forward pass does with its
+            // cheaper y1) the 16 x 16 block costs 24 LDS.128 per warp, ~1 500 LSU cycles per step for 16 warps
+            TL lreg[NB / TPR];
 #pragma unroll
-            for (int i = 0; i < NB / HALVES; ++i) {
-                int c = HALVES * i + half;
-                if ((diag_full || c >= r16) && c < nbe && r16 < nbe) fmacc(xr, cur[(Ra + r16) + c * ldd], win[(t + c) & wm]);
+            for (int i = 0; i < NB / TPR; ++i) {
+                int c = uq + TPR * i;
+                lreg[i] = (urow < Ra && c < nbe) ? cur[urow + c * ldd] : Sc<TL>::zero();
             }
-            if (HALVES == 2) xr += shfl_xor_t<TV>(xr, 16);
-            if (lane < NB) yw[warp][lane] = xr;
-            __syncwarp();
-            if (warp == 0 && lane < nbe) b[t + lane] = xr;
-            TV acc = zero;
-            if (urow < Ra) {
+            if (warp == 0) {
+                TV xr = zero;
 #pragma unroll
-                for (int i = 0; i < NB / TPR; ++i) {
-                    int c = uq + TPR * i;
-                    if (c < nbe) fmacc(acc, cur[urow + c * ldd], yw[warp][c]);
+                for (int i = 0; i < NB / HALVES; ++i) {
+                    int c = HALVES * i + half;
+                    if ((diag_full || c >= r16) && c < nbe && r16 < nbe) fmacc(xr, cur[(Ra + r16) + c * ldd], win[(t + c) & wm]);
                 }
+                if (HALVES == 2) xr += shfl_xor_t<TV>(xr, 16);
+                if (lane < NB) yw[0][lane] = xr;
+                if (lane < nbe) b[t + lane] = xr;
+            }
+            bar_sync0();
+            TV acc = zero;
+#pragma unroll
+            for (int i = 0; i < NB / TPR; ++i) {
+                int c = uq + TPR * i;
+                fmacc(acc, lreg[i], yw[0][c]);
             }
             if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
             if (TPR >= 4) acc += shfl_xor_t<TV>(acc, 2);
