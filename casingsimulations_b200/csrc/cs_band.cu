@@ -1239,7 +1239,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             }
         };
         for (int q = 0; q < nst - 1; ++q) issue(true, q);
-        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(true, s + nst - 1); }
+        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(true, s + nst - 1); if (!diag_full) bar_sync0(); }
         bar_sync0();                                          // forward done: every ring slot is free again
         for (int q = 0; q < nst - 1; ++q) issue(false, q);
         for (int s = 0; s < ns; ++s) { bar_sync0(); issue(false, s + nst - 1); bar_sync0(); }   // (two barriers per backward step)
@@ -1287,27 +1287,47 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             slot = (slot + 1 == nst) ? 0 : slot + 1;
             bar_sync0();                                      // ... and is visible; window of step s-1 complete
             prefetch(true, s + nst - 1);                      // refills the slot step s-1 just released
-            // every warp computes y1 = inv(L11) b1 for itself: lane (r, half) sums the columns of its parity
-            // (block LDU factors have a unit block diagonal in L: nothing to apply)
-            TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
-            if (!diag_full) {
-#pragma unroll
-                for (int i = 0; i < NB / HALVES; ++i) {
-                    int c = HALVES * i + half;
-                    if (c < r16) fmacc(yr, cur[r16 + c * ldd], win[(t + c) & wm]);
-                }
-            }
-            if (HALVES == 2) yr += shfl_xor_t<TV>(yr, 16);
-            if (lane < NB) yw[warp][lane] = yr;
-            __syncwarp();
-            if (warp == 0 && lane < nbe) b[t + lane] = yr;
-            // window update: row (nbe + urow) of the staged block, TPR threads per row
+            // block LDU factors (diag_full) have a unit block diagonal in L: y1 is the window itself and every warp
+            // reads it for itself.  Scalar-LU factors need y1 = inv(L11) b1: warp 0 computes it once and hands it over
+            // through shared memory + one more barrier (see the backward pass).
+            const TL* crow = cur + nbe + urow;
             TV acc = zero;
-            if (urow < R) {
+            if (diag_full) {
+                TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
+                if (HALVES == 2) yr += shfl_xor_t<TV>(yr, 16);
+                if (lane < NB) yw[warp][lane] = yr;
+                __syncwarp();
+                if (warp == 0 && lane < nbe) b[t + lane] = yr;
+                if (urow < R) {
+#pragma unroll
+                    for (int i = 0; i < NB / TPR; ++i) {
+                        int c = uq + TPR * i;
+                        if (c < nbe) fmacc(acc, crow[c * ldd], yw[warp][c]);
+                    }
+                }
+            } else {
+                TL lreg[NB / TPR];
 #pragma unroll
                 for (int i = 0; i < NB / TPR; ++i) {
                     int c = uq + TPR * i;
-                    if (c < nbe) fmacc(acc, cur[(nbe + urow) + c * ldd], yw[warp][c]);
+                    lreg[i] = (urow < R && c < nbe) ? crow[c * ldd] : Sc<TL>::zero();
+                }
+                if (warp == 0) {
+                    TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
+#pragma unroll
+                    for (int i = 0; i < NB / HALVES; ++i) {
+                        int c = HALVES * i + half;
+                        if (c < r16) fmacc(yr, cur[r16 + c * ldd], win[(t + c) & wm]);
+                    }
+                    if (HALVES == 2) yr += shfl_xor_t<TV>(yr, 16);
+                    if (lane < NB) yw[0][lane] = yr;
+                    if (lane < nbe) b[t + lane] = yr;
+                }
+                bar_sync0();
+#pragma unroll
+                for (int i = 0; i < NB / TPR; ++i) {
+                    int c = uq + TPR * i;
+                    fmacc(acc, lreg[i], yw[0][c]);
                 }
             }
             if (TPR >= 2) acc += shfl_xor_t<TV>(acc, 1);
