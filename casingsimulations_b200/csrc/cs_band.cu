@@ -1287,22 +1287,18 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
             slot = (slot + 1 == nst) ? 0 : slot + 1;
             bar_sync0();                                      // ... and is visible; window of step s-1 complete
             prefetch(true, s + nst - 1);                      // refills the slot step s-1 just released
-            // block LDU factors (diag_full) have a unit block diagonal in L: y1 is the window itself and every warp
-            // reads it for itself.  Scalar-LU factors need y1 = inv(L11) b1: warp 0 computes it once and hands it over
+            // block LDU factors (diag_full) have a unit block diagonal in L: y1 is the window itself.  Scalar-LU factors need y1 = inv(L11) b1: warp 0 computes it once and hands it over
             // through shared memory + one more barrier (see the backward pass).
             const TL* crow = cur + nbe + urow;
             TV acc = zero;
             if (diag_full) {
-                TV yr = (half == 0) ? win[(t + r16) & wm] : zero;
-                if (HALVES == 2) yr += shfl_xor_t<TV>(yr, 16);
-                if (lane < NB) yw[warp][lane] = yr;
-                __syncwarp();
-                if (warp == 0 && lane < nbe) b[t + lane] = yr;
+                // y1 is the (finished) window itself: read it in place
+                if (warp == 0 && lane < nbe) b[t + lane] = win[(t + lane) & wm];
                 if (urow < R) {
 #pragma unroll
                     for (int i = 0; i < NB / TPR; ++i) {
                         int c = uq + TPR * i;
-                        if (c < nbe) fmacc(acc, crow[c * ldd], yw[warp][c]);
+                        if (c < nbe) fmacc(acc, crow[c * ldd], win[(t + c) & wm]);
                     }
                 }
             } else {
