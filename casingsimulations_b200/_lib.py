@@ -307,7 +307,11 @@ class Context(object):
     def _unary(self, fn, x, nin, nout):
         assert x.numel() == nin
         y = self.empty(nout, x.is_complex())
-        check(fn(self.h, _tptr(x.contiguous()), _tptr(y), int(x.is_complex())))
+        x = x.contiguous()
+        self._enter()
+        rc = fn(self.h, _tptr(x), _tptr(y), int(x.is_complex()))
+        self._exit()
+        check(rc)
         return y
 
     def curl(self, xE):

@@ -49,6 +49,10 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     Pool* pool = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }          // early returns (CS_TRY / CS_CUDA) hand local buffers back to the pool
     int ensure(size_t need) {
         if (need <= bytes) return CS_OK;
         release();
@@ -79,7 +83,7 @@ struct cs_op {
     long long* csr_indptr = nullptr; int* csr_indices = nullptr; void* csr_vals = nullptr; long long csr_nnz = 0;
     BandPlan bp;
     DevBuf kband;                 // storage behind bp.Kband (pooled)
-    DevBuf bw1, bw2, bmass, bmap, bjstr, bmdiag;   // pooled storage behind w1 / w2 / mass / band maps
+    DevBuf bw1, bw2, bmass, bmap, bjstr, bmdiag, bhs;   // pooled storage behind w1 / w2 / mass / band maps
     DevBuf LU, wts;               // wts: [nshift][n] = 1/|diag A(s)|, the norm of the convergence tests
     bool lu_cplx = false;
     std::vector<zc> shifts;
@@ -102,13 +106,15 @@ struct cs_ctx {
     std::vector<std::pair<std::vector<unsigned long long>, cudaGraphExec_t>> probe_graphs;
     double* pin = nullptr;         // pinned host scratch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long mesh_gen = 0;   // bumped by cs_mesh_set: part of the probe-graph cache key
+    int next_csr_key = -1;             // keys of assembled-matrix operators in `ops`
 };
 
 static void op_free(cs_op* op) {
     if (!op) return;
     op->bw1.release(); op->bw2.release(); op->bmass.release();
     cudaFree(op->csr_indptr); cudaFree(op->csr_indices); cudaFree(op->csr_vals);
-    op->bmap.release(); op->bjstr.release(); op->bmdiag.release();
+    op->bmap.release(); op->bjstr.release(); op->bmdiag.release(); op->bhs.release();
     op->kband.release(); op->bp.Kband = nullptr;
     op->LU.release(); op->wts.release();
     delete op;
@@ -234,6 +240,7 @@ static int build_plan(cs_op* op) {
     int nx = m.nx, nth = m.nth, nz = m.nz;
     std::vector<long long> map;
     std::vector<int> js;
+    std::vector<signed char> hsv;      // theta stagger in half cells: Ey edges sit half a cell after Ex / Ez, Fy faces half a cell before Fx / Fz
     long long L;
     if (op->family == 0) {
         L = nx; bp.n2 = (long long)nx * nz; bp.p = nx;
@@ -245,12 +252,12 @@ static int build_plan(cs_op* op) {
         for (int k = 0; k <= nz; ++k) for (int i = 0; i < nx; ++i) map[k * L + i] = i + (long long)nx * k;
     } else if (op->family == 1) {
         L = 3LL * nx + 1; bp.n2 = L * (nz + 1); bp.p = (int)L + 2;
-        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx); hsv.assign(bp.n2, 0);
         for (int k = 0; k <= nz; ++k) {
             for (int i = 0; i < nx; ++i) {
                 long long q = k * L + 3 * i;
                 map[q] = i + m.nxy * k;
-                map[q + 1] = m.nEx + i + m.nxy * k;
+                map[q + 1] = m.nEx + i + m.nxy * k; hsv[q + 1] = 1;
                 if (k < nz) map[q + 2] = m.nEx + m.nEy + m.ez(i, 0, k);
             }
             if (k < nz) { long long q = k * L + 3 * nx; map[q] = m.nEx + m.nEy + m.ezaxis(k); js[q] = 0; }
@@ -265,11 +272,11 @@ static int build_plan(cs_op* op) {
         }
     } else {
         L = 3LL * nx; bp.n2 = L * (nz + 1); bp.p = (int)L + 3;
-        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx); hsv.assign(bp.n2, 0);
         for (int k = 0; k <= nz; ++k) for (int i = 0; i < nx; ++i) {
             long long q = k * L + 3 * i;
             map[q] = m.nFx + m.nFy + i + m.nxy * k;           // Fz
-            if (k < nz) { map[q + 1] = i + m.nxy * k; map[q + 2] = m.nFx + i + m.nxy * k; }
+            if (k < nz) { map[q + 1] = i + m.nxy * k; map[q + 2] = m.nFx + i + m.nxy * k; hsv[q + 2] = -1; }
         }
     }
     if (bp.p > bp.n2 - 1) bp.p = (int)std::max(1LL, bp.n2 - 1);
@@ -285,15 +292,20 @@ static int build_plan(cs_op* op) {
     bp.nb = band_choose_nb(bp.p);
     bp.pw = bp.p + bp.nb;
     bp.ldab = 2 * bp.pw + 1;
-    bp.nmodes = nth;
-    bp.cplx_band = (nth > 1) || op->csr_cplx;
-    op->bmap.pool = op->bjstr.pool = op->bmdiag.pool = &c->pool;
+    bp.nth = nth;
+    bp.thin_probe = (op->family != 2);
+    bp.nmodes = (nth > 1) ? nth / 2 + 1 : 1;          // modes m and nth - m share one (rotated, real) matrix
+    bp.cplx_band = op->csr_cplx;                      // the rotated mode matrices of a real operator are real
+    hsv.resize(bp.n2, 0);
+    op->bmap.pool = op->bjstr.pool = op->bmdiag.pool = op->bhs.pool = &c->pool;
     CS_TRY(op->bmap.ensure(bp.n2 * sizeof(long long)));
     CS_TRY(op->bjstr.ensure(bp.n2 * sizeof(int)));
     CS_TRY(op->bmdiag.ensure(bp.n2 * sizeof(double)));
-    bp.map3d = (long long*)op->bmap.p; bp.jstr = (int*)op->bjstr.p; bp.mdiag = (double*)op->bmdiag.p;
+    CS_TRY(op->bhs.ensure(bp.n2));
+    bp.map3d = (long long*)op->bmap.p; bp.jstr = (int*)op->bjstr.p; bp.mdiag = (double*)op->bmdiag.p; bp.hs = (signed char*)op->bhs.p;
     CS_CUDA(cudaMemcpyAsync(bp.map3d, map.data(), bp.n2 * sizeof(long long), cudaMemcpyHostToDevice, c->st));
     CS_CUDA(cudaMemcpyAsync(bp.jstr, js.data(), bp.n2 * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CS_CUDA(cudaMemcpyAsync(bp.hs, hsv.data(), bp.n2, cudaMemcpyHostToDevice, c->st));
     CS_CUDA(cudaStreamSynchronize(c->st));
     k_gather_diag<<<cdiv(bp.n2, 256), 256, 0, c->st>>>(bp.map3d, bp.jstr, bp.jprobe, op->mass, bp.n2, bp.mdiag);
     CS_CUDA(cudaGetLastError());
@@ -316,7 +328,7 @@ static int probe_plan(cs_op* op) {
     pb = std::min(pb, ncol);
     CS_TRY(c->tmp1.ensure((size_t)pb * op->n * esz(cv)));
     CS_TRY(c->tmp2.ensure((size_t)pb * op->n * esz(cv)));
-    CS_TRY(c->modes.ensure((size_t)pb * bp.nmodes * bp.n2 * esz(cv)));
+    CS_TRY(c->modes.ensure((size_t)pb * bp.nmodes * bp.n2 * sizeof(cplx)));
     CS_TRY(c->scal.ensure(4096));
     CS_CUDA(cudaMemsetAsync(c->scal.p, 0, 4096, c->st));     // shift 0 for every probing vector
     // ~4 * (2p+1) tiny launches: replay them as one cached CUDA graph (keyed by every pointer
@@ -326,7 +338,7 @@ static int probe_plan(cs_op* op) {
         (unsigned long long)c->scal.p, (unsigned long long)bp.Kband, (unsigned long long)bp.map3d, (unsigned long long)bp.jstr,
         (unsigned long long)op->w1, (unsigned long long)op->w2, (unsigned long long)op->csr_vals, (unsigned long long)op->kind,
         (unsigned long long)bp.n2, (unsigned long long)bp.p, (unsigned long long)bp.nmodes, (unsigned long long)op->n,
-        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables, (unsigned long long)pb, (unsigned long long)bp.jprobe};
+        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables, (unsigned long long)pb, (unsigned long long)bp.jprobe, (unsigned long long)bp.hs, c->mesh_gen};
     g_launches += 4LL * ((ncol + pb - 1) / pb);
     for (auto& g : c->probe_graphs)
         if (g.first == key) { CS_CUDA(cudaGraphLaunch(g.second, c->st)); return CS_OK; }
@@ -335,8 +347,8 @@ static int probe_plan(cs_op* op) {
             int nb = std::min(pb, ncol - col);
             CS_TRY(band_probe_fill(bp, col, nb, c->tmp1.p, op->n, cv, c->st));
             CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, nb, cv));
-            CS_TRY(band_dft_gather(bp, c->tmp2.p, cv, c->modes.p, cv, bp.nmodes, op->n, nb, c->st, bp.jprobe));
-            CS_TRY(band_probe_store(bp, col, nb, c->modes.p, c->st));
+            CS_TRY(band_probe_gather(bp, c->tmp2.p, cv, c->modes.p, op->n, nb, c->st));
+            CS_TRY(band_probe_store(bp, col, nb, c->modes.p, c->tmp2.p, cv, op->n, c->st));
         }
         return CS_OK;
     };
@@ -446,8 +458,7 @@ extern "C" int cs_op_from_csr(cs_ctx* c, int family, long long n, long long nnz,
     if (cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("sync failed in cs_op_from_csr"); op_free(op); return CS_ERR; }
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     op->ms_assemble = ms;
-    static int next_key = -1;
-    c->ops[next_key--] = op;
+    c->ops[c->next_csr_key--] = op;
     *out = op;
     return CS_OK;
 }
@@ -544,9 +555,9 @@ struct Krylov {
     int apply(const void* x, void* y) { n_apply++; return op_apply_dev(op, s_d, x, y, nvec, cv); }
     int precond(const void* x, void* y) {
         BandPlan& bp = op->bp;
-        CS_TRY(band_dft_gather(bp, x, cv, c->modes.p, op->lu_cplx, bp.nmodes, n, nvec, c->st));
+        CS_TRY(band_dft_gather(bp, x, cv, c->modes.p, op->lu_cplx, n, nvec, c->st));
         CS_TRY(band_solve(bp, op->LU.p, op->lu_cplx, c->modes.p, op->lu_cplx, nvec, sov_d, c->st));
-        CS_TRY(band_dft_scatter(bp, c->modes.p, op->lu_cplx, y, cv, bp.nmodes, n, nvec, c->st));
+        CS_TRY(band_dft_scatter(bp, c->modes.p, op->lu_cplx, y, cv, n, nvec, c->st));
         g_launches += 3;
         return CS_OK;
     }
@@ -692,7 +703,8 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
                         double rtol, int maxit, double* info) {
     cs_ctx* c = op->ctx;
     CS_CHECK(op->LU.p && !op->shifts.empty(), "cs_op_factor must be called before cs_op_solve");
-    CS_CHECK(cv || !(op->lu_cplx && !op->bp.cplx_band), "complex shift needs complex vectors");
+    CS_CHECK(cv == op->lu_cplx, cv ? "complex vectors need factors of a complex shift (cs_op_factor(..., complex_shift = 1))"
+                                        : "complex factors (complex shift or matrix) need complex vectors");
     CS_CHECK(nvec >= 1 && nvec <= 1024, "nvec out of range");
     long long n = op->n;
     Krylov K;
@@ -707,7 +719,7 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
     K.a_d = K.s_d + 2 * nvec;
     K.dots_d = K.a_d + 64 * 4 * nvec;
     K.sov_d = (int*)(K.dots_d + 2 * nvec * 260);
-    CS_TRY(c->modes.ensure((size_t)nvec * op->bp.nmodes * op->bp.n2 * esz(op->lu_cplx)));
+    CS_TRY(c->modes.ensure((size_t)nvec * op->bp.nmv(op->lu_cplx) * op->bp.n2 * esz(op->lu_cplx)));
     // per-vector shifts
     std::vector<int> sov(nvec, 0);
     for (int v = 0; v < nvec; ++v) { sov[v] = sov_h ? sov_h[v] : 0; CS_CHECK(sov[v] >= 0 && sov[v] < (int)op->shifts.size(), "shift index out of range"); }
@@ -965,6 +977,10 @@ extern "C" int cs_mesh_set(cs_ctx* c, int nx, int nth, int nz, const double* hx,
     double sth = 0; for (int j = 0; j < nth; ++j) sth += hth[j];
     CS_CHECK(std::fabs(sth - 2 * M_PI) < 1e-6, "hy must sum to 2*pi (mesh.py:408-411)");
     ctx_drop_ops(c);
+    // cached probing graphs bake the by-value mesh tables (axis weights included) into their launches
+    for (auto& g : c->probe_graphs) cudaGraphExecDestroy(g.second);
+    c->probe_graphs.clear();
+    c->mesh_gen++;
     cudaFree(c->tables); cudaFree(c->sigma); cudaFree(c->mu);
     c->tables = c->sigma = c->mu = nullptr; c->has_model = false;
     c->hx.assign(hx, hx + nx); c->hth.assign(hth, hth + nth); c->hz.assign(hz, hz + nz);
@@ -1082,7 +1098,7 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
     // how many frequencies fit at once (driver queries only when the cached buffers are too small:
     // cudaMemGetInfo / cudaMalloc / cudaFree serialise against concurrent nvidia-smi polling)
     size_t per = (size_t)op->bp.nmodes * op->bp.band_elems() * sizeof(cplx);
-    size_t vecs = (size_t)(8 + 2) * n * sizeof(cplx) + (size_t)op->bp.nmodes * op->bp.n2 * sizeof(cplx);
+    size_t vecs = (size_t)(8 + 2) * n * sizeof(cplx) + (size_t)op->bp.nth * op->bp.n2 * sizeof(cplx);
     long long chunk = std::min(nfreq, 256);
     if ((size_t)chunk * per > op->LU.bytes + c->pool.total()) {
         size_t fr = 0, tot = 0;

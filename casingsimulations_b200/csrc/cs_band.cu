@@ -71,94 +71,210 @@ void band_release_stream(cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ DFT -----
-// xm[v][m][q] = sum_j x3d[v][map3d[q] + j*jstr[q]] * exp(-2 pi i j m / nth)
+// Rotated theta-mode basis.  For mode m (phi = 2 pi m / nth) the mode matrix K_m of a theta-invariant operator is
+// Hermitian; the only complex entries couple the component that is staggered by half a cell in theta (Ey against
+// Ex / Ez, Fy against Fx / Fz) to the others, with phase (exp(+-i phi) - 1) = +-2i sin(phi/2) exp(+-i phi/2).
+// With T_m = diag(1 | i exp(i hs phi / 2)) (hs = +-1: the stagger in half cells)
+//     K''_m = T_m^* K_m T_m   is REAL symmetric   and   K''_{nth-m} = K''_m
+// (checked in numpy: tools/proto/mode_similarity.py), so only modes 0 .. nth/2 are stored and factored, in real
+// arithmetic when the shift is real (DC, TDEM) -- half the systems, half the bytes per entry.  The rotation costs
+// nothing: it turns the DFT twiddle exp(-2 pi i j m / nth) into (-i) exp(-i pi m (2 j + hs) / nth).
+//   gather : xm[v][m][q]  = conj(T_m[q]) sum_j x3d[v][map3d[q] + j*jstr[q]] exp(-2 pi i j m / nth)
+//   scatter: x3d[..j..]   = (1/nth) sum_m T_m[q] xm[v][m][q] exp(+2 pi i j m / nth)
+// mode_sel 0: all nth modes, complex (complex factors; mode m is solved with the factor of min(m, nth - m));
+//          1: modes 0 .. nmodes-1, complex (probing);
+//          2: modes 0 .. nmodes-1 of a REAL 3-D vector split into (Re, Im) real vectors (real factors; the other
+//             modes are complex conjugates in the rotated basis as well).
+// A block handles DFT_QB unknowns x all modes: the theta line of every unknown is staged once in shared memory,
+// the 2 nth twiddles exp(-+ i pi t / nth) are tabulated per block (no sincospi in the inner loop).
+static const int DFT_QB = 32, DFT_MY = 8;
+__device__ __forceinline__ cplx to_c(double v) { return mk(v, 0.0); }
+__device__ __forceinline__ cplx to_c(cplx v) { return v; }
+template <typename T> __device__ __forceinline__ T from_c(cplx v);
+template <> __device__ __forceinline__ double from_c<double>(cplx v) { return v.x; }
+template <> __device__ __forceinline__ cplx from_c<cplx>(cplx v) { return v; }
+
 template <typename TX, typename TM>
-__global__ void k_dft_gather(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int nth,
-                             const TX* __restrict__ x3d, long long n3d, TM* __restrict__ xm, int jshift) {
-    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int v = blockIdx.y;
-    if (q >= n2) return;
-    x3d += v * n3d;
-    xm += (long long)v * nth * n2;
-    long long b = map3d[q];
-    int st = jstr[q];
-    if (b < 0) {
-        for (int m = 0; m < nth; ++m) xm[m * n2 + q] = Sc<TM>::zero();
-        return;
+__global__ void __launch_bounds__(DFT_QB * DFT_MY)
+k_dft_gather(const long long* __restrict__ map3d, const int* __restrict__ jstr, const signed char* __restrict__ hs,
+             long long n2, int nth, int nfac, int mode_sel, const TX* __restrict__ x3d, long long n3d,
+             TM* __restrict__ xm, int jshift, int thin) {
+    extern __shared__ __align__(16) unsigned char dft_sm[];
+    cplx* tw = reinterpret_cast<cplx*>(dft_sm);        // [2 nth]: exp(-i pi t / nth)
+    cplx* xs = tw + 2 * nth;                           // [nj][DFT_QB]
+    const int tq = threadIdx.x, ty = threadIdx.y;
+    const int nj = thin ? 3 : nth;
+    const int n2t = 2 * nth;
+    for (int t = ty * DFT_QB + tq; t < n2t; t += DFT_QB * DFT_MY) {
+        double sn, cs_;
+        sincospi(-(double)t / (double)nth, &sn, &cs_);
+        tw[t] = mk(cs_, sn);
     }
-    if (st == 0 || nth == 1) {
-        TX val = x3d[b];
-        xm[q] = Sc<TM>::from(Sc<TX>::re(val), Sc<TX>::im(val));
-        for (int m = 1; m < nth; ++m) xm[m * n2 + q] = Sc<TM>::zero();
-        return;
-    }
-    for (int m = 0; m < nth; ++m) {
-        double re = 0.0, im = 0.0;
-        for (int j = 0; j < nth; ++j) {
-            // jshift: theta column that plays the role of column 0 (probing at a column other than 0)
-            int jj = j + jshift; if (jj >= nth) jj -= nth;
-            TX val = x3d[b + (long long)jj * st];
-            double sn, cs_;
-            sincospi(-2.0 * (double)((j * m) % nth) / (double)nth, &sn, &cs_);
-            double vr = Sc<TX>::re(val), vi = Sc<TX>::im(val);
-            re += vr * cs_ - vi * sn;
-            im += vr * sn + vi * cs_;
+    const long long q = blockIdx.x * (long long)DFT_QB + tq;
+    const int v = blockIdx.y;
+    x3d += (size_t)v * n3d;
+    const int nmv = mode_sel == 0 ? nth : (mode_sel == 1 ? nfac : 2 * nfac);
+    xm += (size_t)v * nmv * n2;
+    long long b = -1; int st = 0, h2 = 0;
+    if (q < n2) { b = map3d[q]; st = jstr[q]; h2 = hs[q]; }
+    for (int jj = ty; jj < nj; jj += DFT_MY) {
+        cplx val = mk(0.0, 0.0);
+        if (b >= 0 && st != 0) {
+            // jshift: theta column that plays the role of column 0; thin: only columns jshift-1 .. jshift+1 carry data
+            int col = (jshift + jj - (thin ? 1 : 0)) % nth;
+            if (col < 0) col += nth;
+            val = to_c(x3d[b + (long long)col * st]);
         }
-        xm[m * n2 + q] = Sc<TM>::from(re, im);
+        xs[jj * DFT_QB + tq] = val;
+    }
+    __syncthreads();
+    if (q >= n2) return;
+    const int nm = mode_sel == 0 ? nth : nfac;
+    for (int m = ty; m < nm; m += DFT_MY) {
+        cplx acc = mk(0.0, 0.0);
+        if (b >= 0) {
+            if (st == 0) { if (m == 0) acc = to_c(x3d[b]); }      // the shared axis unknown lives in mode 0 only
+            else {
+                // entry jj sits at theta position p = jj (thin: jj - 1) + hs/2: twiddle index m (2 p + hs) mod 2 nth
+                int idx = ((m * (h2 - (thin ? 2 : 0))) % n2t + n2t) % n2t;
+                const int stp = (2 * m) % n2t;
+                for (int jj = 0; jj < nj; ++jj) {
+                    fmacc(acc, xs[jj * DFT_QB + tq], tw[idx]);
+                    idx += stp; if (idx >= n2t) idx -= n2t;
+                }
+                if (h2 != 0) acc = mk(acc.y, -acc.x);              // conj(T): times -i
+            }
+        }
+        if constexpr (sizeof(TM) == sizeof(cplx)) xm[(size_t)m * n2 + q] = acc;
+        else { xm[(size_t)(2 * m) * n2 + q] = acc.x; xm[(size_t)(2 * m + 1) * n2 + q] = acc.y; }
     }
 }
 
-// x3d[v][map3d[q] + j*jstr[q]] = (1/nth) sum_m xm[v][m][q] exp(+2 pi i j m / nth)
 template <typename TX, typename TM>
-__global__ void k_dft_scatter(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int nth,
-                              const TM* __restrict__ xm, TX* __restrict__ x3d, long long n3d) {
-    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int v = blockIdx.y;
-    if (q >= n2) return;
-    x3d += v * n3d;
-    xm += (long long)v * nth * n2;
-    long long b = map3d[q];
-    int st = jstr[q];
-    if (b < 0) return;
-    if (st == 0 || nth == 1) {
-        TM val = xm[q];
-        x3d[b] = Sc<TX>::from(Sc<TM>::re(val), Sc<TM>::im(val));
+__global__ void __launch_bounds__(DFT_QB * DFT_MY)
+k_dft_scatter(const long long* __restrict__ map3d, const int* __restrict__ jstr, const signed char* __restrict__ hs,
+              long long n2, int nth, int nfac, int mode_sel, const TM* __restrict__ xm, TX* __restrict__ x3d, long long n3d) {
+    extern __shared__ __align__(16) unsigned char dft_sm[];
+    cplx* tw = reinterpret_cast<cplx*>(dft_sm);        // [2 nth]: exp(+i pi t / nth)
+    cplx* ys = tw + 2 * nth;                           // [nm][DFT_QB]
+    const int tq = threadIdx.x, ty = threadIdx.y;
+    const int n2t = 2 * nth;
+    for (int t = ty * DFT_QB + tq; t < n2t; t += DFT_QB * DFT_MY) {
+        double sn, cs_;
+        sincospi((double)t / (double)nth, &sn, &cs_);
+        tw[t] = mk(cs_, sn);
+    }
+    const long long q = blockIdx.x * (long long)DFT_QB + tq;
+    const int v = blockIdx.y;
+    x3d += (size_t)v * n3d;
+    const int nm = mode_sel == 0 ? nth : nfac;
+    const int nmv = mode_sel == 0 ? nth : 2 * nfac;
+    xm += (size_t)v * nmv * n2;
+    long long b = -1; int st = 0, h2 = 0;
+    if (q < n2) { b = map3d[q]; st = jstr[q]; h2 = hs[q]; }
+    for (int m = ty; m < nm; m += DFT_MY) {
+        cplx val = mk(0.0, 0.0);
+        if (b >= 0) {
+            if constexpr (sizeof(TM) == sizeof(cplx)) val = to_c(xm[(size_t)m * n2 + q]);
+            else {
+                // real factors: (Re, Im) of modes 0 .. nth/2; modes m and nth - m are conjugates, so the sum over all
+                // modes is 2 Re(sum over the stored ones) with weight 1/2 for the self-conjugate modes 0 and nth/2
+                double wgt = (m == 0 || 2 * m == nth) ? 1.0 : 2.0;
+                val = mk(wgt * (double)xm[(size_t)(2 * m) * n2 + q], wgt * (double)xm[(size_t)(2 * m + 1) * n2 + q]);
+            }
+        }
+        ys[m * DFT_QB + tq] = val;
+    }
+    __syncthreads();
+    if (q >= n2 || b < 0) return;
+    const double inv = 1.0 / (double)nth;
+    if (st == 0) {
+        if (ty == 0) {
+            cplx a = ys[tq];                                       // mode 0, T = 1 (weight 1 above)
+            x3d[b] = from_c<TX>(a);
+        }
         return;
     }
-    double inv = 1.0 / (double)nth;
-    for (int j = 0; j < nth; ++j) {
-        double re = 0.0, im = 0.0;
-        for (int m = 0; m < nth; ++m) {
-            TM val = xm[m * n2 + q];
-            double sn, cs_;
-            sincospi(2.0 * (double)((j * m) % nth) / (double)nth, &sn, &cs_);
-            double vr = Sc<TM>::re(val), vi = Sc<TM>::im(val);
-            re += vr * cs_ - vi * sn;
-            im += vr * sn + vi * cs_;
+    for (int j = ty; j < nth; j += DFT_MY) {
+        cplx acc = mk(0.0, 0.0);
+        const int stp = ((2 * j + h2) % n2t + n2t) % n2t;
+        int idx = 0;
+        for (int m = 0; m < nm; ++m) {
+            fmacc(acc, ys[m * DFT_QB + tq], tw[idx]);
+            idx += stp; if (idx >= n2t) idx -= n2t;
         }
-        x3d[b + (long long)j * st] = Sc<TX>::from(re * inv, im * inv);
+        if (h2 != 0) acc = mk(-acc.y, acc.x);                      // T: times i
+        x3d[b + (long long)j * st] = from_c<TX>(mk(acc.x * inv, acc.y * inv));   // (real factors: from_c<double> takes Re)
     }
 }
 
-int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st, int jshift) {
-    dim3 g((unsigned)cdiv(bp.n2, TPB), nvec);
-    if (x_cplx && xm_cplx) k_dft_gather<cplx, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const cplx*)x3d, n3d, (cplx*)xm, jshift);
-    else if (!x_cplx && xm_cplx) k_dft_gather<double, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const double*)x3d, n3d, (cplx*)xm, jshift);
-    else if (!x_cplx && !xm_cplx) {
-        CS_CHECK(nth == 1, "real mode vectors need nth == 1");
-        k_dft_gather<double, double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const double*)x3d, n3d, (double*)xm, jshift);
-    } else CS_CHECK(false, "complex vector into real mode storage");
+// cylindrically symmetric mesh: one mode, no rotation -- a gather / scatter through map3d
+template <typename TX, typename TM>
+__global__ void k_mode_copy(const long long* __restrict__ map3d, long long n2, TX* __restrict__ x3d, long long n3d, TM* __restrict__ xm, int to_modes) {
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= n2) return;
+    x3d += (size_t)blockIdx.y * n3d;
+    xm += (size_t)blockIdx.y * n2;
+    long long b = map3d[q];
+    if (to_modes) xm[q] = (b >= 0) ? from_c<TM>(to_c(x3d[b])) : Sc<TM>::zero();
+    else if (b >= 0) x3d[b] = from_c<TX>(to_c(xm[q]));
+}
+
+static size_t dft_smem(int nth, int rows) { return (size_t)(2 * nth + rows * DFT_QB) * sizeof(cplx); }
+template <typename K> static int dft_smem_attr(K kern, size_t sm) {
+    if (sm > 48 * 1024) CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    return CS_OK;
+}
+
+int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm, bool xm_cplx, long long n3d, int nvec, cudaStream_t st) {
+    CS_CHECK(!(x_cplx && !xm_cplx), "complex vectors need complex factors (complex shift)");
+    if (bp.nth == 1) {
+        dim3 g((unsigned)cdiv(bp.n2, 256), nvec);
+        if (x_cplx) k_mode_copy<cplx, cplx><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (cplx*)x3d, n3d, (cplx*)xm, 1);
+        else if (xm_cplx) k_mode_copy<double, cplx><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (double*)x3d, n3d, (cplx*)xm, 1);
+        else k_mode_copy<double, double><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (double*)x3d, n3d, (double*)xm, 1);
+        CS_CUDA(cudaGetLastError());
+        return CS_OK;
+    }
+    dim3 g((unsigned)cdiv(bp.n2, DFT_QB), nvec), blk(DFT_QB, DFT_MY);
+    size_t sm = dft_smem(bp.nth, bp.nth);
+    const int sel = xm_cplx ? 0 : 2;
+    if (x_cplx) {
+        CS_TRY(dft_smem_attr(k_dft_gather<cplx, cplx>, sm));
+        k_dft_gather<cplx, cplx><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, sel, (const cplx*)x3d, n3d, (cplx*)xm, 0, 0);
+    } else if (xm_cplx) {
+        CS_TRY(dft_smem_attr(k_dft_gather<double, cplx>, sm));
+        k_dft_gather<double, cplx><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, sel, (const double*)x3d, n3d, (cplx*)xm, 0, 0);
+    } else {
+        CS_TRY(dft_smem_attr(k_dft_gather<double, double>, sm));
+        k_dft_gather<double, double><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, sel, (const double*)x3d, n3d, (double*)xm, 0, 0);
+    }
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
-int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, int nth, long long n3d, int nvec, cudaStream_t st) {
-    dim3 g((unsigned)cdiv(bp.n2, TPB), nvec);
-    if (x_cplx && xm_cplx) k_dft_scatter<cplx, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const cplx*)xm, (cplx*)x3d, n3d);
-    else if (!x_cplx && xm_cplx) k_dft_scatter<double, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const cplx*)xm, (double*)x3d, n3d);
-    else if (!x_cplx && !xm_cplx) {
-        CS_CHECK(nth == 1, "real mode vectors need nth == 1");
-        k_dft_scatter<double, double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, nth, (const double*)xm, (double*)x3d, n3d);
-    } else CS_CHECK(false, "complex mode storage into real vector needs cplx modes");
+int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, long long n3d, int nvec, cudaStream_t st) {
+    CS_CHECK(!(x_cplx && !xm_cplx), "complex vectors need complex factors (complex shift)");
+    if (bp.nth == 1) {
+        dim3 g((unsigned)cdiv(bp.n2, 256), nvec);
+        if (x_cplx) k_mode_copy<cplx, cplx><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (cplx*)x3d, n3d, (cplx*)xm, 0);
+        else if (xm_cplx) k_mode_copy<double, cplx><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (double*)x3d, n3d, (cplx*)xm, 0);
+        else k_mode_copy<double, double><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (double*)x3d, n3d, (double*)xm, 0);
+        CS_CUDA(cudaGetLastError());
+        return CS_OK;
+    }
+    dim3 g((unsigned)cdiv(bp.n2, DFT_QB), nvec), blk(DFT_QB, DFT_MY);
+    const int sel = xm_cplx ? 0 : 2;
+    size_t sm = dft_smem(bp.nth, xm_cplx ? bp.nth : bp.nmodes);
+    if (x_cplx) {
+        CS_TRY(dft_smem_attr(k_dft_scatter<cplx, cplx>, sm));
+        k_dft_scatter<cplx, cplx><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, sel, (const cplx*)xm, (cplx*)x3d, n3d);
+    } else if (xm_cplx) {
+        CS_TRY(dft_smem_attr(k_dft_scatter<double, cplx>, sm));
+        k_dft_scatter<double, cplx><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, sel, (const cplx*)xm, (double*)x3d, n3d);
+    } else {
+        CS_TRY(dft_smem_attr(k_dft_scatter<double, double>, sm));
+        k_dft_scatter<double, double><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, sel, (const double*)xm, (double*)x3d, n3d);
+    }
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
@@ -166,8 +282,9 @@ int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d
 // ------------------------------------------------------------- probing ------
 // Columns of the s-independent part K are obtained by applying the *same*
 // stencil kernel that the Krylov loop uses to 2p+1 "coloured" probe vectors
-// (ones at j = 0 for every band index q == color mod (2p+1)); the DFT of the
-// response holds column q of every mode matrix at once.
+// (ones at theta column jprobe for every band index q == color mod (2p+1)).  The stencils couple
+// neighbouring theta columns only, so the response lives in columns jprobe-1 .. jprobe+1 and its
+// three-term DFT holds column q of every mode matrix at once (cost independent of nth).
 template <typename TX>
 __global__ void k_probe_fill(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int ncol, int color0,
                              long long n3d, int jprobe, TX* __restrict__ x3d) {
@@ -188,14 +305,40 @@ int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d, long long 
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
+int band_probe_gather(const BandPlan& bp, const void* y3d, bool y_cplx, void* ym, long long n3d, int nb, cudaStream_t st) {
+    if (bp.nth == 1) {
+        dim3 g((unsigned)cdiv(bp.n2, 256), nb);
+        if (y_cplx) k_mode_copy<cplx, cplx><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (cplx*)y3d, n3d, (cplx*)ym, 1);
+        else k_mode_copy<double, cplx><<<g, 256, 0, st>>>(bp.map3d, bp.n2, (double*)y3d, n3d, (cplx*)ym, 1);
+        CS_CUDA(cudaGetLastError());
+        return CS_OK;
+    }
+    const int thin = (bp.nth >= 3 && bp.thin_probe) ? 1 : 0;
+    dim3 g((unsigned)cdiv(bp.n2, DFT_QB), nb), blk(DFT_QB, DFT_MY);
+    size_t sm = dft_smem(bp.nth, thin ? 3 : bp.nth);
+    if (y_cplx) {
+        CS_TRY(dft_smem_attr(k_dft_gather<cplx, cplx>, sm));
+        k_dft_gather<cplx, cplx><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, 1, (const cplx*)y3d, n3d, (cplx*)ym, bp.jprobe, thin);
+    } else {
+        CS_TRY(dft_smem_attr(k_dft_gather<double, cplx>, sm));
+        k_dft_gather<double, cplx><<<g, blk, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.nth, bp.nmodes, 1, (const double*)y3d, n3d, (cplx*)ym, bp.jprobe, thin);
+    }
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
 
-template <typename TB>
-__global__ void k_probe_store(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int p, int pw, int ldab,
-                              int color0, int nmodes, const TB* __restrict__ ym, TB* __restrict__ K) {
+// K''_m[r, q] = conj(T_m[r]) K_m[r, q] T_m[q]: the gather delivered conj(T_m[r]) K_m[r, q]; the column factor is applied here.
+// Real band storage keeps the real part (the imaginary part is rounding noise for a theta-invariant operator; for a
+// theta-varying one the circulant preconditioner is symmetrised by dropping it).
+template <typename TB, typename TX>
+__global__ void k_probe_store(const long long* __restrict__ map3d, const int* __restrict__ jstr, const signed char* __restrict__ hs,
+                              long long n2, int p, int pw, int ldab, int color0, int nmodes, int nth, int jprobe,
+                              const cplx* __restrict__ ym, const TX* __restrict__ y3d, long long n3d, TB* __restrict__ K) {
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int m = blockIdx.y;
     const int color = color0 + blockIdx.z;                   // response of probing vector blockIdx.z
     ym += (size_t)blockIdx.z * nmodes * n2;
+    y3d += (size_t)blockIdx.z * n3d;
     if (r >= n2) return;
     if (map3d[r] < 0) return;
     if (jstr[r] == 0 && m > 0) return;
@@ -206,12 +349,26 @@ __global__ void k_probe_store(const long long* __restrict__ map3d, const int* __
     if (q < 0 || q >= n2) return;
     if (map3d[q] < 0) return;
     if (jstr[q] == 0 && m > 0) return;
-    K[(size_t)m * n2 * ldab + (size_t)(pw + r - q) + (size_t)q * ldab] = ym[(size_t)m * n2 + r];
+    cplx val = ym[(size_t)m * n2 + r];
+    if (jstr[q] == 0 && jstr[r] != 0) {
+        // column of the shared axis unknown: it couples to EVERY theta column with the same entry B, the
+        // mode-0 entry is the sum over all nth of them (the three-term gather saw only three)
+        val = (double)nth * to_c(y3d[map3d[r] + (long long)jprobe * jstr[r]]);
+        if (hs[r] != 0) val = mk(val.y, -val.x);
+    }
+    const int h2 = hs[q];
+    if (h2 != 0) {
+        double sn, cs_;
+        sincospi((double)(h2 * m) / (double)nth, &sn, &cs_);   // T_m[q] = i exp(i hs pi m / nth)
+        val = val * mk(-sn, cs_);
+    }
+    K[(size_t)m * n2 * ldab + (size_t)(pw + r - q) + (size_t)q * ldab] = from_c<TB>(val);
 }
-int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, cudaStream_t st) {
+int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st) {
     dim3 g((unsigned)cdiv(bp.n2, TPB), bp.nmodes, nb);
-    if (bp.cplx_band) k_probe_store<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, (const cplx*)ym, (cplx*)bp.Kband);
-    else k_probe_store<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, (const double*)ym, (double*)bp.Kband);
+    CS_CHECK(bp.cplx_band == y_cplx, "probing vectors must have the scalar type of the band storage");
+    if (bp.cplx_band) k_probe_store<cplx, cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, bp.nth, bp.jprobe, (const cplx*)ym, (const cplx*)y3d, n3d, (cplx*)bp.Kband);
+    else k_probe_store<double, double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, bp.nth, bp.jprobe, (const cplx*)ym, (const double*)y3d, n3d, (double*)bp.Kband);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
@@ -252,9 +409,10 @@ int band_form_shifted(const BandPlan& bp, const double* s_d, int nshift, void* L
     return CS_OK;
 }
 
+// (the diagonal is invariant under the rotation; modes m and nth - m share it)
 template <typename TB>
 __global__ void k_diag_weights(const long long* __restrict__ map3d, const int* __restrict__ jstr, const double* __restrict__ mdiag,
-                               long long n2, int pw, int ldab, int nmodes, const TB* __restrict__ K,
+                               long long n2, int pw, int ldab, int nmodes, int nth, const TB* __restrict__ K,
                                const double* __restrict__ s_d, long long n3d, double* __restrict__ w) {
     long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int f = blockIdx.y;
@@ -265,22 +423,24 @@ __global__ void k_diag_weights(const long long* __restrict__ map3d, const int* _
     size_t nel = (size_t)n2 * ldab;
     double re = 0.0, im = 0.0;
     int nm = (st == 0) ? 1 : nmodes;
+    double cnt = 0.0;
     for (int m = 0; m < nm; ++m) {
         TB kv = K[(size_t)m * nel + (size_t)pw + (size_t)q * ldab];
-        re += Sc<TB>::re(kv); im += Sc<TB>::im(kv);
+        double wgt = (nth == 1 || st == 0 || m == 0 || 2 * m == nth) ? 1.0 : 2.0;
+        re += wgt * Sc<TB>::re(kv); im += wgt * Sc<TB>::im(kv); cnt += wgt;
     }
-    re /= nm; im /= nm;
+    re /= cnt; im /= cnt;
     re += s_d[2 * f] * mdiag[q];
     im += s_d[2 * f + 1] * mdiag[q];
     double ww = 1.0 / sqrt(re * re + im * im);
     double* wf = w + (size_t)f * n3d;
     if (st == 0) { wf[b] = ww; return; }
-    for (int j = 0; j < nmodes; ++j) wf[b + (long long)j * st] = ww;
+    for (int j = 0; j < nth; ++j) wf[b + (long long)j * st] = ww;
 }
 int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long long n3d, double* w, cudaStream_t st) {
     dim3 g((unsigned)cdiv(bp.n2, TPB), nshift);
-    if (bp.cplx_band) k_diag_weights<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.mdiag, bp.n2, bp.pw, bp.ldab, bp.nmodes, (const cplx*)bp.Kband, s_d, n3d, w);
-    else k_diag_weights<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.mdiag, bp.n2, bp.pw, bp.ldab, bp.nmodes, (const double*)bp.Kband, s_d, n3d, w);
+    if (bp.cplx_band) k_diag_weights<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.mdiag, bp.n2, bp.pw, bp.ldab, bp.nmodes, bp.nth, (const cplx*)bp.Kband, s_d, n3d, w);
+    else k_diag_weights<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.mdiag, bp.n2, bp.pw, bp.ldab, bp.nmodes, bp.nth, (const double*)bp.Kband, s_d, n3d, w);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
@@ -483,9 +643,9 @@ __global__ void k_invert_diag(T* __restrict__ LU, size_t nel, long long n2, int 
 // one by one they make the solve hostage to host-thread jitter, so the whole sequence is
 // captured once into a CUDA graph per (buffer, shape) and replayed with a single launch.
 struct FactorGraphKey {
-    void* LU; void* scratch; long long n2; int p, nsys, cplx;
+    void* LU; void* scratch; long long n2; int p, nsys, cplx, dev;
     bool operator==(const FactorGraphKey& o) const {
-        return LU == o.LU && scratch == o.scratch && n2 == o.n2 && p == o.p && nsys == o.nsys && cplx == o.cplx;
+        return LU == o.LU && scratch == o.scratch && n2 == o.n2 && p == o.p && nsys == o.nsys && cplx == o.cplx && dev == o.dev;
     }
 };
 struct FactorGraph { FactorGraphKey key; cudaGraphExec_t exec; unsigned long long stamp; };
@@ -515,7 +675,9 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_band_mu);
     void* scratch = nullptr;
     CS_TRY(band_scratch(0, st, (size_t)nsys * NB * NB * sizeof(T), false, &scratch));
-    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB};
+    int dev_key = 0;
+    CS_CUDA(cudaGetDevice(&dev_key));
+    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
             g.stamp = ++g_stamp;
@@ -528,12 +690,17 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     // The chain is latency-bound and barely depends on the number of systems per launch, so the
     // systems are split into up to 4 groups whose chains run concurrently on forked streams
     // (inside the captured graph: parallel branches) and hide each other's latency.
-    static cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-    if (!ev_fork) {
-        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-        for (int g = 0; g < 3; ++g) { cudaStreamCreateWithFlags(&aux[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming); }
+    // (capture streams / events belong to a device: one set per device, created on first use under g_band_mu)
+    struct AuxSet { cudaStream_t aux[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}; };
+    static std::map<int, AuxSet> aux_sets;
+    int dev_now = 0;
+    CS_CUDA(cudaGetDevice(&dev_now));
+    AuxSet& as = aux_sets[dev_now];
+    if (!as.ev_fork) {
+        cudaEventCreateWithFlags(&as.ev_fork, cudaEventDisableTiming);
+        for (int g = 0; g < 3; ++g) { cudaStreamCreateWithFlags(&as.aux[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&as.ev_join[g], cudaEventDisableTiming); }
     }
+    cudaStream_t* aux = as.aux; cudaEvent_t ev_fork = as.ev_fork; cudaEvent_t* ev_join = as.ev_join;
     const int groups = (nsys >= 16) ? 4 : (nsys >= 6 ? 2 : 1);
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
         bool okq = true;
@@ -1187,7 +1354,7 @@ __device__ __forceinline__ void bar_sync0() { asm volatile("bar.sync 0;" ::: "me
 template <typename TL, typename TV, int TPR, int NB, bool HP>
 __global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0) {
+                             int nmodes, int nmv, int fold, int nth, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool USE_TMA = sizeof(TL) == 16;                // complex: TMA bulk copies, real: cp.async
     __shared__ unsigned long long full_bar[8];
@@ -1200,10 +1367,13 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
         }
         bar_sync0();
     }
-    const int v = blockIdx.y, m = blockIdx.x;
+    // mode vector mm of 3-D vector v is solved with the stored factor h: all nth modes of a complex vector fold onto
+    // min(mm, nth - mm) (K''_{nth-m} = K''_m), the (Re, Im) pairs of a real vector's modes share factor mm / 2
+    const int v = blockIdx.y, mm = blockIdx.x;
+    const int m = fold == 0 ? mm : (fold == 1 ? min(mm, nth - mm) : (mm >> 1));
     const int f = shift_of_vec ? shift_of_vec[v] : 0;
     const TL* A = LU + ((size_t)f * nmodes + m) * nel + pw;
-    TV* b = xm + ((size_t)v * nmodes + m) * n2;
+    TV* b = xm + ((size_t)v * nmv + mm) * n2;
     // rows per staged block column, padded so that the TPR column groups of a quarter warp fall into
     // distinct shared-memory banks (TPR = 4: ldd = 2 mod 8, TPR = 2: ldd = 4 mod 8)
     int ldd = NB + p;
@@ -1395,9 +1565,11 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
     const bool hp = (sizeof(T) == 16 || (e && atoi(e) > 0)) && (th + 32 <= bound) && !(e && atoi(e) == 0);
     if (hp) CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     else CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
-    dim3 g(bp.nmodes, nvec);
-    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, th);
-    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, sov, xm, wsz, nst, bp.diag_full, 0);
+    const bool xc = sizeof(T) == sizeof(cplx);
+    const int nmv = bp.nmv(xc), fold = bp.fold(xc);
+    dim3 g(nmv, nvec);
+    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, sov, xm, wsz, nst, bp.diag_full, th);
+    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, sov, xm, wsz, nst, bp.diag_full, 0);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

@@ -55,10 +55,15 @@ struct BandPlan {
     int nb = 16;               // block size of the blocked LU
     int pw = 0;                // stored half bandwidth = p + nb
     int ldab = 0;              // 2*pw + 1
-    int nmodes = 1;            // nth
-    bool cplx_band = false;    // storage scalar type of K band / LU
+    int nth = 1;               // azimuthal cells of the mesh
+    // stored mode systems per shift.  With T_m = diag(1 | i exp(+-i pi m / nth)) on the theta-staggered component
+    // K''_m = T_m^* K_m T_m is REAL symmetric and K''_{nth-m} = K''_m, so only modes 0 .. nth/2 are probed,
+    // stored and factored (nth/2 + 1 systems; 1 for a cylindrically symmetric mesh)
+    int nmodes = 1;
+    bool cplx_band = false;    // storage scalar type of K band (complex only for assembled complex CSR matrices)
     long long* map3d = nullptr;  // [n2] index into the 3-D vector at j = 0, -1 = dummy
     int* jstr = nullptr;         // [n2] stride per theta step (0 = axis unknown)
+    signed char* hs = nullptr;   // [n2] theta stagger of the unknown in half cells: 0, +1 (Ey) or -1 (Fy)
     double* mdiag = nullptr;     // [n2] diagonal "mass" part multiplied by the shift s
     void* Kband = nullptr;       // [nmodes][n2*ldab] band of the s-independent part
     // format of the factored diagonal blocks, set by band_factor: 0 = inv(L11) \ inv(U11) of the
@@ -71,17 +76,28 @@ struct BandPlan {
     // theta column the band matrices are probed at: 0 for uniform azimuthal widths, otherwise the column whose
     // width is closest to the mean (the circulant preconditioner then models an "average" column)
     int jprobe = 0;
+    // the probing response is confined to theta columns jprobe-1 .. jprobe+1 (three-term DFT).  Not for face unknowns:
+    // the Fy faces of the innermost cells share the single axis Ez edge, so C C^T couples them across ALL theta columns
+    bool thin_probe = true;
     size_t band_elems() const { return (size_t)n2 * ldab; }
+    // mode vectors per 3-D vector: complex factors take all nth modes (mode m uses factor min(m, nth - m));
+    // real factors (real shift) take Re / Im of modes 0 .. nth/2 of a REAL 3-D vector as 2 * nmodes real vectors
+    int nmv(bool xm_cplx) const { return nth == 1 ? 1 : (xm_cplx ? nth : 2 * nmodes); }
+    int fold(bool xm_cplx) const { return nth == 1 ? 0 : (xm_cplx ? 1 : 2); }
 };
 
 // block size (16 or 32) for a plan with half bandwidth p
 int band_choose_nb(int p);
 void band_release_stream(cudaStream_t st);   // frees the band scratch buffers keyed by this stream
 int band_factor_launches(const BandPlan& bp, bool lu_cplx);
-int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm /*[nvec][nmodes][n2]*/, bool xm_cplx, int nth, long long n3d, int nvec, cudaStream_t st, int jshift = 0);
-int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, int nth, long long n3d, int nvec, cudaStream_t st);
+// theta-DFT into the rotated mode basis x''_m = T_m^* x_m; xm [nvec][nmv][n2]
+int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm, bool xm_cplx, long long n3d, int nvec, cudaStream_t st);
+int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, long long n3d, int nvec, cudaStream_t st);
 int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]*/, long long n3d, bool x_cplx, cudaStream_t st);
-int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym /*[nb][nmodes][n2]*/, cudaStream_t st);
+// modes 0 .. nmodes-1 of the probing responses y3d [nb][n3d] (nonzero in theta columns jprobe-1 .. jprobe+1 only)
+// -> ym complex [nb][nmodes][n2], then column `color + b` of every mode matrix
+int band_probe_gather(const BandPlan& bp, const void* y3d, bool y_cplx, void* ym, long long n3d, int nb, cudaStream_t st);
+int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st);
 // w[f][3-D index] = 1 / |diag(A(s_f))| recovered from the mode matrices (mean over modes of K_m[q,q]) + s_f * mass
 int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long long n3d, double* w, cudaStream_t st);
 // LU[f][mode] = Kband[mode] + s[f] * diag(mdiag)   (f = 0..nshift-1)
@@ -89,7 +105,7 @@ int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shif
 // in-place blocked LU without pivoting of nsys_tot = nshift*nmodes band matrices
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st);
 int band_form_and_factor(const BandPlan& bp, const double* s_d /*device*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
-// solve: rhs/solution xm [nvec][nmodes][n2]; vector v uses factor shift_of_vec[v]
+// solve: rhs/solution xm [nvec][nmv][n2]; vector v uses the factors of shift shift_of_vec[v]
 int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st);
 
 }  // namespace cs

@@ -201,6 +201,8 @@ class BaseMeshGenerator(BaseCasing):
 
     def serialize(self):
         out = super(BaseMeshGenerator, self).serialize()
+        if self.__dict__.get("domain_z_user", None) is not None:
+            out["domain_z"] = self.domain_z_user
         return out
 
 
@@ -230,17 +232,20 @@ class BaseCylMixin(object):
 
     @property
     def domain_z(self):
-        if getattr(self, "_domain_z", None) is None:
-            mp = self.modelParameters
-            dz = np.absolute(mp.src_b[2] - mp.src_a[2])
-            if getattr(mp, "casing_z", None) is not None:
-                dz = max(np.absolute(mp.casing_z[1] - mp.casing_z[0]), dz)
-            object.__setattr__(self, "_domain_z", dz)
-        return self._domain_z
+        # an explicit user value (mesh.py domain_z.setter) wins and must survive the cache invalidation that every
+        # public assignment triggers: it is kept under a public name, outside the '_'-prefixed derived quantities
+        user = self.__dict__.get("domain_z_user", None)
+        if user is not None:
+            return user
+        mp = self.modelParameters
+        dz = np.absolute(mp.src_b[2] - mp.src_a[2])
+        if getattr(mp, "casing_z", None) is not None:
+            dz = max(np.absolute(mp.casing_z[1] - mp.casing_z[0]), dz)
+        return dz
 
     @domain_z.setter
     def domain_z(self, value):
-        object.__setattr__(self, "_domain_z", value)
+        object.__setattr__(self, "domain_z_user", None if value is None else float(value))
 
     @property
     def ncy(self):

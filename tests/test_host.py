@@ -41,6 +41,22 @@ def test_mesh_sizes_match_survey_appendix_b():
         cs.CylMeshGenerator(modelParameters=w, hy=np.ones(4))                    # must sum to 2 pi (mesh.py:408-411)
 
 
+def test_domain_z_override_is_kept():
+    """mesh.py domain_z.setter: an explicit value wins over the model-derived extent, as attribute and as keyword,
+    and survives copy() / later parameter changes (the cache invalidation must not drop it)."""
+    mp = cs.model.CasingInHalfspace(src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0])
+    mg = cs.CasingMeshGenerator(modelParameters=mp, csz=10.0)
+    assert mg.domain_z == 1000.0 and mg.ncz == 110
+    mg.domain_z = 500.0
+    assert mg.domain_z == 500.0 and mg.ncz == 60 and len(mg.hz) == 60 + 2 * mg.npadz
+    mg.csz = 5.0                                     # another assignment: the override stays
+    assert mg.domain_z == 500.0 and mg.ncz == 110
+    mg2 = cs.CasingMeshGenerator(modelParameters=mp, domain_z=500.0, csz=10.0)
+    assert mg2.domain_z == 500.0 and mg2.ncz == 60 and mg2.copy().domain_z == 500.0
+    g3 = cs.CylMeshGenerator(modelParameters=mp, domain_z=200.0, csz=10.0)
+    assert g3.ncz == 30
+
+
 def test_mesh_geometry_matches_oracle():
     from oracle.cyl_oracle import OracleCylMesh
     mp, mg = _casing_setup(4, npadx=3, npadz=4, csz=50.0)
