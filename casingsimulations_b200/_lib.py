@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libcasing_b200.so")
 
 KIND_DC, KIND_DC_GROUNDED, KIND_EDGE_H, KIND_EDGE_E, KIND_FACE_J, KIND_FACE_B = range(6)
 INFO_LEN = 16
-INFO_NAMES = ["iters", "relres", "ms_assemble", "ms_factor", "ms_solve", "n_apply", "n_launch", "bytes", "converged", "backward_err"]
+INFO_NAMES = ["iters", "relres", "ms_assemble", "ms_factor", "ms_solve", "n_apply", "n_launch", "bytes", "converged", "backward_err",
+              "dd_steps", "dd_corr"]
 
 _lib = None
 
@@ -53,6 +54,8 @@ def load_library():
         "cs_ctx_create": (c.c_int, [c.c_int, vp, c.POINTER(vp)]),
         "cs_ctx_destroy": (c.c_int, [vp]),
         "cs_ctx_sync": (c.c_int, [vp]),
+        "cs_fp64_peak": (c.c_int, [vp, dp]),
+        "cs_ctx_set_refine": (c.c_int, [vp, c.c_int]),
         "cs_mesh_set": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, dp, dp, dp, c.c_double, c.c_double, c.c_double]),
         "cs_mesh_counts": (c.c_int, [vp, c.POINTER(ll)]),
         "cs_model_paint": (c.c_int, [vp, dp, vp, vp]),
@@ -89,7 +92,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_mesh_set",
+    "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_fp64_peak", "cs_ctx_set_refine", "cs_mesh_set",
     "cs_mesh_counts", "cs_model_paint", "cs_model_set", "cs_face_inner_product", "cs_edge_inner_product",
     "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_op_get", "cs_op_get_noplan", "cs_op_apply_timed", "cs_op_from_csr", "cs_op_size", "cs_op_apply", "cs_op_factor",
     "cs_op_solve", "cs_op_clean", "cs_solve_dc", "cs_solve_fdem", "cs_tdem_run", "cs_fields_fdem",
@@ -244,6 +247,19 @@ class Context(object):
 
     def launch_count(self):
         return int(self.lib.cs_launch_count())
+
+    def set_refine(self, max_dd_steps):
+        """iterative refinement of edge-form solves with a double-double residual (0 = off, the default)"""
+        check(self.lib.cs_ctx_set_refine(self.h, int(max_dd_steps)))
+
+    def fp64_peak_tflops(self):
+        """DFMA throughput of this device (TFLOP/s), measured live: the FP64 roofline denominator"""
+        v = ctypes.c_double(0.0)
+        self._enter()
+        rc = self.lib.cs_fp64_peak(self.h, ctypes.byref(v))
+        self._exit()
+        check(rc)
+        return v.value
 
     # -- mesh / model -------------------------------------------------------
     def set_mesh(self, hx, hy, hz, z0, axis_weight_edge=1.0, axis_weight_face=0.5):

@@ -17,6 +17,23 @@ from .info import __version__
 _REGISTRY = {}
 
 
+def memo_property(fn):
+    """Property evaluated once and kept under a '_'-prefixed name, i.e. among the lazily cached derived quantities that
+    BaseCasing._invalidate drops whenever a public parameter is assigned.  (The reference recomputes its face masks and
+    s_e on every access, sources.py:570, 698, 822 test `_srcList` instead of `_s_e`; on a 14.6 M-face mesh one evaluation
+    costs seconds of numpy.)"""
+    key = "_memo_" + fn.__name__
+
+    def getter(self):
+        d = self.__dict__
+        if key not in d:
+            object.__setattr__(self, key, fn(self))
+        return d[key]
+    getter.__name__ = fn.__name__
+    getter.__doc__ = fn.__doc__
+    return property(getter)
+
+
 def load_properties(filename):
     """utils.py:11-24: rebuild an instance from its JSON file."""
     with open(filename, "r") as f:

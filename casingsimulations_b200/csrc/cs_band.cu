@@ -17,6 +17,7 @@
 #include "cs_internal.h"
 #include <cuda_pipeline.h>
 #include <vector>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -677,7 +678,9 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_TRY(band_scratch(0, st, (size_t)nsys * NB * NB * sizeof(T), false, &scratch));
     int dev_key = 0;
     CS_CUDA(cudaGetDevice(&dev_key));
-    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB, dev_key};
+    int groups_key = 0;
+    { const char* e = getenv("CS_BAND_GROUPS"); if (e) groups_key = atoi(e); }
+    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
             g.stamp = ++g_stamp;
@@ -691,17 +694,19 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     // systems are split into up to 4 groups whose chains run concurrently on forked streams
     // (inside the captured graph: parallel branches) and hide each other's latency.
     // (capture streams / events belong to a device: one set per device, created on first use under g_band_mu)
-    struct AuxSet { cudaStream_t aux[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}; };
+    static const int MAXG = 32;
+    struct AuxSet { cudaStream_t aux[MAXG - 1] = {}; cudaEvent_t ev_fork = nullptr, ev_join[MAXG - 1] = {}; };
     static std::map<int, AuxSet> aux_sets;
     int dev_now = 0;
     CS_CUDA(cudaGetDevice(&dev_now));
     AuxSet& as = aux_sets[dev_now];
     if (!as.ev_fork) {
         cudaEventCreateWithFlags(&as.ev_fork, cudaEventDisableTiming);
-        for (int g = 0; g < 3; ++g) { cudaStreamCreateWithFlags(&as.aux[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&as.ev_join[g], cudaEventDisableTiming); }
+        for (int g = 0; g < MAXG - 1; ++g) { cudaStreamCreateWithFlags(&as.aux[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&as.ev_join[g], cudaEventDisableTiming); }
     }
     cudaStream_t* aux = as.aux; cudaEvent_t ev_fork = as.ev_fork; cudaEvent_t* ev_join = as.ev_join;
-    const int groups = (nsys >= 16) ? 4 : (nsys >= 6 ? 2 : 1);
+    int groups = (nsys >= 16) ? 4 : (nsys >= 6 ? 2 : 1);
+    { const char* e = getenv("CS_BAND_GROUPS"); if (e && atoi(e) >= 1) groups = std::min(std::min(atoi(e), nsys), MAXG); }
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
         bool okq = true;
         if (groups > 1) {

@@ -31,6 +31,11 @@ int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const d
 int launch_face_op(const MeshD& m, const double* uF, const double* gE, const double* s_d,
                    const void* x, void* y, int nsys, bool cplx_vec, void* ework /*nsys*nE workspace or nullptr*/, cudaStream_t st);
 
+// cs_dd.cu: r = b - A(s) x of the edge-form operator with exact products and double-double sums (iterative refinement);
+// s_h: 2 doubles per system on the HOST, work: 2 * nF doubles
+int launch_edge_resid_dd(const MeshD& m, const double* wF, const double* beta, const double* s_h, const void* x, const void* b,
+                         void* r, int nsys, bool cplx_vec, double* work, cudaStream_t st);
+
 int launch_csr_spmv(long long n, const long long* indptr, const int* indices, const void* vals, bool a_cplx,
                     const void* x, void* y, int nsys, bool x_cplx, cudaStream_t st);
 

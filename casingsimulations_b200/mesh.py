@@ -141,6 +141,9 @@ class CylMesh(object):
 
     @property
     def area(self):
+        return self._cached("area", self._area)
+
+    def _area(self):
         ax = np.kron(self.hz, np.kron(self.hy, self.vectorNx))
         az = np.kron(np.ones(len(self.hz) + 1), np.kron(self.hy, self._ring))
         if self.isSymmetric:

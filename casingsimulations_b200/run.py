@@ -104,6 +104,8 @@ class _Problem(object):
             m = self.mesh
             ctx.set_mesh(m.hx, m.hy, m.hz, m.x0[2], self.solver_opts.get("axis_weight_edge", 1.0),
                          self.solver_opts.get("axis_weight_face", 0.5))
+            if self.solver_opts.get("dd_refine", 0):
+                ctx.set_refine(self.solver_opts["dd_refine"])
             self._ctx = ctx
         return self._ctx
 
@@ -196,15 +198,17 @@ class _ProblemFDEM(_Problem):
     def fields(self, m=None):
         self._set_model(m)
         ctx = self.ctx
+        torch = _lib._torch()
         srcs = self.survey.srcList
         n = self.mesh.nE if self.form == "h" else self.mesh.nF
-        sol = np.zeros((n, len(srcs)), dtype=complex)
+        # one contiguous column per source (Fortran order, like the (n, nSrc) arrays SimPEG fields hold)
+        sol = np.zeros((len(srcs), n), dtype=complex).T
         # sources that share one s_e vector (casingSimulations: one source per frequency,
         # sources.py:119-123) go to the GPU as one batched multi-frequency solve
         groups = []
         for i, s in enumerate(srcs):
             for g in groups:
-                if g[0].shape == s.s_e.shape and np.array_equal(g[0], s.s_e):
+                if g[0] is s.s_e or (g[0].shape == s.s_e.shape and np.array_equal(g[0], s.s_e)):
                     g[1].append(i)
                     break
             else:
@@ -217,8 +221,14 @@ class _ProblemFDEM(_Problem):
             u = ctx.solve_fdem(self.form, freqs, se_d, rtol=self.rtol, maxit=self.maxit)
             for key, val in ctx.info.items():
                 info[key] = max(info.get(key, 0.0), val) if key in ("relres", "iters") else info.get(key, 0.0) + val
-            sol[:, members] = u.cpu().numpy().T
+            # device -> pinned staging buffer (kept with the problem) -> the caller's fresh array
+            stage = getattr(self, "_stage", None)
+            if stage is None or stage.shape != u.shape:
+                stage = self._stage = torch.empty(u.shape, dtype=u.dtype, pin_memory=True)
+            stage.copy_(u)
+            uh = stage.numpy()
             for k, i in enumerate(members):
+                sol[:, i] = uh[k]
                 self._se_d[i], self._u_d[i] = se_d, u[k]
         self.info = info
         return Fields(self, sol, srcs)

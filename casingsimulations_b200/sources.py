@@ -8,7 +8,7 @@ vector is uploaded once and becomes the right-hand side on the GPU.
 """
 import numpy as np
 
-from .base import BaseCasing
+from .base import BaseCasing, memo_property
 from .mesh import closestPoints
 
 
@@ -99,16 +99,16 @@ class HorizontalElectricDipole(BaseCasingSrc):
         super(HorizontalElectricDipole, self).__init__(**kwargs)
         assert self.src_a[2] == self.src_b[2], "z locations must be the same for a HED"
 
-    @property
+    @memo_property
     def src_a_closest(self):
         # the reference indexes gridFx with an 'Fz' closest-point index (sources.py:149)
         return self.mesh.gridFx[closestPoints(self.mesh, self.src_a, "Fz"), :][0]
 
-    @property
+    @memo_property
     def src_b_closest(self):
         return self.mesh.gridFx[closestPoints(self.mesh, self.src_b, "Fz"), :][0]
 
-    @property
+    @memo_property
     def surface_wire(self):
         mesh, g = self.mesh, self.mesh.gridFx
         lo, hi = min(self.src_a[0], self.src_b[0]), max(self.src_a[0], self.src_b[0])
@@ -120,7 +120,7 @@ class HorizontalElectricDipole(BaseCasingSrc):
     def surface_wire_direction(self):
         return -1.0 if self.src_a[0] < self.src_b[0] else 1.0
 
-    @property
+    @memo_property
     def s_e(self):
         mesh = self.mesh
         s_x, s_z = np.zeros(mesh.vnF[0]), np.zeros(mesh.vnF[2])
@@ -138,15 +138,15 @@ class VerticalElectricDipole(BaseCasingSrc):
         super(VerticalElectricDipole, self).__init__(**kwargs)
         assert all(self.src_a[:2] == self.src_b[:2]), "src_a and src_b must have the same horizontal location"
 
-    @property
+    @memo_property
     def src_a_closest(self):
         return self.mesh.gridFz[closestPoints(self.mesh, self.src_a, "Fz"), :][0]
 
-    @property
+    @memo_property
     def src_b_closest(self):
         return self.mesh.gridFz[closestPoints(self.mesh, self.src_b, "Fz"), :][0]
 
-    @property
+    @memo_property
     def wire_in_borehole(self):
         mesh, g = self.mesh, self.mesh.gridFz
         dx, dz = mesh.hx.min() / 2.0, 0.5 * mesh.hz.min()
@@ -155,13 +155,13 @@ class VerticalElectricDipole(BaseCasingSrc):
         mask = (g[:, 0] < xa + dx) & (g[:, 0] > xa - dx) & (g[:, 2] >= zlo - dz) & (g[:, 2] <= zhi + dz)
         return mask & self._theta_window(g, self.src_a[1], mesh.hy.min() / 2.0)
 
-    @property
+    @memo_property
     def _wire_direction(self):
         # the reference reads an attribute it never defines (sources.py:374); current
         # flows from src_a to src_b, matching the other sources' sign convention
         return -1.0 if self.src_a[2] > self.src_b[2] else 1.0
 
-    @property
+    @memo_property
     def s_e(self):
         mesh = self.mesh
         s_x, s_z = np.zeros(mesh.vnF[0]), np.zeros(mesh.vnF[2])
@@ -176,15 +176,15 @@ class DownHoleTerminatingSrc(BaseCasingSrc):
     """A wire down the borehole axis that ends down-hole, a surface wire and a
     return electrode (sources.py:416-643)."""
 
-    @property
+    @memo_property
     def src_a_closest(self):
         return self.mesh.gridFz[closestPoints(self.mesh, self.src_a, "Fz"), :][0]
 
-    @property
+    @memo_property
     def src_b_closest(self):
         return self.mesh.gridFz[closestPoints(self.mesh, self.src_b, "Fz"), :][0]
 
-    @property
+    @memo_property
     def wire_in_borehole(self):
         mesh, g = self.mesh, self.mesh.gridFz
         dx, xa = mesh.hx.min() / 2.0, self.src_a_closest[0]
@@ -192,7 +192,7 @@ class DownHoleTerminatingSrc(BaseCasingSrc):
                 (g[:, 2] >= self.src_a[2] - 0.5 * mesh.hz.min()) & (g[:, 2] < self.src_b[2] + 1.5 * mesh.hz.min()))
         return mask & self._theta_window(g, self.src_a[1], mesh.hy.min() / 2.0)
 
-    @property
+    @memo_property
     def surface_wire(self):
         mesh, g = self.mesh, self.mesh.gridFx
         xa, xb = self.src_a_closest[0], self.src_b_closest[0]
@@ -200,7 +200,7 @@ class DownHoleTerminatingSrc(BaseCasingSrc):
                 (g[:, 2] > mesh.hz.min()) & (g[:, 2] <= 2 * mesh.hz.min()))
         return mask & self._theta_window(g, self.src_b[1], mesh.hy.min() / 2.0)
 
-    @property
+    @memo_property
     def surface_electrode(self):
         mesh, g = self.mesh, self.mesh.gridFz
         dx, xb = mesh.hx.min() / 2.0, self.src_b_closest[0]
@@ -212,7 +212,7 @@ class DownHoleTerminatingSrc(BaseCasingSrc):
     def surface_wire_direction(self):
         return -1.0 if self.src_a[0] < self.src_b[0] else 1.0
 
-    @property
+    @memo_property
     def s_e(self):
         mesh = self.mesh
         s_x, s_z = np.zeros(mesh.vnF[0]), np.zeros(mesh.vnF[2])
@@ -230,14 +230,14 @@ class DownHoleTerminatingSrc(BaseCasingSrc):
 class DownHoleCasingSrc(DownHoleTerminatingSrc):
     """Down-hole electrode coupled to the casing wall (sources.py:647-748)."""
 
-    @property
+    @memo_property
     def downhole_electrode(self):
         mesh, g = self.mesh, self.mesh.gridFx
         za = self.src_a_closest[2]
         mask = (g[:, 0] <= self.casing_a) & (g[:, 2] <= za) & (g[:, 2] > za - mesh.hz.min())
         return mask & self._theta_window(g, self.src_a[1], mesh.hy.min() / 2.0)
 
-    @property
+    @memo_property
     def s_e(self):
         mesh = self.mesh
         s_x, s_z = np.zeros(mesh.vnF[0]), np.zeros(mesh.vnF[2])
@@ -254,14 +254,14 @@ class DownHoleCasingSrc(DownHoleTerminatingSrc):
 class SurfaceGroundedSrc(DownHoleTerminatingSrc):
     """Two surface electrodes joined by a surface wire (sources.py:751-897)."""
 
-    @property
+    @memo_property
     def positive_electrode(self):
         mesh, g = self.mesh, self.mesh.gridFz
         a = self.src_a_closest
         mask = (g[:, 0] == a[0]) & (g[:, 2] >= a[2]) & (g[:, 2] < 1.5 * mesh.hz.min())
         return mask & self._theta_window(g, self.src_a[1], mesh.hy.min())
 
-    @property
+    @memo_property
     def s_e(self):
         mesh = self.mesh
         s_x, s_z = np.zeros(mesh.vnF[0]), np.zeros(mesh.vnF[2])

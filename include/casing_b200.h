@@ -40,6 +40,8 @@ typedef struct cs_op cs_op;
 #define CS_INFO_BYTES 7      /* algorithmic bytes moved by the stencil applies */
 #define CS_INFO_CONVERGED 8
 #define CS_INFO_BACKWARD_ERR 9 /* set when relres stalls above rtol at the fp64 floor: ||r~||/(8||x~||+||b~||) <= 2e-15 is accepted */
+#define CS_INFO_DD_STEPS 10    /* refinement steps taken with the double-double residual (edge-form operators)  */
+#define CS_INFO_DD_CORR 11     /* size of the last such correction, ||D^1/2 dx|| / ||D^1/2 x||                    */
 #define CS_INFO_LEN 16
 
 const char* cs_last_error(void);
@@ -49,6 +51,15 @@ long long cs_launch_count(void);
 int cs_ctx_create(int device, void* stream, cs_ctx** out);
 int cs_ctx_destroy(cs_ctx* ctx);
 int cs_ctx_sync(cs_ctx* ctx);
+/* optional forward-accuracy polish of the edge-form solves (FDEM-h / -e): up to max_dd_steps steps of iterative
+ * refinement x += M^-1 (b - A x) with the residual evaluated in double-double arithmetic (exact products, csrc/cs_dd.cu).
+ * Default 0 (off): the fp64 data of a 3-D casing problem do not determine the plain-L2 solution beyond 1e-5 at 1 Hz
+ * anyway; energy-norm fields and casing currents are at 1e-10 without it. */
+int cs_ctx_set_refine(cs_ctx* ctx, int max_dd_steps);
+
+/* measurement aid (no reference counterpart): DFMA throughput of the context's device in TFLOP/s, the denominator
+ * of the factorisation's FP64 roofline in bench.py */
+int cs_fp64_peak(cs_ctx* ctx, double* tflops_h);
 
 /* discretize.CylMesh([hx, hy, hz], x0)            mesh.py:87-99, 518, 563 */
 int cs_mesh_set(cs_ctx* ctx, int nx, int nth, int nz, const double* hx_h, const double* hth_h,

@@ -101,11 +101,14 @@ class OracleCylMesh(object):
     innermost cell gives to the Ey edge / Fx face at r_1 (A.4, open question 1).
     """
 
-    def __init__(self, h, x0=None, axis_weight_edge=1.0, axis_weight_face=0.5):
-        self.hx = np.asarray(h[0], dtype=float).copy()
-        self.hy = np.atleast_1d(np.asarray(h[1], dtype=float)).copy()
-        self.hz = np.asarray(h[2], dtype=float).copy()
-        self.x0 = np.zeros(3) if x0 is None else np.asarray(x0, dtype=float).copy()
+    def __init__(self, h, x0=None, axis_weight_edge=1.0, axis_weight_face=0.5, dtype=float):
+        # dtype=np.longdouble assembles every measure, operator and inner product in extended precision from the same
+        # fp64 inputs: the "exact" discrete system of exact_mesh() / the parity truth (see solve_refined)
+        self.dtype = dtype
+        self.hx = np.asarray(h[0], dtype=dtype).copy()
+        self.hy = np.atleast_1d(np.asarray(h[1], dtype=dtype)).copy()
+        self.hz = np.asarray(h[2], dtype=dtype).copy()
+        self.x0 = np.zeros(3, dtype=dtype) if x0 is None else np.asarray(x0, dtype=dtype).copy()
         assert abs(self.hy.sum() - 2 * np.pi) < 1e-6
         self.nx, self.nth, self.nz = len(self.hx), len(self.hy), len(self.hz)
         self.isSymmetric = self.nth == 1
@@ -353,14 +356,14 @@ class OracleCylMesh(object):
         return sp.vstack([AvEx.T, AvEy.T, AvEz.T], format="csr")
 
     def getFaceInnerProduct(self, prop=None, invProp=False, invMat=False):
-        p = np.ones(self.nC) if prop is None else np.asarray(prop, dtype=float)
+        p = np.ones(self.nC, dtype=self.dtype) if prop is None else np.asarray(prop, dtype=self.dtype)
         if invProp:
             p = 1.0 / p
         d = self.face_average_transpose() @ (self.vol * p)
         return _sdiag(1.0 / d if invMat else d)
 
     def getEdgeInnerProduct(self, prop=None, invProp=False, invMat=False):
-        p = np.ones(self.nC) if prop is None else np.asarray(prop, dtype=float)
+        p = np.ones(self.nC, dtype=self.dtype) if prop is None else np.asarray(prop, dtype=self.dtype)
         if invProp:
             p = 1.0 / p
         d = self.edge_average_transpose() @ (self.vol * p)
@@ -426,9 +429,23 @@ class SolverLU(object):
         self.lu = None
 
 
+def exact_mesh(mesh):
+    """The same mesh with every measure / operator / inner product assembled in np.longdouble (eps 1e-19) from the same
+    fp64 inputs.  Problems built on it (OracleDC / OracleFDEM / OracleTDEM with refine=True) give the solution of the
+    EXACT discrete system.  Why it matters: an fp64-assembled matrix (the reference's included) carries entry roundings
+    of 1e-16 relative to the LARGE conductances on its diagonal -- next to the 1e13 coefficient contrast of a casing
+    model that is a spurious leak comparable to the true small couplings, and it moves the solution by 1e-6 (DC) to
+    1e-4 (3-D curl-curl).  A matrix-free difference-form operator (the GPU path) does not have that error, so it is
+    compared with THIS truth at a fixed tolerance; the fp64-assembled oracle's own distance from it is reported."""
+    return OracleCylMesh([mesh.hx, mesh.hy, mesh.hz], mesh.x0, mesh.axis_weight_edge, mesh.axis_weight_face,
+                         dtype=np.longdouble)
+
+
 def solve_refined(A, b, iters=10, lu=None):
     """"Truth" for parity tests: SuperLU solution polished by iterative refinement
     with the residual b - A x accumulated in extended precision (np.longdouble).
+    If A itself holds long-double entries (exact_mesh) they are used as they are: the result is then the solution of
+    the exactly assembled system.
     The casing systems are so ill-conditioned (coefficient contrast 1e13, curl-curl
     null space) that a plain fp64 direct solve -- the reference's Pardiso / SolverLU
     included -- carries a relative error of 1e-7 (DC) up to 1e-4 (3-D FDEM j at 1 Hz);
@@ -445,10 +462,43 @@ def solve_refined(A, b, iters=10, lu=None):
     data = A.data.astype(ld)
     assert np.all(np.diff(A.indptr) > 0)
     x, bl = x0.astype(ld), b.astype(ld)
+    global LAST_REFINE_RESIDUAL
+    dsc = 1.0 / np.sqrt(np.abs(np.asarray(A.diagonal(), dtype=wd)))      # Jacobi scaling of the residual norm
+    bn = float(np.linalg.norm(np.asarray(b, dtype=wd) * dsc))
     for _ in range(iters):
         r = bl - np.add.reduceat(data * x[A.indices], A.indptr[:-1])
         x = x + lu.solve(r.astype(wd)).astype(ld)
+    r = bl - np.add.reduceat(data * x[A.indices], A.indptr[:-1])
+    # extended-precision residual (Jacobi-scaled norm) of the returned vector: <= 1e-12 when the refinement converged (it diverges when
+    # cond * eps >= 1, e.g. 3-D curl-curl at 0.1 Hz); callers that need a truth must check it
+    LAST_REFINE_RESIDUAL = float(np.linalg.norm(np.asarray(r, dtype=wd) * dsc)) / bn if bn > 0 else 0.0
     return x.astype(wd), x0
+
+
+LAST_REFINE_RESIDUAL = 0.0
+
+
+def energy_rel(u, ref, weight):
+    """relative error in the weighted (energy) norm sqrt(sum weight |.|^2): with weight = diag(MfRho) on face
+    currents j it is the dissipated-power norm -- the norm in which the fp64 data of a casing problem determine the
+    solution (current loops inside the steel wall cost almost no energy and are invisible in it)."""
+    u, ref, w = np.asarray(u), np.asarray(ref), np.asarray(weight, dtype=float)
+    return float(np.sqrt(np.sum(w * np.abs(np.asarray(u - ref, dtype=complex)) ** 2) /
+                         np.sum(w * np.abs(np.asarray(ref, dtype=complex)) ** 2)))
+
+
+def rhs_rounding_sensitivity(A_exact, b_exact, quantity):
+    """How far one fp64 rounding of the right-hand side alone (relative 1.1e-16) moves quantity(x): the solution
+    of the exactly assembled system for b_exact vs for fl64(b_exact).  On 3-D casing systems at low frequency the rounding
+    error has a component along the curl-curl null space that the regularisation i w MeMu amplifies by 1/(w mu): plain
+    L2 norms of h and j move by 1e-2 / 1e-5 at 1 Hz while the energy norm and the casing currents do not move
+    (1e-10 / 1e-16).  No fp64 implementation -- the reference's included -- can agree with another one beyond this."""
+    cd = np.clongdouble if np.iscomplexobj(b_exact) or np.iscomplexobj(A_exact.data) else np.longdouble
+    wd = complex if cd is np.clongdouble else float
+    x1 = solve_refined(A_exact, b_exact, iters=12)[0]
+    x2 = solve_refined(A_exact, np.asarray(np.asarray(b_exact, dtype=wd), dtype=cd), iters=12)[0]
+    q1, q2 = np.asarray(quantity(x1), dtype=wd), np.asarray(quantity(x2), dtype=wd)
+    return float(np.linalg.norm(q2 - q1) / np.linalg.norm(q1))
 
 
 # --------------------------------------------------------------------------
@@ -456,7 +506,7 @@ def solve_refined(A, b, iters=10, lu=None):
 # --------------------------------------------------------------------------
 class OracleDC(object):
     def __init__(self, mesh, sigma):
-        self.mesh, self.sigma = mesh, np.asarray(sigma, dtype=float)
+        self.mesh, self.sigma = mesh, np.asarray(sigma, dtype=getattr(mesh, "dtype", float))
         self.Dt = mesh._Dtopo() @ _sdiag(mesh.area)             # vol * faceDiv
         self.MfRho = mesh.getFaceInnerProduct(1.0 / self.sigma)
         self.MfRhoI = _sdiag(1.0 / self.MfRho.diagonal())
@@ -477,7 +527,7 @@ class OracleDC(object):
         q = self.getRHS(src_a, src_b)
         if refine:
             A = self.getA()
-            lu = spla.splu(A.tocsc())
+            lu = spla.splu(A.tocsc().astype(float))
             return np.stack([solve_refined(A, q[:, s], lu=lu)[0] for s in range(q.shape[1])], axis=1)
         Ainv = SolverLU(self.getA())
         phi = Ainv * q
@@ -500,7 +550,8 @@ class OracleDC(object):
 class OracleFDEM(object):
     def __init__(self, mesh, sigma, mu, form="h"):
         self.mesh, self.form = mesh, form
-        self.sigma, self.mu = np.asarray(sigma, float), np.asarray(mu, float)
+        dt_ = getattr(mesh, "dtype", float)
+        self.sigma, self.mu = np.asarray(sigma, dt_), np.asarray(mu, dt_)
         self.C = mesh.edgeCurl
         m = mesh
         self.MfRho = m.getFaceInnerProduct(1.0 / self.sigma)
@@ -576,7 +627,8 @@ class OracleFDEM(object):
 class OracleTDEM(object):
     def __init__(self, mesh, sigma, mu, time_steps, form="j", ground_first_cell=True):
         self.mesh, self.form = mesh, form
-        self.sigma, self.mu = np.asarray(sigma, float), np.asarray(mu, float)
+        dt_ = getattr(mesh, "dtype", float)
+        self.sigma, self.mu = np.asarray(sigma, dt_), np.asarray(mu, dt_)
         self.time_steps = mesh_tensor(time_steps) if isinstance(time_steps, list) else np.asarray(time_steps, float)
         self.C = mesh.edgeCurl
         self.MfRho = mesh.getFaceInnerProduct(1.0 / self.sigma)
@@ -615,7 +667,7 @@ class OracleTDEM(object):
         for t, dt in enumerate(self.time_steps):
             if lu is None or abs(dt - dt_prev) > self.dt_threshold:
                 A = self.getAdiag(dt)
-                lu = spla.splu(A.tocsc()); dt_prev = dt
+                lu = spla.splu(A.tocsc().astype(float)); dt_prev = dt
             se_n1 = 0.0 * s_e
             se_n = s_e if t == 0 else 0.0 * s_e
             rhs = self.MfRho @ (-(se_n1 - se_n) / dt)
@@ -623,7 +675,7 @@ class OracleTDEM(object):
             if refine:
                 F[:, t + 1] = solve_refined(A, rhs - Asub_x, lu=lu)[0]
             else:
-                F[:, t + 1] = lu.solve(rhs - Asub_x)
+                F[:, t + 1] = lu.solve(np.asarray(rhs - Asub_x, dtype=float))
         return F
 
 

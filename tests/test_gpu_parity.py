@@ -1,8 +1,16 @@
 """GPU parity tests: every CUDA kernel / driver behind the C ABI against the CPU
 oracle (oracle/cyl_oracle.py) on the same seeded inputs.  Tolerances: fp64 stencil
-applies 1e-12 relative (sum-order differences only); solves: Krylov relres <= 1e-10
-and solution rel-L2 vs the oracle's SuperLU solve <= 1e-6 (BASELINE.json north_star)
-wherever the system's conditioning allows the oracle itself that accuracy."""
+applies 1e-12 relative (sum-order differences only); solves: Krylov relres <= 1e-10 and
+rel-L2 <= 1e-6 (BASELINE.json north_star, FIXED) against the solution of the EXACTLY assembled
+discrete system (oracle.exact_mesh: long-double assembly + long-double refinement).  The
+fp64-assembled oracle -- the reference's own arithmetic -- is itself 1e-6 (DC) .. 7e-4 (3-D
+FDEM j at 1 Hz) away from that truth, because entry roundings of 1e-16 relative to the LARGE
+conductances act as spurious leaks next to a 1e13 coefficient contrast; the matrix-free
+difference-form GPU operators do not have that error.  Where even one fp64 rounding of the
+DATA moves a plain L2 norm by more than 1e-6 (3-D curl-curl at low frequency: a null-space
+component amplified by 1/(w mu), oracle.rhs_rounding_sensitivity; rounding the weights does the
+same) the plain norm is only reported, and the 1e-6 contract is asserted on the quantities the data
+do determine: e, j in the energy (MfRho) norm, and the casing currents -- measured 1e-10 .. 1e-14."""
 import numpy as np
 import pytest
 
@@ -105,28 +113,25 @@ def test_operator_apply(gpu_ctx, nth, kind):
 
 @pytest.mark.parametrize("nth", [1, 4])
 def test_dc_solve(gpu_ctx, nth):
-    from oracle.cyl_oracle import OracleDC
+    from oracle.cyl_oracle import OracleDC, exact_mesh
     om, sig, mu, *_ = setup(gpu_ctx, nth)
-    P = OracleDC(om, sig)
+    P, PX = OracleDC(om, sig), OracleDC(exact_mesh(om), sig)
     a = np.array([[0.03, np.pi / 4 if nth > 1 else 0.0, -0.25], [0.03, 0.0, -1.2]])
     b = np.array([[2.0, 5 * np.pi / 4 if nth > 1 else 0.0, -0.25], [1.0, 0.0, -0.25]])
     q = P.getRHS(a, b)
-    phi_lu = P.fields(a, b)                    # the reference's solver (SuperLU), plain fp64
-    phi_ref = P.fields(a, b, refine=True)      # extended-precision refined "truth"
+    phi_lu = P.fields(a, b)                    # the reference's solver (SuperLU) on its fp64-assembled matrix
+    phi_ref = PX.fields(a, b, refine=True)     # solution of the exactly assembled system
     phi = gpu_ctx.solve_dc(gpu_ctx.to_device(q.T.copy())).cpu().numpy().T
-    print("dc info", gpu_ctx.info, "gpu vs truth", rel(phi, phi_ref), "splu vs truth", rel(phi_lu, phi_ref))
+    print("dc info", gpu_ctx.info, "gpu vs exact", rel(phi, phi_ref), "fp64-assembled SuperLU vs exact", rel(phi_lu, phi_ref))
     assert gpu_ctx.info["relres"] <= 1e-10
-    # 5e-6: the matrix-free operator and the oracle's assembled CSR matrix differ in the
-    # last bit of their entries (diagonal = rounded sum of conductances); with
-    # cond(A) ~ 1e10 that alone moves the solution by ~1e-6 -- the same distance the
-    # reference's own SuperLU solve is from the refined truth (printed above).
-    assert rel(phi, phi_ref) < 5e-6, rel(phi, phi_ref)
-    # derived fields: differences of nearly equal potentials inside the casing lose
+    assert rel(phi, phi_ref) < 1e-6, rel(phi, phi_ref)          # measured 5e-10 .. 1e-9 (the reference's solver: 1e-7 .. 2e-6)
+    # derived fields of the SAME potentials: differences of nearly equal potentials inside the casing lose
     # digits to cancellation in either implementation -> 1e-7
     j = gpu_ctx.fields_dc("j", gpu_ctx.to_device(phi.T.copy())).cpu().numpy().T
     assert rel(j, P.j(phi)) < 1e-7
     e = gpu_ctx.fields_dc("e", gpu_ctx.to_device(phi.T.copy())).cpu().numpy().T
     assert rel(e, P.e(phi)) < 1e-7
+    assert rel(j, PX.j(phi_ref)) < 1e-6, rel(j, PX.j(phi_ref))  # and against the exact system's current density
     ch = gpu_ctx.fields_dc("charge", gpu_ctx.to_device(phi.T.copy())).cpu().numpy().T
     print("charge rel", rel(ch, P.charge(phi)))
 
@@ -145,7 +150,7 @@ def source_wire(om):
 @pytest.mark.parametrize("nth", [1, 4])
 @pytest.mark.parametrize("form", ["h", "j"])
 def test_fdem_solve(gpu_ctx, nth, form):
-    from oracle.cyl_oracle import OracleFDEM
+    from oracle.cyl_oracle import OracleFDEM, exact_mesh, energy_rel, rhs_rounding_sensitivity, casing_currents
     om, sig, mu, *_ = setup(gpu_ctx, nth)
     se = source_wire(om)
     # the j formulation is numerically useless in fp64 at low frequency for ANY direct
@@ -154,21 +159,20 @@ def test_fdem_solve(gpu_ctx, nth, form):
     # algebraically equivalent h formulation.
     freqs = np.r_[1.0, 100.0, 1e4] if form == "h" else np.r_[1e5, 1e6]
     P = OracleFDEM(om, sig, mu, form)
+    PX = OracleFDEM(exact_mesh(om), sig, mu, "h")          # the exactly assembled h system: the truth
     Ph = OracleFDEM(om, sig, mu, "h")
+    rho = np.asarray(Ph.MfRho.diagonal())
     rtol = 1e-10 if form == "h" else 1e-6
     u = gpu_ctx.solve_fdem(form, freqs, gpu_ctx.to_device(se), rtol=rtol).cpu().numpy()
     print("fdem info", form, nth, gpu_ctx.info)
     assert gpu_ctx.info["relres"] <= rtol
+    cas = (CASING["casing_a"], CASING["casing_b"], CASING["casing_z"])
     for f, freq in enumerate(freqs):
-        h_true = Ph.solve(freq, se, refine=True)
+        h_true = PX.solve(freq, se, refine=True)
+        j_true = np.asarray(PX.j_from(freq, h_true, se), dtype=complex)
         h_lu = Ph.solve(freq, se)
-        j_true, j_lu = Ph.j_from(freq, h_true, se), Ph.j_from(freq, h_lu, se)
-        uref = h_true if form == "h" else j_true
-        jref, jg = j_true, P.j_from(freq, u[f], se)
-        # self-calibrating tolerance: 1e-6 (north_star) unless the reference's own
-        # fp64 direct solve is further than that from the refined truth
-        tol = max(1e-6, 10 * rel(j_lu, j_true)) if form == "h" else 1e-4
-        print("  f", freq, "u rel", rel(u[f], uref), "j rel", rel(jg, jref), "splu j vs truth", rel(j_lu, j_true), "tol", tol)
+        j_lu = Ph.j_from(freq, h_lu, se)
+        jg = P.j_from(freq, u[f], se)
         jd = gpu_ctx.fields_fdem(form, "j", freq, gpu_ctx.to_device(u[f]), gpu_ctx.to_device(se)).cpu().numpy()
         assert rel(jd, jg) < 1e-12
         ed = gpu_ctx.fields_fdem(form, "e", freq, gpu_ctx.to_device(u[f]), gpu_ctx.to_device(se)).cpu().numpy()
@@ -177,26 +181,70 @@ def test_fdem_solve(gpu_ctx, nth, form):
         assert rel(hd, P.h_from(freq, u[f], se)) < 1e-7      # C^T MfRho j cancels heavily for the j form
         bd = gpu_ctx.fields_fdem(form, "b", freq, gpu_ctx.to_device(u[f]), gpu_ctx.to_device(se)).cpu().numpy()
         assert rel(bd, P.b_from(freq, u[f], se)) < 1e-7
-        if nth == 1 and form == "h":
-            assert rel(u[f], uref) < 1e-6, rel(u[f], uref)
-        assert rel(jg, jref) < tol, (rel(jg, jref), tol)
+        if form == "j":
+            print("  f", freq, "j rel", rel(jg, j_true))
+            assert rel(jg, j_true) < 1e-4, rel(jg, j_true)
+            continue
+        # what ONE fp64 rounding of the right-hand side does to the plain L2 norm of j (a property of the problem)
+        sens = rhs_rounding_sensitivity(PX.getA(freq), PX.getRHS(freq, se), lambda x: PX.j_from(freq, x, se))
+        e_true = np.asarray(PX.e_from(freq, h_true, se), dtype=complex)
+        iz_true = casing_currents(j_true, om, *cas)["z"][1]
+        iz = casing_currents(jd, om, *cas)["z"][1]
+        print("  f %g: h %.2e | j plain %.2e (data-rounding sensitivity %.2e; fp64 SuperLU %.2e) | j energy %.2e | e %.2e | casing Iz %.2e"
+              % (freq, rel(u[f], h_true), rel(jd, j_true), sens, rel(j_lu, j_true), energy_rel(jd, j_true, rho), rel(ed, e_true), rel(iz, iz_true)))
+        # the 1e-6 contract on everything the fp64 data determine
+        assert rel(ed, e_true) < 1e-6
+        assert energy_rel(jd, j_true, rho) < 1e-6
+        assert rel(iz, iz_true) < 1e-6
+        if sens < 1e-7:                                      # plain L2 only where the fp64 data determine it (3-D: >= 10 kHz here)
+            assert rel(jd, j_true) < 1e-6, (rel(jd, j_true), sens)
+        if nth == 1:
+            assert sens < 1e-12 and rel(u[f], h_true) < 1e-6 and rel(jd, j_true) < 1e-6
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_fdem_refinement_double_double(gpu_ctx, nth):
+    """cs_ctx_set_refine: iterative refinement with the residual in double-double.  On the 2-D mesh it reaches the exact
+    solution to fp64 representation accuracy (1e-15); in 3-D it converges (corrections shrink to the null-space noise
+    level) and must not move the data-determined quantities."""
+    from oracle.cyl_oracle import OracleFDEM, exact_mesh, energy_rel
+    om, sig, mu, *_ = setup(gpu_ctx, nth)
+    se = source_wire(om)
+    PX = OracleFDEM(exact_mesh(om), sig, mu, "h")
+    rho = np.asarray(OracleFDEM(om, sig, mu, "h").MfRho.diagonal())
+    freqs = np.r_[1.0, 100.0]
+    gpu_ctx.set_refine(8)
+    try:
+        u = gpu_ctx.solve_fdem("h", freqs, gpu_ctx.to_device(se)).cpu().numpy()
+        info = dict(gpu_ctx.info)
+    finally:
+        gpu_ctx.set_refine(0)
+    print("refine info", info)
+    assert info["dd_steps"] >= 1
+    for f, freq in enumerate(freqs):
+        h_true = PX.solve(freq, se, refine=True)
+        j_true = np.asarray(PX.j_from(freq, h_true, se), dtype=complex)
+        jg = np.asarray(PX.j_from(freq, u[f], se), dtype=complex)
+        print("  f", freq, "h", rel(u[f], h_true), "j", rel(jg, j_true), "j energy", energy_rel(jg, j_true, rho))
+        assert energy_rel(jg, j_true, rho) < 1e-9
+        if nth == 1:
+            assert rel(u[f], h_true) < 1e-14 and rel(jg, j_true) < 1e-13
 
 
 @pytest.mark.parametrize("nth", [1, 4])
 def test_tdem_run(gpu_ctx, nth):
-    from oracle.cyl_oracle import OracleTDEM
+    from oracle.cyl_oracle import OracleTDEM, exact_mesh
     om, sig, mu, *_ = setup(gpu_ctx, nth)
     se = source_wire(om)
     steps = [(1e-5, 3), (1e-4, 3)]
     P = OracleTDEM(om, sig, mu, steps)
-    Flu = P.fields(se)
-    Fref = P.fields(se, refine=True)
+    Flu = P.fields(se)                                                   # the reference's arithmetic: fp64 assembly + SuperLU
+    Fref = OracleTDEM(exact_mesh(om), sig, mu, steps).fields(se, refine=True)   # exactly assembled systems
     F = gpu_ctx.tdem_run("j", P.time_steps, gpu_ctx.to_device(se)).cpu().numpy().T
     print("tdem info", gpu_ctx.info)
     for t in range(Fref.shape[1]):
-        print("  step", t, "gpu vs truth", rel(F[:, t], Fref[:, t]), "splu vs truth", rel(Flu[:, t], Fref[:, t]))
-    tol = max(1e-6, 10 * rel(Flu, Fref))
-    assert rel(F, Fref) < tol, (rel(F, Fref), tol)
+        print("  step", t, "gpu vs exact", rel(F[:, t], Fref[:, t]), "fp64 SuperLU vs exact", rel(Flu[:, t], Fref[:, t]))
+    assert rel(F, Fref) < 1e-6, rel(F, Fref)                             # measured 3e-7 (fp64 SuperLU: 1e-5 / 4e-3)
 
 
 @pytest.mark.parametrize("nth", [1, 4])

@@ -134,17 +134,19 @@ def test_simulation_dc_and_casing_currents(tmp_path):
     f = sim.run()
     assert sim.prob.info["relres"] <= 1e-10 or sim.prob.info["backward_err"] <= 2e-15     # fp64 floor, see DESIGN.md
     assert np.array_equal(np.load(os.path.join(tmp, "fieldsDC.npy")), f[:, "phiSolution"])
-    from oracle.cyl_oracle import OracleCylMesh, OracleDC, casing_currents
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, casing_currents, exact_mesh
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
-    P = OracleDC(om, mp.sigma(m))
+    P = OracleDC(exact_mesh(om), mp.sigma(m))                          # the exactly assembled system
     phi = P.fields(a, b, refine=True)
-    assert rel(f[:, "phi"], phi) < 5e-6
+    print("DC sim: phi vs exact", rel(f[:, "phi"], phi))
+    assert rel(f[:, "phi"], phi) < 1e-6
     j = f[:, "j"]
-    assert rel(j, P.j(phi)) < 1e-4
+    jref = np.asarray(P.j(phi), dtype=float)
+    assert rel(j, jref) < 1e-6
     cur = cs.casing_currents(j, m, mp)
-    ref = casing_currents(P.j(phi), om, mp.casing_a, mp.casing_b, mp.casing_z)
-    assert np.array_equal(cur["z"][0], ref["z"][0]) and rel(cur["z"][1][:, 0], ref["z"][1]) < 1e-4
-    assert rel(cur["x"][1][:, 0], ref["x"][1]) < 1e-4
+    ref = casing_currents(jref, om, mp.casing_a, mp.casing_b, mp.casing_z)
+    assert np.array_equal(cur["z"][0], ref["z"][0]) and rel(cur["z"][1][:, 0], ref["z"][1]) < 1e-6
+    assert rel(cur["x"][1][:, 0], ref["x"][1]) < 1e-6
     assert 0.5 < -cur["z"][1][-1, 0] <= 1.0 + 1e-6                     # ~1 A enters the casing top
     z, q = cs.casing_charges(f[:, "charge"][:, 0], m, mp)
     assert len(z) == len(q)
@@ -161,12 +163,16 @@ def test_simulation_tdem(tmp_path, nth):
     jsol = f[:, "jSolution"]
     assert jsol.shape == (mg.mesh.nF, 7)
     assert np.array_equal(np.load(os.path.join(tmp, "fields.npy")), jsol)
-    from oracle.cyl_oracle import OracleCylMesh, OracleTDEM
+    from oracle.cyl_oracle import OracleCylMesh, OracleTDEM, exact_mesh
     m = mg.mesh
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
-    T = OracleTDEM(om, mp.sigma(m), mp.mu(m), mp.timeSteps)
-    Flu, Fref = T.fields(src.s_e), T.fields(src.s_e, refine=True)
-    tol = max(1e-6, 10 * rel(Flu, Fref))
+    Fref = OracleTDEM(exact_mesh(om), mp.sigma(m), mp.mu(m), mp.timeSteps).fields(src.s_e, refine=True)
+    # fixed tolerance vs the exactly assembled systems: every backward-Euler solve of the face-form system leaves ~1e-7
+    # (plain L2) that the fp64 residual cannot see, and the steps add up -- 3e-6 over these 6 steps (measured 1.1e-6 /
+    # 1.6e-6; the reference's arithmetic -- fp64 assembly + SuperLU -- 1e-5 / 4e-3).  (The energy norm is no help here:
+    # the j formulation's weak spot is the galvanic part in the resistive air cells, which that norm weighs by 1e6.)
+    print("TDEM sim vs exact: plain", rel(jsol, Fref))
+    tol = 3e-6
     assert rel(jsol, Fref) < tol, (rel(jsol, Fref), tol)
     assert rel(f[:, "j", 3][:, 0], Fref[:, 3]) < tol
     e = f[:, "e"]
@@ -192,7 +198,11 @@ def test_solver_plugin_protocol(nth):
     x = Ainv * q
     assert x.shape == q.shape
     for c in range(2):
-        assert rel(x[:, c], solve_refined(A, q[:, c])[0]) < 5e-6
+        # here the system IS the fp64-assembled matrix handed to the plugin (its SpMV is the operator), so the truth is that
+        # matrix' refined solution; cond * eps bounds what any fp64 solver can do with it (SuperLU: 7e-7 on this matrix)
+        err = rel(x[:, c], solve_refined(A, q[:, c])[0])
+        print("plugin DC column", c, "vs refined solution of the same matrix", err)
+        assert err < 1e-6, err
     x1 = Ainv * q[:, 0]
     assert x1.shape == (om.nC,) and rel(x1, x[:, 0]) < 1e-9
     with pytest.raises(TypeError):
@@ -231,12 +241,12 @@ def test_full_size_c1_dc():
     info = sim.prob.info
     print("C1 info", info)
     assert info["relres"] <= 1e-10 or info["backward_err"] <= 2e-15
-    from oracle.cyl_oracle import OracleCylMesh, OracleDC
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, exact_mesh
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
-    P = OracleDC(om, mp.sigma(m))
-    phi_lu, phi = P.fields(a, b), P.fields(a, b, refine=True)
-    print("C1 gpu vs truth", rel(f[:, "phi"], phi), "splu vs truth", rel(phi_lu, phi))
-    assert rel(f[:, "phi"], phi) < max(5e-6, 10 * rel(phi_lu, phi))
+    phi_lu = OracleDC(om, mp.sigma(m)).fields(a, b)
+    phi = OracleDC(exact_mesh(om), mp.sigma(m)).fields(a, b, refine=True)
+    print("C1 gpu vs exact", rel(f[:, "phi"], phi), "fp64-assembled SuperLU vs exact", rel(phi_lu, phi))
+    assert rel(f[:, "phi"], phi) < 1e-6
     cur = cs.casing_currents(f[:, "j"], m, mp)
     assert 0.9 < -cur["z"][1][-1, 0] <= 1.0 + 1e-6
     sim.prob.clean()
@@ -283,7 +293,7 @@ def test_theta_varying_flawed_casing_krylov(tmp_path):
     tmp = str(tmp_path / "flaw")
     nth = 8
     mp = cs.model.FlawedCasingInHalfspace(directory=tmp, sigma_back=1e-1, src_a=np.r_[0.0, 0.0, 0.0],
-                                          src_b=np.r_[1000.0, 0.0, 0.0], freqs=np.r_[5.0], casing_l=100.0,
+                                          src_b=np.r_[1000.0, 0.0, 0.0], freqs=np.r_[50.0], casing_l=100.0,
                                           flaw_r=np.r_[0.04, 0.06], flaw_z=np.r_[-60.0, -40.0],
                                           flaw_theta=np.r_[np.pi / 2, np.pi], sigma_flaw=1e-1)
     mg = cs.CasingMeshGenerator(directory=tmp, modelParameters=mp, hy=np.ones(nth) * 2 * np.pi / nth, npadx=4, npadz=5, csz=10.0)
@@ -297,42 +307,52 @@ def test_theta_varying_flawed_casing_krylov(tmp_path):
     a = np.array([[0.05125, th, -5.0]])
     b = np.array([[500.0, th, -5.0]])
     sim = run.SimulationDC(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a, src_b=b,
-                           solver_opts=dict(maxit=300, rtol=1e-7))
+                           solver_opts=dict(maxit=300, rtol=1e-10))
     f = sim.run(save=False)
     info = sim.prob.info
     print("flawed DC info", info)
     assert info["iters"] >= 2                              # not a one-shot direct solve any more
-    from oracle.cyl_oracle import OracleCylMesh, OracleDC, OracleFDEM
+    import oracle.cyl_oracle as oc
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, OracleFDEM, exact_mesh, energy_rel, casing_currents
     om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
-    P = OracleDC(om, mp.sigma(m))
-    phi_lu, phi = P.fields(a, b), P.fields(a, b, refine=True)
+    ox = exact_mesh(om)
+    phi_lu = OracleDC(om, mp.sigma(m)).fields(a, b)
+    phi = OracleDC(ox, mp.sigma(m)).fields(a, b, refine=True)          # exactly assembled system
     err = rel(f[:, "phi"], phi)
-    print("flawed DC gpu vs truth", err, "splu vs truth", rel(phi_lu, phi))
-    assert err < max(1e-4, 10 * rel(phi_lu, phi))
+    print("flawed DC gpu vs exact", err, "fp64-assembled SuperLU vs exact", rel(phi_lu, phi))
+    assert err < 1e-6, err                                             # Krylov rtol 1e-10 through the approximate (circulant) preconditioner
     sim.prob.clean()
     # FDEM-h
     src = sources.TopCasingSrc(directory=tmp, modelParameters=mp, meshGenerator=mg)
-    simf = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src, solver_opts=dict(maxit=300, rtol=1e-7))
+    simf = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src,
+                              solver_opts=dict(maxit=300, rtol=1e-10))
     ff = simf.run(save=False)
     print("flawed FDEM info", simf.prob.info)
-    Pf = OracleFDEM(om, mp.sigma(m), mp.mu(m))
+    Pf, PX = OracleFDEM(om, mp.sigma(m), mp.mu(m)), OracleFDEM(ox, mp.sigma(m), mp.mu(m))
     s = simf.survey.srcList[0]
-    h_lu, h_true = Pf.solve(s.freq, np.real(s.s_e)), Pf.solve(s.freq, np.real(s.s_e), refine=True)
-    j_lu, j_true = Pf.j_from(s.freq, h_lu, np.real(s.s_e)), Pf.j_from(s.freq, h_true, np.real(s.s_e))
-    jg = ff[s, "j"][:, 0]
-    A, rhs = Pf.getA(s.freq), Pf.getRHS(s.freq, np.real(s.s_e))
+    se = np.real(s.s_e)
+    A, rhs = Pf.getA(s.freq), Pf.getRHS(s.freq, se)
     d = np.sqrt(np.abs(A.diagonal()))
     res = np.linalg.norm((A @ ff[s, "h"][:, 0] - rhs) / d) / np.linalg.norm(rhs / d)
-    print("flawed FDEM scaled residual", res, "j gpu vs splu", rel(jg, j_lu), "gpu vs refined", rel(jg, j_true),
-          "splu vs refined", rel(j_lu, j_true))
-    assert res < 1e-6
-    # the extended-precision refinement does not always converge for this 3-D system (SuperLU's
-    # factors are too inaccurate); compare with whichever reference is self-consistent
-    # (measured: refinement diverges here; GPU (scaled residual 7e-10) and SuperLU disagree by
-    # 7 % in j -- the 5 Hz 3-D curl-curl system with 2.5 mm air cells is beyond fp64 for a direct
-    # solve).  The residual is the hard criterion, j only a sanity bound.
-    ref = j_true if rel(j_lu, j_true) < 1e-2 else j_lu
-    assert rel(jg, ref) < 0.2
+    h_true = PX.solve(s.freq, se, refine=True)
+    truth_res = oc.LAST_REFINE_RESIDUAL
+    j_true = np.asarray(PX.j_from(s.freq, h_true, se), dtype=complex)
+    j_lu = Pf.j_from(s.freq, Pf.solve(s.freq, se), se)
+    jg = ff[s, "j"][:, 0]
+    rho = np.asarray(Pf.MfRho.diagonal())
+    iz = casing_currents(jg, om, mp.casing_a, mp.casing_b, mp.casing_z)["z"][1]
+    iz_true = casing_currents(j_true, om, mp.casing_a, mp.casing_b, mp.casing_z)["z"][1]
+    print("flawed FDEM scaled residual", res, "| truth refinement residual", truth_res, "| j plain gpu vs exact", rel(jg, j_true),
+          "(fp64 SuperLU", rel(j_lu, j_true), ") | j energy norm", energy_rel(jg, j_true, rho), "| casing Iz", rel(iz, iz_true))
+    assert res < 1e-10
+    assert truth_res < 1e-12, "the long-double refinement of the exact system did not converge: no truth for this case"
+    # 50 Hz: the long-double refinement of the exact system converges (at 5 Hz it diverges: no truth exists there).
+    # Fixed tolerances, GMRES to rtol 1e-10 through the circulant preconditioner (measured 3e-7 / 3e-7 / 2e-5; the
+    # reference's arithmetic -- fp64 assembly + SuperLU -- is 2e-3 away in j).  The energy norm weighs the resistive air
+    # faces, which an iterative solve at a given residual resolves last.
+    assert rel(jg, j_true) < 1e-6
+    assert rel(iz, iz_true) < 1e-6
+    assert energy_rel(jg, j_true, rho) < 1e-4
     simf.prob.clean()
 
 
@@ -357,13 +377,26 @@ def test_against_committed_golden_vectors(nth):
     q[0, closestPoints(mesh, g[tag + "dc_a"][0])[0]] = 1.0
     q[0, closestPoints(mesh, g[tag + "dc_b"][0])[0]] = -1.0
     phi = ctx.solve_dc(ctx.to_device(q)).cpu().numpy()[0]
-    assert rel(phi, g[tag + "dc_phi"]) < 5e-6
+    assert rel(phi, g[tag + "dc_phi"]) < 1e-6
     se = ctx.to_device(g[tag + "s_e"])
-    u = ctx.solve_fdem("h", [100.0], se)
-    j = ctx.fields_fdem("h", "j", 100.0, u[0], se).cpu().numpy()
-    assert rel(j, g[tag + "fdem_j_100Hz"]) < (1e-6 if nth == 1 else 1e-4)
-    if nth == 1:
-        assert rel(u[0].cpu().numpy(), g[tag + "fdem_h_100Hz"]) < 1e-6
+    from oracle.cyl_oracle import OracleCylMesh, casing_currents, energy_rel
+    om = OracleCylMesh([hx, hy, hz], [0, 0, z0])
+    freqs = [1.0, 100.0]
+    u = ctx.solve_fdem("h", freqs, se)
+    for f, name in enumerate(("1Hz", "100Hz")):
+        j = ctx.fields_fdem("h", "j", freqs[f], u[f], se).cpu().numpy()
+        e = ctx.fields_fdem("h", "e", freqs[f], u[f], se).cpu().numpy()
+        iz = casing_currents(j, om, CASING["casing_a"], CASING["casing_b"], CASING["casing_z"])["z"][1]
+        sens = float(g[tag + "fdem_j_sens_" + name])           # effect of ONE fp64 rounding of the rhs on plain-L2 j
+        print(tag, name, "j plain", rel(j, g[tag + "fdem_j_" + name]), "sens", sens, "energy", energy_rel(j, g[tag + "fdem_j_" + name], g[tag + "MfRho"]),
+              "e", rel(e, g[tag + "fdem_e_" + name]), "Iz", rel(iz, g[tag + "fdem_Iz_" + name]))
+        assert rel(e, g[tag + "fdem_e_" + name]) < 1e-6
+        assert energy_rel(j, g[tag + "fdem_j_" + name], g[tag + "MfRho"]) < 1e-6
+        assert rel(iz, g[tag + "fdem_Iz_" + name]) < 1e-6
+        if sens < 1e-7:                                        # plain L2 only where the fp64 data determine it
+            assert rel(j, g[tag + "fdem_j_" + name]) < 1e-6
+        if nth == 1:
+            assert rel(u[f].cpu().numpy(), g[tag + "fdem_h_" + name]) < 1e-6 and rel(j, g[tag + "fdem_j_" + name]) < 1e-6
     F = ctx.tdem_run("j", np.r_[np.ones(3) * 1e-5, np.ones(3) * 1e-4], se).cpu().numpy().T
     assert rel(F, g[tag + "tdem_j"]) < 1e-6
     ctx.close()
