@@ -642,3 +642,117 @@ def test_plain_c_client_of_the_c_abi(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     print(res.stdout, res.stderr)
     assert res.returncode == 0 and "C ABI OK" in res.stdout
+
+
+def test_reference_smoke_setup_at_full_size(tmp_path):
+    """The reference's own smoke test at its real size (tests/test_SimulationRun.py:18-81): CasingInWholespace,
+    CasingMeshGenerator(npadx=8, npadz=19, csz=0.25) = 107 x 1 x 4048 = 433 136 cells, 0.5 Hz, the three source classes.
+    Its assertion (saved fields.npy == fields[:, 'h']) plus parity of h, j, e against the exactly assembled system."""
+    tmp = str(tmp_path / "sim2D")
+    mp = cs.model.CasingInWholespace(directory=tmp, src_a=np.r_[0.0, np.pi, 0.0], src_b=np.r_[1e3, np.pi, 0.0], freqs=np.r_[0.5],
+                                     sigma_back=1e-1)
+    mg = cs.CasingMeshGenerator(directory=tmp, modelParameters=mp, npadx=8, npadz=19, csz=0.25)
+    m = mg.mesh
+    assert tuple(m.vnC) == (107, 1, 4048) and m.nC == 433136 and m.nE == 433243          # SURVEY Appendix B
+    from oracle.cyl_oracle import OracleCylMesh, OracleFDEM, exact_mesh
+    import oracle.cyl_oracle as oc
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    PX = OracleFDEM(exact_mesh(om), mp.sigma(m), mp.mu(m))
+    for klass in (sources.TopCasingSrc, sources.DownHoleCasingSrc, sources.DownHoleTerminatingSrc):
+        src = klass(directory=tmp, modelParameters=mp, meshGenerator=mg)
+        src.validate()
+        sim = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src)
+        fields = sim.run()
+        loaded = np.load("/".join([tmp, "fields.npy"]))
+        assert np.all(fields[:, "h"] == loaded)                                            # tests/test_SimulationRun.py:51
+        assert sim.prob.info["relres"] <= 1e-10
+        s = sim.survey.srcList[0]
+        se = np.real(s.s_e)
+        h = PX.solve(s.freq, se, refine=True)
+        assert oc.LAST_REFINE_RESIDUAL < 1e-12
+        errs = (rel(fields[s, "h"][:, 0], h), rel(fields[s, "j"][:, 0], np.asarray(PX.j_from(s.freq, h, se), dtype=complex)),
+                rel(fields[s, "e"][:, 0], np.asarray(PX.e_from(s.freq, h, se), dtype=complex)))
+        print(klass.__name__, "433k cells: h, j, e vs exact system", errs, {k: round(float(v), 2) for k, v in sim.prob.info.items() if k.startswith("ms_")})
+        assert max(errs) < 1e-6, (klass.__name__, errs)
+        sim.prob.clean()
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+def test_dipole_sources_gpu(tmp_path, nth):
+    """HorizontalElectricDipole / VerticalElectricDipole (sources.py:130-413) through SimulationFDEM on
+    the GPU, h / e / energy-norm j against the exactly assembled system (plain-L2 j too on the 2-D mesh)."""
+    tmp = str(tmp_path / "dip")
+    from oracle.cyl_oracle import OracleCylMesh, OracleFDEM, exact_mesh, energy_rel
+    hy = np.r_[2 * np.pi] if nth == 1 else np.ones(nth) * 2 * np.pi / nth
+    mp = cs.model.Halfspace(directory=tmp, sigma_back=1e-1, src_a=np.r_[50.0, 0.0, -5.0], src_b=np.r_[150.0, 0.0, -5.0], freqs=np.r_[10.0, 1000.0])
+    mg = cs.CylMeshGenerator(directory=tmp, modelParameters=mp, hy=hy, csx=25.0, csz=10.0, domain_x=300.0, domain_z=60.0, npadx=6, npadz=7)
+    m = mg.mesh
+    th = float(m.vectorCCy[min(1, nth - 1)])
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    PX = OracleFDEM(exact_mesh(om), mp.sigma(m), mp.mu(m))
+    rho = np.asarray(om.getFaceInnerProduct(1.0 / mp.sigma(m)).diagonal())
+    zc = float(m.vectorCCz[np.argmin(np.abs(m.vectorCCz + 5.0))])
+    cases = [(sources.HorizontalElectricDipole, np.r_[50.0, th, zc], np.r_[150.0, th, zc]),
+             (sources.VerticalElectricDipole, np.r_[0.0, th, -45.0], np.r_[0.0, th, -5.0])]
+    for klass, a, b in cases:
+        src = klass(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a.copy(), src_b=b.copy())
+        src.validate()
+        assert np.count_nonzero(src.s_e) > 0
+        sim = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src)
+        fields = sim.run(save=False)
+        assert sim.prob.info["relres"] <= 1e-10
+        for s in sim.survey.srcList:
+            se = np.real(s.s_e)
+            h = PX.solve(s.freq, se, refine=True)
+            jt = np.asarray(PX.j_from(s.freq, h, se), dtype=complex)
+            et = np.asarray(PX.e_from(s.freq, h, se), dtype=complex)
+            ee, ej = rel(fields[s, "e"][:, 0], et), energy_rel(fields[s, "j"][:, 0], jt, rho)
+            print(klass.__name__, nth, s.freq, "e", ee, "j energy", ej, "j plain", rel(fields[s, "j"][:, 0], jt), "h", rel(fields[s, "h"][:, 0], h))
+            assert ee < 1e-6 and ej < 1e-6
+            if nth == 1:
+                assert rel(fields[s, "j"][:, 0], jt) < 1e-6 and rel(fields[s, "h"][:, 0], h) < 1e-6
+        sim.prob.clean()
+
+
+@pytest.mark.parametrize("klass_name", ["SingleLayer", "Layers", "TargetInHalfspace", "CasingInLayers", "CasingInHalfspaceWithTarget"])
+def test_remaining_painters_gpu(tmp_path, klass_name):
+    """the layer / target painters (model.py:263-403, 720-800) drive the GPU path (K1 when the class has
+    paint parameters, otherwise sigma()/mur() uploaded through cs_model_set): DC potentials and FDEM-h fields against
+    the exactly assembled systems with the same painted model."""
+    tmp = str(tmp_path / "paint")
+    from oracle.cyl_oracle import OracleCylMesh, OracleDC, OracleFDEM, exact_mesh
+    kw = dict(directory=tmp, sigma_back=1e-2, src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0], freqs=np.r_[5.0])
+    if klass_name in ("SingleLayer",):
+        kw.update(sigma_layer=1.0, layer_z=np.r_[-60.0, -30.0])
+    if klass_name in ("Layers", "CasingInLayers"):
+        kw.update(sigma_layers=[1e-1, 1.0, 1e-2], layer_tops=[0.0, -30.0, -60.0])
+    if "Target" in klass_name:
+        kw.update(target_radius=np.r_[0.0, 40.0], target_z=np.r_[-80.0, -50.0], sigma_target=10.0)
+    if klass_name.startswith("Casing"):
+        kw.update(casing_l=100.0)
+    mp = getattr(cs.model, klass_name)(**kw)
+    mg = cs.CasingMeshGenerator(directory=tmp, modelParameters=mp, npadx=6, npadz=8, csz=5.0, domain_z=100.0) if klass_name.startswith("Casing") \
+        else cs.CylMeshGenerator(directory=tmp, modelParameters=mp, csx=10.0, csz=5.0, domain_x=100.0, domain_z=100.0, npadx=8, npadz=8)
+    m = mg.mesh
+    sig = mp.sigma(m)
+    assert len(np.unique(sig)) >= 3                                                     # the painter did paint something
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    ox = exact_mesh(om)
+    r0 = float(m.vectorCCx[3])
+    a, b = np.array([[r0, 0.0, -2.5]]), np.array([[float(m.vectorCCx[-6]), 0.0, -2.5]])
+    sim = run.SimulationDC(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=a, src_b=b)
+    f = sim.run(save=False)
+    phi = OracleDC(ox, sig).fields(a, b, refine=True)
+    print(klass_name, "DC phi vs exact", rel(f[:, "phi"], phi))
+    assert rel(f[:, "phi"], phi) < 1e-6
+    sim.prob.clean()
+    src = sources.VerticalElectricDipole(directory=tmp, modelParameters=mp, meshGenerator=mg, src_a=np.r_[0.0, 0.0, -42.5], src_b=np.r_[0.0, 0.0, -2.5])
+    simf = run.SimulationFDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=src)
+    ff = simf.run(save=False)
+    s = simf.survey.srcList[0]
+    PX = OracleFDEM(ox, sig, mp.mu(m))
+    h = PX.solve(s.freq, np.real(s.s_e), refine=True)
+    print(klass_name, "FDEM h vs exact", rel(ff[s, "h"][:, 0], h))
+    assert rel(ff[s, "h"][:, 0], h) < 1e-6
+    assert rel(ff[s, "e"][:, 0], np.asarray(PX.e_from(s.freq, h, np.real(s.s_e)), dtype=complex)) < 1e-6
+    simf.prob.clean()

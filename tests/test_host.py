@@ -300,3 +300,24 @@ def test_c_abi_header_compiles_and_links_from_plain_c(tmp_path):
     """the boundary is a C ABI: include/casing_b200.h is valid C and a C client links against the library"""
     exe = _compile_c_example(str(tmp_path / "c_abi_dc"))
     assert os.path.exists(exe)
+
+
+def test_unsupported_formulations_raise_explicitly(tmp_path):
+    """run.py:226-230, 273-277 accept formulation in e/b/h/j, but casingSimulations' sources are FACE vectors
+    (sources.py:236, RawVec_e(s_e)): SimPEG's e / b problems integrate s_e with the EDGE inner product and cannot take
+    them (a size mismatch nE vs nF).  The facade says so when the problem is built instead of failing inside a kernel."""
+    mp = cs.model.CasingInHalfspace(directory=str(tmp_path), src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0], freqs=np.r_[1.0],
+                                    timeSteps=[(1e-5, 2)])
+    mg = cs.CasingMeshGenerator(directory=str(tmp_path), modelParameters=mp, npadx=4, npadz=6, csz=20.0)
+    for form in ("e", "b"):
+        src = cs.sources.TopCasingSrc(directory=str(tmp_path), modelParameters=mp, meshGenerator=mg, physics="fdem")
+        sim = cs.run.SimulationFDEM(directory=str(tmp_path), modelParameters=mp, meshGenerator=mg, src=src, formulation=form)
+        with pytest.raises(NotImplementedError, match="face vectors"):
+            sim.prob
+    with pytest.raises(ValueError):
+        cs.run.SimulationFDEM(directory=str(tmp_path), modelParameters=mp, meshGenerator=mg, src=src, formulation="x")
+    src = cs.sources.TopCasingSrc(directory=str(tmp_path), modelParameters=mp, meshGenerator=mg, physics="tdem")
+    for form in ("b", "h"):
+        sim = cs.run.SimulationTDEM(directory=str(tmp_path), modelParameters=mp, meshGenerator=mg, src=src, formulation=form)
+        with pytest.raises(NotImplementedError):
+            sim.prob
