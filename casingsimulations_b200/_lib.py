@@ -56,6 +56,10 @@ def load_library():
         "cs_ctx_sync": (c.c_int, [vp]),
         "cs_fp64_peak": (c.c_int, [vp, dp]),
         "cs_ctx_set_refine": (c.c_int, [vp, c.c_int]),
+        "cs_comm_unique_id": (c.c_int, [vp]),
+        "cs_comm_init": (c.c_int, [vp, vp, c.c_int, c.c_int, c.c_int, c.c_int]),
+        "cs_comm_local_range": (c.c_int, [vp, ip]),
+        "cs_comm_halo": (c.c_int, [vp, c.c_int, vp, c.c_int, c.c_int]),
         "cs_mesh_set": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, dp, dp, dp, c.c_double, c.c_double, c.c_double]),
         "cs_mesh_counts": (c.c_int, [vp, c.POINTER(ll)]),
         "cs_model_paint": (c.c_int, [vp, dp, vp, vp]),
@@ -92,7 +96,8 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_fp64_peak", "cs_ctx_set_refine", "cs_mesh_set",
+    "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_fp64_peak", "cs_ctx_set_refine",
+    "cs_comm_unique_id", "cs_comm_init", "cs_comm_local_range", "cs_comm_halo", "cs_mesh_set",
     "cs_mesh_counts", "cs_model_paint", "cs_model_set", "cs_face_inner_product", "cs_edge_inner_product",
     "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_op_get", "cs_op_get_noplan", "cs_op_apply_timed", "cs_op_from_csr", "cs_op_size", "cs_op_apply", "cs_op_factor",
     "cs_op_solve", "cs_op_clean", "cs_solve_dc", "cs_solve_fdem", "cs_tdem_run", "cs_fields_fdem",
@@ -247,6 +252,37 @@ class Context(object):
 
     def launch_count(self):
         return int(self.lib.cs_launch_count())
+
+    # -- z-slab decomposition of one system over several GPUs (one process per GPU) ------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id drawn by rank 0; hand it to the other ranks (e.g. torch.distributed.broadcast)"""
+        buf = ctypes.create_string_buffer(128)
+        check(load_library().cs_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, nranks, z_lo, z_hi):
+        """this context owns the global cell levels [z_lo, z_hi); call before set_mesh (which then takes the global mesh)"""
+        buf = ctypes.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(self.lib.cs_comm_init(self.h, buf, int(rank), int(nranks), int(z_lo), int(z_hi)))
+        self.slab = (int(z_lo), int(z_hi))
+
+    def local_range(self):
+        """global cell levels [k0, k1) the local mesh covers (owned levels plus one ghost layer below)"""
+        kk = (ctypes.c_int * 2)()
+        check(self.lib.cs_comm_local_range(self.h, kk))
+        return int(kk[0]), int(kk[1])
+
+    def halo(self, vec, family):
+        """refresh the ghost levels of a local vector (family 0 cells, 1 edges, 2 faces) in place"""
+        n = {0: self.nC, 1: self.nE, 2: self.nF}[family]
+        v2 = vec.reshape(-1, n)
+        assert v2.is_contiguous()
+        self._enter()
+        rc = self.lib.cs_comm_halo(self.h, family, _tptr(v2), v2.shape[0], int(v2.is_complex()))
+        self._exit()
+        check(rc)
+        return vec
 
     def set_refine(self, max_dd_steps):
         """iterative refinement of edge-form solves with a double-double residual (0 = off, the default)"""

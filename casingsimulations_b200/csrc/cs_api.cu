@@ -2,6 +2,7 @@
 // batched preconditioned BiCGStab, and the physics-level DC / FDEM / TDEM drivers.
 #include "../../include/casing_b200.h"
 #include "cs_internal.h"
+#include "cs_dist.h"
 #include <complex>
 #include <map>
 #include <vector>
@@ -72,6 +73,17 @@ struct DevBuf {
     }
 };
 
+// z-slab decomposition of one system over the ranks of an NCCL communicator (cs_comm_init; see cs_dist.cu)
+struct DistState {
+    bool on = false;
+    DistGeom g;
+    void* comm = nullptr;
+    std::vector<int> zsplit;                      // nranks + 1 global cell-level boundaries (every rank knows all)
+    double* mask[3] = {nullptr, nullptr, nullptr};   // 1.0 on owned cells / edges / faces of the local mesh
+    int k0_of(int r) const { return std::max(zsplit[r] - 1, 0); }
+    int nzl_of(int r) const { return zsplit[r + 1] - k0_of(r); }
+};
+
 struct cs_op {
     cs_ctx* ctx = nullptr;
     int kind = 0, family = 0;        // family: 0 cell, 1 edge, 2 face
@@ -88,6 +100,12 @@ struct cs_op {
     bool lu_cplx = false;
     std::vector<zc> shifts;
     double ms_assemble = 0.0, ms_factor = 0.0;
+    // mode-sharded global factors of the z-slab solve: bp stays the LOCAL plan (gather / scatter / probing of the owned
+    // columns), bpg describes the global mode systems whose factors this rank owns
+    BandPlan bpg;
+    long long Lrow = 0;                           // band rows per z level
+    DevBuf gmap, gjstr, gmdiag, gfmap, gstage, gmodes;
+    std::vector<int> mv_owner, mv_pos, own_mv;    // per mode vector m: owning rank, position among the owner's vectors
 };
 
 struct cs_ctx {
@@ -109,7 +127,12 @@ struct cs_ctx {
     unsigned long long mesh_gen = 0;   // bumped by cs_mesh_set: part of the probe-graph cache key
     int next_csr_key = -1;             // keys of assembled-matrix operators in `ops`
     int dd_steps_max = 0;              // cs_ctx_set_refine: refinement steps with the double-double residual (0 = off)
+    DistState dist;
+    DevBuf halo_s, halo_r;             // packed halo planes: two halves each (down / up neighbour)
+    size_t halo_half = 0;
 };
+
+static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc);
 
 static void op_free(cs_op* op) {
     if (!op) return;
@@ -118,6 +141,7 @@ static void op_free(cs_op* op) {
     op->bmap.release(); op->bjstr.release(); op->bmdiag.release(); op->bhs.release();
     op->kband.release(); op->bp.Kband = nullptr;
     op->LU.release(); op->wts.release();
+    op->gmap.release(); op->gjstr.release(); op->gmdiag.release(); op->gfmap.release(); op->gstage.release(); op->gmodes.release();
     delete op;
 }
 static void ctx_drop_ops(cs_ctx* c) {
@@ -507,7 +531,7 @@ extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int c
     BandPlan& bp = op->bp;
     bool lc = bp.cplx_band || complex_shift != 0;
     size_t need = (size_t)nshift * bp.nmodes * bp.band_elems() * esz(lc);
-    CS_TRY(op->LU.ensure(need));
+    if (!c->dist.on) CS_TRY(op->LU.ensure(need));
     op->lu_cplx = lc;
     op->shifts.resize(nshift);
     for (int f = 0; f < nshift; ++f) op->shifts[f] = zc(shifts_h[2 * f], shifts_h[2 * f + 1]);
@@ -516,12 +540,193 @@ extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int c
     CS_CUDA(cudaMemcpyAsync(c->scal.p, shifts_h, 2 * nshift * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CS_TRY(op->wts.ensure((size_t)nshift * op->n * sizeof(double)));
     CS_TRY(band_diag_weights(bp, (const double*)c->scal.p, nshift, op->n, (double*)op->wts.p, c->st));
-    CS_TRY(band_form_and_factor(bp, (const double*)c->scal.p, nshift, op->LU.p, lc, c->st));
-    g_launches += band_factor_launches(bp, lc);
+    if (c->dist.on) {
+        CS_TRY(dist_factor(op, shifts_h, nshift, lc));
+    } else {
+        CS_TRY(band_form_and_factor(bp, (const double*)c->scal.p, nshift, op->LU.p, lc, c->st));
+        g_launches += band_factor_launches(bp, lc);
+    }
     CS_CUDA(cudaEventRecord(c->ev1, c->st));
     CS_CUDA(cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     op->ms_factor = ms;
+    return CS_OK;
+}
+
+
+// ------------------------------------------------ z-slab helpers (cs_dist.cu) -----
+static int halo_exchange(cs_ctx* c, int family, void* vec, long long n, int nvec, bool cplx_vec) {
+    DistState& d = c->dist;
+    if (!d.on || d.g.nranks == 1) return CS_OK;
+    // the largest message: two node planes + one cell plane of every component of the family
+    size_t need = (size_t)nvec * 3 * (size_t)(c->m.nxy + 1) * 2 * sizeof(cplx);
+    if (need > c->halo_half) {
+        CS_TRY(c->halo_s.ensure(2 * need)); CS_TRY(c->halo_r.ensure(2 * need));
+        c->halo_half = need;
+    }
+    g_launches += 4;
+    return dist_halo_exchange(c->m, d.g, d.comm, family, vec, n, nvec, cplx_vec, c->halo_s.p, c->halo_r.p, c->halo_half, c->st);
+}
+static const double* own_mask(cs_ctx* c, int family) { return c->dist.on ? c->dist.mask[family] : nullptr; }
+
+// mode vectors between the slab layout (all modes, local rows) and the mode-sharded layout (owned modes, all rows)
+//   forward : xm_l [nvec][nth][n2_l]  (my owned rows)          -> xm_g [nvec][nmv_own][n2_g] on the owner of each mode
+//   backward: xm_g (all rows of my modes) -> every rank's xm_l (all of ITS local rows, ghost levels included)
+static int mode_exchange(cs_op* op, void* xm_l, void* xm_g, int nvec, bool forward) {
+    cs_ctx* c = op->ctx;
+    DistState& d = c->dist;
+    const BandPlan& bl = op->bp; const BandPlan& bg = op->bpg;
+    const long long L = op->Lrow;
+    const int nth = bl.nth, me = d.g.rank, R = d.g.nranks;
+    const NcclApi* nc = R > 1 ? nccl_api() : nullptr;
+    CS_CHECK(R == 1 || nc, "NCCL is not available");
+    auto rows_owned = [&](int r, long long& row0, long long& cnt) {
+        row0 = (long long)d.zsplit[r] * L;
+        long long row1 = (r == R - 1) ? bg.n2 : (long long)d.zsplit[r + 1] * L;
+        cnt = row1 - row0;
+    };
+    auto rows_local = [&](int r, long long& row0, long long& cnt) {
+        row0 = (long long)d.k0_of(r) * L;
+        cnt = L * (d.nzl_of(r) + 1);
+    };
+    cplx* xl = (cplx*)xm_l; cplx* xg = (cplx*)xm_g;
+    const int nmv_me = bg.nmv_own;
+    if (nc) nc->GroupStart();
+    ncclResult_t rc = ncclSuccess;
+    for (int v = 0; v < nvec; ++v)
+        for (int m = 0; m < nth; ++m) {
+            const int owner = op->mv_owner[m], pos = op->mv_pos[m];
+            if (forward) {
+                long long g0, cnt; rows_owned(me, g0, cnt);
+                const cplx* src = xl + ((size_t)v * nth + m) * bl.n2 + (g0 - (long long)d.g.k0 * L);
+                if (owner == me) {
+                    CS_CUDA(cudaMemcpyAsync(xg + ((size_t)v * nmv_me + pos) * bg.n2 + g0, src, cnt * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
+                    for (int r = 0; r < R; ++r) if (r != me) {
+                        long long r0, rc_; rows_owned(r, r0, rc_);
+                        rc = nc->Recv(xg + ((size_t)v * nmv_me + pos) * bg.n2 + r0, (size_t)rc_ * 2, ncclDouble, r, (ncclComm_t)d.comm, c->st);
+                    }
+                } else rc = nc->Send(src, (size_t)cnt * 2, ncclDouble, owner, (ncclComm_t)d.comm, c->st);
+            } else {
+                if (owner == me) {
+                    for (int r = 0; r < R; ++r) {
+                        long long r0, cnt; rows_local(r, r0, cnt);
+                        const cplx* src = xg + ((size_t)v * nmv_me + pos) * bg.n2 + r0;
+                        if (r == me) CS_CUDA(cudaMemcpyAsync(xl + ((size_t)v * nth + m) * bl.n2, src, cnt * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
+                        else rc = nc->Send(src, (size_t)cnt * 2, ncclDouble, r, (ncclComm_t)d.comm, c->st);
+                    }
+                } else {
+                    long long r0, cnt; rows_local(me, r0, cnt);
+                    rc = nc->Recv(xl + ((size_t)v * nth + m) * bl.n2, (size_t)cnt * 2, ncclDouble, owner, (ncclComm_t)d.comm, c->st);
+                }
+            }
+        }
+    if (nc) rc = nc->GroupEnd();
+    CS_CHECK(rc == ncclSuccess, "NCCL mode exchange failed");
+    g_launches += 1;
+    return CS_OK;
+}
+
+__global__ void k_fill_rows(double* __restrict__ dst, const double* __restrict__ src, long long cnt) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < cnt) dst[t] = src[t];
+}
+
+// Factors of the mode systems this rank owns, over the GLOBAL z range.  Every rank has probed the band columns of its
+// owned z levels for all modes with its local operator (exact: a column only involves the adjacent levels, which the local
+// mesh holds with the right weights); the columns travel to the owner of each mode, which forms A(s) = K + s M and
+// factors it.  One mode at a time through a staging buffer: no rank ever holds more than its own factors.
+static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
+    cs_ctx* c = op->ctx;
+    DistState& d = c->dist;
+    BandPlan& bl = op->bp; BandPlan& bg = op->bpg;
+    const MeshD& m = c->m;
+    CS_CHECK(op->family == 1 && !op->is_csr, "the z-slab solve is implemented for the edge-form operators (FDEM-h / -e)");
+    CS_CHECK(lc && !bl.cplx_band, "the z-slab solve needs a complex shift (FDEM) on a real operator");
+    const int R = d.g.nranks, me = d.g.rank, H = bl.nmodes, nth = bl.nth;
+    const long long L = bl.n2 / (m.nz + 1);
+    op->Lrow = L;
+    bg = bl;
+    bg.n2 = L * (d.g.gnz + 1);
+    int n_own = 0;
+    for (int h = me; h < H; h += R) ++n_own;
+    CS_CHECK(n_own >= 1, "more ranks than theta modes: nothing to own");
+    bg.nmodes = n_own;
+    // mode vectors: all nth modes of a complex vector, mode m uses the factor of h = min(m, nth - m)
+    op->mv_owner.assign(nth, 0); op->mv_pos.assign(nth, 0); op->own_mv.clear();
+    std::vector<int> cnt(R, 0), fmap;
+    for (int mm = 0; mm < nth; ++mm) {
+        int h = (nth == 1) ? 0 : std::min(mm, nth - mm);
+        int o = h % R;
+        op->mv_owner[mm] = o; op->mv_pos[mm] = cnt[o]++;
+        if (o == me) { op->own_mv.push_back(mm); fmap.push_back(h / R); }
+    }
+    bg.nmv_own = (int)op->own_mv.size();
+    op->gfmap.pool = op->gmap.pool = op->gjstr.pool = op->gmdiag.pool = op->gstage.pool = op->gmodes.pool = &c->pool;
+    CS_TRY(op->gfmap.ensure(std::max<size_t>(fmap.size(), 1) * sizeof(int)));
+    CS_CUDA(cudaMemcpyAsync(op->gfmap.p, fmap.data(), fmap.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    bg.fmap = (const int*)op->gfmap.p;
+    // global row tables: the per-level pattern of the local plan repeated (the top node level has no Ez entries)
+    std::vector<long long> mapl(bl.n2); std::vector<int> jsl(bl.n2);
+    CS_CUDA(cudaMemcpyAsync(mapl.data(), bl.map3d, bl.n2 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CS_CUDA(cudaMemcpyAsync(jsl.data(), bl.jstr, bl.n2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    std::vector<long long> mapg(bg.n2); std::vector<int> jsg(bg.n2);
+    for (int k = 0; k <= d.g.gnz; ++k)
+        for (long long r = 0; r < L; ++r) {
+            // level 0 of the local plan is a regular level (nz_l >= 2), its last level the pattern of a top level
+            long long src = (k == d.g.gnz) ? (long long)m.nz * L + r : r;
+            mapg[k * L + r] = mapl[src] < 0 ? -1 : 0;
+            jsg[k * L + r] = jsl[src];
+        }
+    CS_TRY(op->gmap.ensure(bg.n2 * sizeof(long long))); CS_TRY(op->gjstr.ensure(bg.n2 * sizeof(int))); CS_TRY(op->gmdiag.ensure(bg.n2 * sizeof(double)));
+    CS_CUDA(cudaMemcpyAsync(op->gmap.p, mapg.data(), bg.n2 * sizeof(long long), cudaMemcpyHostToDevice, c->st));
+    CS_CUDA(cudaMemcpyAsync(op->gjstr.p, jsg.data(), bg.n2 * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    bg.map3d = (long long*)op->gmap.p; bg.jstr = (int*)op->gjstr.p; bg.mdiag = (double*)op->gmdiag.p; bg.hs = nullptr;
+    CS_CUDA(cudaStreamSynchronize(c->st));                      // (host vectors go out of scope)
+    // global mass diagonal: every rank contributes its owned rows, summed over the ranks
+    const long long g0 = (long long)d.g.z_lo * L, g1 = (me == R - 1) ? bg.n2 : (long long)d.g.z_hi * L;
+    const long long l0 = g0 - (long long)d.g.k0 * L;
+    CS_CUDA(cudaMemsetAsync(bg.mdiag, 0, bg.n2 * sizeof(double), c->st));
+    k_fill_rows<<<cdiv(g1 - g0, 256), 256, 0, c->st>>>(bg.mdiag + g0, bl.mdiag + l0, g1 - g0);
+    CS_TRY(dist_allreduce_sum(d.g, d.comm, bg.mdiag, (size_t)bg.n2, c->st));
+    // factors
+    const size_t nel_g = bg.band_elems(), nel_l = bl.band_elems();
+    CS_TRY(op->LU.ensure((size_t)nshift * n_own * nel_g * sizeof(cplx)));
+    CS_TRY(op->gstage.ensure(nel_g * sizeof(double)));
+    double* stage = (double*)op->gstage.p;
+    const NcclApi* nc = R > 1 ? nccl_api() : nullptr;
+    CS_CHECK(R == 1 || nc, "NCCL is not available");
+    const double* Kl = (const double*)bl.Kband;
+    BandPlan one = bg;                     // view of ONE mode system for k_form_shifted
+    one.nmodes = 1;
+    for (int h = 0; h < H; ++h) {
+        const int owner = h % R;
+        const double* src = Kl + (size_t)h * nel_l + (size_t)l0 * bl.ldab;
+        const size_t cnt_me = (size_t)(g1 - g0) * bl.ldab;
+        ncclResult_t rc = ncclSuccess;
+        if (nc) nc->GroupStart();
+        if (owner == me) {
+            CS_CUDA(cudaMemcpyAsync(stage + (size_t)g0 * bg.ldab, src, cnt_me * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            for (int r = 0; r < R; ++r) if (r != me) {
+                long long r0 = (long long)d.zsplit[r] * L, r1 = (r == R - 1) ? bg.n2 : (long long)d.zsplit[r + 1] * L;
+                rc = nc->Recv(stage + (size_t)r0 * bg.ldab, (size_t)(r1 - r0) * bg.ldab, ncclDouble, r, (ncclComm_t)d.comm, c->st);
+            }
+        } else rc = nc->Send(src, cnt_me, ncclDouble, owner, (ncclComm_t)d.comm, c->st);
+        if (nc) rc = nc->GroupEnd();
+        CS_CHECK(rc == ncclSuccess, "NCCL exchange of the band columns failed");
+        if (owner == me) {
+            // mode h > 0 systems treat the axis unknown as a dummy: k_form_shifted decides that from its mode index,
+            // which in the one-mode view is always 0 -> pass the true mode through the Kband offset trick below
+            one.Kband = stage;
+            for (int f = 0; f < nshift; ++f) {
+                cplx* dst = (cplx*)op->LU.p + ((size_t)f * n_own + h / R) * nel_g;
+                CS_TRY(band_form_shifted_mode(one, h, (const double*)c->scal.p + 2 * f, dst, c->st));
+            }
+        }
+    }
+    g_launches += 2 * H;
+    CS_TRY(band_factor(bg, op->LU.p, true, nshift * n_own, c->st));
+    g_launches += band_factor_launches(bg, true);
     return CS_OK;
 }
 
@@ -533,7 +738,9 @@ struct Krylov {
     long long n_apply = 0;
     void* vec(int i) { return base + (size_t)i * vb; }
     int dots(const void* a, const void* b, bool conj, std::vector<zc>& out, bool scaled = false, int winv = 0) {
-        CS_TRY(launch_dot(a, b, n, nvec, cv, conj, dots_d, c->st, scaled ? (const double*)op->wts.p : nullptr, scaled ? sov_d : nullptr, winv));
+        CS_TRY(launch_dot(a, b, n, nvec, cv, conj, dots_d, c->st, scaled ? (const double*)op->wts.p : nullptr, scaled ? sov_d : nullptr, winv,
+                          own_mask(c, op->family)));
+        if (c->dist.on) CS_TRY(dist_allreduce_sum(c->dist.g, c->dist.comm, dots_d, 2 * (size_t)nvec, c->st));   // K11: one message per phase
         CS_CUDA(cudaMemcpyAsync(c->pin, dots_d, 2 * nvec * sizeof(double), cudaMemcpyDeviceToHost, c->st));
         CS_CUDA(cudaStreamSynchronize(c->st));
         out.resize(nvec);
@@ -553,9 +760,23 @@ struct Krylov {
         return launch_axpby(y, x, n, nvec, cv, pd, pd + 2 * nvec, c->st);
     }
     int slot = 0;
-    int apply(const void* x, void* y) { n_apply++; return op_apply_dev(op, s_d, x, y, nvec, cv); }
+    int apply(const void* x, void* y) {
+        n_apply++;
+        CS_TRY(op_apply_dev(op, s_d, x, y, nvec, cv));
+        return halo_exchange(c, op->family, y, n, nvec, cv);      // (no-op on a single GPU)
+    }
     int precond(const void* x, void* y) {
         BandPlan& bp = op->bp;
+        if (c->dist.on) {
+            // slab layout -> mode-sharded layout -> banded solves of the owned modes -> back (ghost levels included)
+            CS_TRY(band_dft_gather(bp, x, cv, c->modes.p, true, n, nvec, c->st));
+            CS_TRY(mode_exchange(op, c->modes.p, op->gmodes.p, nvec, true));
+            CS_TRY(band_solve(op->bpg, op->LU.p, true, op->gmodes.p, true, nvec, sov_d, c->st));
+            CS_TRY(mode_exchange(op, c->modes.p, op->gmodes.p, nvec, false));
+            CS_TRY(band_dft_scatter(bp, c->modes.p, true, y, cv, n, nvec, c->st));
+            g_launches += 3;
+            return CS_OK;
+        }
         CS_TRY(band_dft_gather(bp, x, cv, c->modes.p, op->lu_cplx, n, nvec, c->st));
         CS_TRY(band_solve(bp, op->LU.p, op->lu_cplx, c->modes.p, op->lu_cplx, nvec, sov_d, c->st));
         CS_TRY(band_dft_scatter(bp, c->modes.p, op->lu_cplx, y, cv, n, nvec, c->st));
@@ -721,6 +942,10 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
     K.dots_d = K.a_d + 64 * 4 * nvec;
     K.sov_d = (int*)(K.dots_d + 2 * nvec * 260);
     CS_TRY(c->modes.ensure((size_t)nvec * op->bp.nmv(op->lu_cplx) * op->bp.n2 * esz(op->lu_cplx)));
+    if (c->dist.on) {
+        CS_CHECK(cv && op->lu_cplx && op->bpg.fmap, "the z-slab solve needs the factors of cs_op_factor in slab mode and complex vectors");
+        CS_TRY(op->gmodes.ensure((size_t)nvec * op->bpg.nmv_own * op->bpg.n2 * sizeof(cplx)));
+    }
     // per-vector shifts
     std::vector<int> sov(nvec, 0);
     for (int v = 0; v < nvec; ++v) { sov[v] = sov_h ? sov_h[v] : 0; CS_CHECK(sov[v] >= 0 && sov[v] < (int)op->shifts.size(), "shift index out of range"); }
@@ -835,7 +1060,7 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
         }
         if (!(worst > std::min(1e-3 * rtol, 1e-13))) break;      // >= 3 digits below the target: done
         if (round > 0 && !(worst < 0.1 * prev_worst)) break;
-        if (round == 0 && !(worst < 1e-3) && maxit > bicg_cap) { want_gmres = true; break; }
+        if (round == 0 && !(worst < 1e-3) && maxit > bicg_cap && !c->dist.on) { want_gmres = true; break; }
         prev_worst = worst;
     }
     if (!(worst <= best_worst)) {
@@ -883,7 +1108,7 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
         return CS_OK;
     };
     if (!all_ok) CS_TRY(floor_test());
-    if (!all_ok && !want_gmres && maxit - total_it > 0) {
+    if (!all_ok && !want_gmres && maxit - total_it > 0 && !c->dist.on) {      // (the GMRES continuation is single-GPU only)
         // the BiCGStab rounds stalled above the target and not at the fp64 floor (the theta-mode factors are
         // only an approximate preconditioner, e.g. non-uniform azimuthal widths): continue with GMRES from here
         int rcg = gmres_solve(K, rhs, x, bnorm, std::max(0.1 * rtol, 1e-13), maxit - total_it, total_it, worst);
@@ -902,7 +1127,7 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
     double dd_steps = 0.0, dd_corr = 0.0;
     static const int dd_env = [] { const char* e = getenv("CS_DD_REFINE"); return e ? atoi(e) : -1; }();     // overrides the context setting
     const int dd_max = dd_env >= 0 ? dd_env : c->dd_steps_max;
-    if (dd_max > 0 && all_ok && !want_gmres && op->family == 1 && !op->is_csr && total_it <= 4) {
+    if (dd_max > 0 && all_ok && !want_gmres && op->family == 1 && !op->is_csr && total_it <= 4 && !c->dist.on) {
         CS_TRY(c->ddwork.ensure((size_t)2 * c->m.nF * sizeof(double)));
         std::vector<double> sh_h(2 * nvec);
         for (int v = 0; v < nvec; ++v) { sh_h[2 * v] = op->shifts[sov[v]].real(); sh_h[2 * v + 1] = op->shifts[sov[v]].imag(); }
@@ -1035,6 +1260,9 @@ extern "C" int cs_ctx_destroy(cs_ctx* c) {
     ctx_drop_ops(c);
     cudaFree(c->tables); cudaFree(c->sigma); cudaFree(c->mu);
     c->work.release(); c->scal.release(); c->modes.release(); c->tmp1.release(); c->tmp2.release(); c->ework.release(); c->ddwork.release();
+    c->halo_s.release(); c->halo_r.release();
+    for (int fam = 0; fam < 3; ++fam) cudaFree(c->dist.mask[fam]);
+    if (c->dist.comm) { const NcclApi* nc = nccl_api(); if (nc) nc->CommDestroy((ncclComm_t)c->dist.comm); }
     c->pool.clear();
     for (auto& g : c->probe_graphs) cudaGraphExecDestroy(g.second);
     cudaFreeHost(c->pin);
@@ -1051,12 +1279,82 @@ extern "C" int cs_ctx_set_refine(cs_ctx* c, int max_dd_steps) {
 }
 extern "C" int cs_ctx_sync(cs_ctx* c) { CS_CHECK(c, "null ctx"); CS_CUDA(cudaStreamSynchronize(c->st)); return CS_OK; }
 
+// ---- z-slab decomposition (cs_comm_init; no reference counterpart, run.py:50-53) ----
+extern "C" int cs_comm_unique_id(void* id128_h) {
+    CS_CHECK(id128_h, "null argument");
+    const NcclApi* nc = nccl_api();
+    CS_CHECK(nc, "NCCL is not available");
+    ncclUniqueId id;
+    CS_CHECK(nc->GetUniqueId(&id) == ncclSuccess, "ncclGetUniqueId failed");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128_h, &id, 128);
+    return CS_OK;
+}
+extern "C" int cs_comm_init(cs_ctx* c, const void* nccl_unique_id_h, int rank, int nranks, int z_lo, int z_hi) {
+    CS_CHECK(c && nranks >= 1 && rank >= 0 && rank < nranks && z_lo >= 0 && z_hi > z_lo, "bad arguments");
+    CS_CHECK(!c->has_mesh, "cs_comm_init must come before cs_mesh_set (which then takes the GLOBAL mesh)");
+    CS_CUDA(cudaSetDevice(c->device));
+    DistState& d = c->dist;
+    d.g.rank = rank; d.g.nranks = nranks; d.g.z_lo = z_lo; d.g.z_hi = z_hi;
+    d.zsplit.assign(nranks + 1, 0);
+    if (nranks > 1) {
+        CS_CHECK(nccl_unique_id_h, "the NCCL unique id of rank 0 (cs_comm_unique_id) is required");
+        const NcclApi* nc = nccl_api();
+        CS_CHECK(nc, "NCCL is not available");
+        ncclUniqueId id;
+        memcpy(&id, nccl_unique_id_h, 128);
+        ncclComm_t comm = nullptr;
+        CS_CHECK(nc->CommInitRank(&comm, nranks, id, rank) == ncclSuccess, "ncclCommInitRank failed");
+        d.comm = comm;
+        // every rank learns every slab: all-reduce of a table that each rank fills at its own slots
+        CS_TRY(c->scal.ensure(std::max<size_t>(4096, 2 * (size_t)nranks * sizeof(double))));
+        std::vector<double> tab(2 * nranks, 0.0);
+        tab[2 * rank] = z_lo; tab[2 * rank + 1] = z_hi;
+        CS_CUDA(cudaMemcpyAsync(c->scal.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        CS_TRY(dist_allreduce_sum(d.g, d.comm, (double*)c->scal.p, tab.size(), c->st));
+        CS_CUDA(cudaMemcpyAsync(tab.data(), c->scal.p, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CS_CUDA(cudaStreamSynchronize(c->st));
+        for (int r = 0; r < nranks; ++r) {
+            d.zsplit[r] = (int)tab[2 * r]; d.zsplit[r + 1] = (int)tab[2 * r + 1];
+            if (r > 0) CS_CHECK((int)tab[2 * r] == (int)tab[2 * r - 1], "the z slabs of consecutive ranks must be contiguous");
+            CS_CHECK((int)tab[2 * r + 1] - (int)tab[2 * r] >= 2, "every rank must own at least two z levels");
+        }
+    } else { d.zsplit[0] = z_lo; d.zsplit[1] = z_hi; }
+    CS_CHECK(d.zsplit[0] == 0, "the first slab must start at z level 0");
+    d.on = true;
+    return CS_OK;
+}
+extern "C" int cs_comm_local_range(cs_ctx* c, int* k0_k1_h) {
+    CS_CHECK(c && c->dist.on && c->has_mesh && k0_k1_h, "slab mode with a mesh is required");
+    k0_k1_h[0] = c->dist.g.k0; k0_k1_h[1] = c->dist.g.k1;
+    return CS_OK;
+}
+// refresh the ghost levels of nvec local vectors (family 0 cells, 1 edges, 2 faces) from the neighbouring slabs
+extern "C" int cs_comm_halo(cs_ctx* c, int family, void* vec_d, int nvec, int is_complex) {
+    CS_CHECK(c && c->has_mesh && family >= 0 && family <= 2, "bad arguments");
+    CS_CUDA(cudaSetDevice(c->device));
+    long long n = family == 0 ? c->m.nC : (family == 1 ? c->m.nE : c->m.nF);
+    return halo_exchange(c, family, vec_d, n, nvec, is_complex != 0);
+}
+
 extern "C" int cs_mesh_set(cs_ctx* c, int nx, int nth, int nz, const double* hx, const double* hth, const double* hz,
                            double z0, double w_edge, double w_face) {
     CS_CHECK(c && nx >= 1 && nth >= 1 && nz >= 1, "bad mesh sizes");
     CS_CUDA(cudaSetDevice(c->device));
     double sth = 0; for (int j = 0; j < nth; ++j) sth += hth[j];
     CS_CHECK(std::fabs(sth - 2 * M_PI) < 1e-6, "hy must sum to 2*pi (mesh.py:408-411)");
+    // slab mode: the arguments describe the GLOBAL mesh; the context keeps the cells [z_lo - 1, z_hi) of it (one ghost
+    // layer below) with the node coordinates of the global mesh, bit for bit (the painters compare with strict inequalities)
+    std::vector<double> zn_loc;
+    if (c->dist.on) {
+        DistState& d = c->dist;
+        CS_CHECK(d.zsplit[d.g.nranks] == nz, "the last z slab must end at the top of the mesh");
+        std::vector<double> gzn(nz + 1, z0);
+        { double a = 0; for (int k = 0; k < nz; ++k) { a += hz[k]; gzn[k + 1] = z0 + a; } }
+        d.g.gnz = nz; d.g.k0 = std::max(d.g.z_lo - 1, 0); d.g.k1 = d.g.z_hi;
+        zn_loc.assign(gzn.begin() + d.g.k0, gzn.begin() + d.g.k1 + 1);
+        hz += d.g.k0; nz = d.g.k1 - d.g.k0; z0 = zn_loc[0];
+    }
     ctx_drop_ops(c);
     // cached probing graphs bake the by-value mesh tables (axis weights included) into their launches
     for (auto& g : c->probe_graphs) cudaGraphExecDestroy(g.second);
@@ -1068,6 +1366,7 @@ extern "C" int cs_mesh_set(cs_ctx* c, int nx, int nth, int nz, const double* hx,
     c->rn.assign(nx + 1, 0.0); c->zn.assign(nz + 1, z0);
     for (int i = 0; i < nx; ++i) c->rn[i + 1] = c->rn[i] + hx[i];
     { double a = 0; for (int k = 0; k < nz; ++k) { a += hz[k]; c->zn[k + 1] = z0 + a; } }
+    if (!zn_loc.empty()) c->zn = zn_loc;
     std::vector<double> ring(nx);
     for (int i = 0; i < nx; ++i) ring[i] = 0.5 * (c->rn[i + 1] * c->rn[i + 1] - c->rn[i] * c->rn[i]);
     size_t tot = nx + (nx + 1) + nx + nth + nz + (nz + 1);
@@ -1093,6 +1392,15 @@ extern "C" int cs_mesh_set(cs_ctx* c, int nx, int nth, int nz, const double* hx,
     m.nF = m.nFx + m.nFy + m.nFz; m.nE = m.nEx + m.nEy + m.nEz;
     CS_CUDA(cudaMalloc(&c->sigma, m.nC * 8));
     CS_CUDA(cudaMalloc(&c->mu, m.nC * 8));
+    if (c->dist.on) {
+        for (int fam = 0; fam < 3; ++fam) {
+            std::vector<double> mk_;
+            dist_mask_host(m, c->dist.g, fam, mk_);
+            cudaFree(c->dist.mask[fam]); c->dist.mask[fam] = nullptr;
+            CS_CUDA(cudaMalloc(&c->dist.mask[fam], mk_.size() * sizeof(double)));
+            CS_CUDA(cudaMemcpy(c->dist.mask[fam], mk_.data(), mk_.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
     c->has_mesh = true;
     return CS_OK;
 }
@@ -1181,7 +1489,8 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
     size_t per = (size_t)op->bp.nmodes * op->bp.band_elems() * sizeof(cplx);
     size_t vecs = (size_t)(8 + 2) * n * sizeof(cplx) + (size_t)op->bp.nth * op->bp.n2 * sizeof(cplx);
     long long chunk = std::min(nfreq, 256);
-    if ((size_t)chunk * per > op->LU.bytes + c->pool.total()) {
+    if (c->dist.on) chunk = 1;                 // slab mode: one frequency at a time (the factors of a rank's modes fill its memory)
+    else if ((size_t)chunk * per > op->LU.bytes + c->pool.total()) {
         size_t fr = 0, tot = 0;
         CS_CUDA(cudaMemGetInfo(&fr, &tot));
         fr += op->LU.bytes + c->pool.total();
@@ -1220,6 +1529,7 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
             CS_CUDA(cudaStreamSynchronize(c->st));
             g_launches += 1;
         }
+        if (c->dist.on) CS_TRY(halo_exchange(c, op->family, rhs.p, n, nf, true));     // right-hand sides valid on the ghost levels too
         rc = cs_op_factor(op, sh.data(), nf, 1);
         if (rc) break;
         ms_fac += op->ms_factor;

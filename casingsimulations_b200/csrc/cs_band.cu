@@ -410,6 +410,30 @@ int band_form_shifted(const BandPlan& bp, const double* s_d, int nshift, void* L
     return CS_OK;
 }
 
+// one mode matrix (Kband = that mode's real band) -> A(s) in complex storage; `mode` is its true theta-mode index
+// (the shared axis unknown is a dummy in every mode but 0).  Used by the mode-sharded factorisation of the z-slab solve.
+__global__ void k_form_shifted_one(const long long* __restrict__ map3d, const int* __restrict__ jstr, const double* __restrict__ mdiag,
+                                   long long n2, int pw, int ldab, int mode, const double* __restrict__ K,
+                                   const double* __restrict__ s_d, cplx* __restrict__ LU) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n2 * (long long)ldab) return;
+    long long q = e / ldab;
+    int d = (int)(e - q * ldab);
+    cplx v = mk(K[e], 0.0);
+    if (d == pw) {
+        bool dummy = (map3d[q] < 0) || (jstr[q] == 0 && mode > 0);
+        v = dummy ? mk(1.0, 0.0) : mk(v.x + s_d[0] * mdiag[q], s_d[1] * mdiag[q]);
+    }
+    LU[e] = v;
+}
+int band_form_shifted_mode(const BandPlan& bp, int mode, const double* s_d, void* LU, cudaStream_t st) {
+    long long nel = bp.n2 * (long long)bp.ldab;
+    k_form_shifted_one<<<(unsigned)cdiv(nel, 256), 256, 0, st>>>(bp.map3d, bp.jstr, bp.mdiag, bp.n2, bp.pw, bp.ldab, mode,
+                                                                  (const double*)bp.Kband, s_d, (cplx*)LU);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
 // (the diagonal is invariant under the rotation; modes m and nth - m share it)
 template <typename TB>
 __global__ void k_diag_weights(const long long* __restrict__ map3d, const int* __restrict__ jstr, const double* __restrict__ mdiag,
@@ -1359,7 +1383,7 @@ __device__ __forceinline__ void bar_sync0() { asm volatile("bar.sync 0;" ::: "me
 template <typename TL, typename TV, int TPR, int NB, bool HP>
 __global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, int nmv, int fold, int nth, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0) {
+                             int nmodes, int nmv, int fold, int nth, const int* __restrict__ fmap, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool USE_TMA = sizeof(TL) == 16;                // complex: TMA bulk copies, real: cp.async
     __shared__ unsigned long long full_bar[8];
@@ -1375,7 +1399,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     // mode vector mm of 3-D vector v is solved with the stored factor h: all nth modes of a complex vector fold onto
     // min(mm, nth - mm) (K''_{nth-m} = K''_m), the (Re, Im) pairs of a real vector's modes share factor mm / 2
     const int v = blockIdx.y, mm = blockIdx.x;
-    const int m = fold == 0 ? mm : (fold == 1 ? min(mm, nth - mm) : (mm >> 1));
+    const int m = fold == 0 ? mm : (fold == 1 ? min(mm, nth - mm) : (fold == 2 ? (mm >> 1) : fmap[mm]));
     const int f = shift_of_vec ? shift_of_vec[v] : 0;
     const TL* A = LU + ((size_t)f * nmodes + m) * nel + pw;
     TV* b = xm + ((size_t)v * nmv + mm) * n2;
@@ -1573,8 +1597,8 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
     const bool xc = sizeof(T) == sizeof(cplx);
     const int nmv = bp.nmv(xc), fold = bp.fold(xc);
     dim3 g(nmv, nvec);
-    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, sov, xm, wsz, nst, bp.diag_full, th);
-    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, sov, xm, wsz, nst, bp.diag_full, 0);
+    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, th);
+    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, 0);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

@@ -43,7 +43,7 @@ int launch_csr_spmv(long long n, const long long* indptr, const int* indices, co
 // out[sys] = sum conj?(a) * b over n entries; results to dots_d[2*sys..]
 // optional weights w[wsel[sys]*n + t] (real, >= 0) give the diagonally scaled norms used by the convergence tests
 int launch_dot(const void* a, const void* b, long long n, int nsys, bool cplx_vec, bool conj_a, double* dots_d, cudaStream_t st,
-               const double* w = nullptr, const int* wsel = nullptr, int winv = 0);
+               const double* w = nullptr, const int* wsel = nullptr, int winv = 0, const double* mask = nullptr);
 // y = a*x + b*y with per-system complex scalars (host arrays of 2 doubles per system)
 int launch_axpby(void* y, const void* x, long long n, int nsys, bool cplx_vec, const double* a_d, const double* b_d, cudaStream_t st);
 // z = x .* w (w real, shared by all systems), optionally reciprocal
@@ -87,8 +87,12 @@ struct BandPlan {
     size_t band_elems() const { return (size_t)n2 * ldab; }
     // mode vectors per 3-D vector: complex factors take all nth modes (mode m uses factor min(m, nth - m));
     // real factors (real shift) take Re / Im of modes 0 .. nth/2 of a REAL 3-D vector as 2 * nmodes real vectors
-    int nmv(bool xm_cplx) const { return nth == 1 ? 1 : (xm_cplx ? nth : 2 * nmodes); }
-    int fold(bool xm_cplx) const { return nth == 1 ? 0 : (xm_cplx ? 1 : 2); }
+    int nmv(bool xm_cplx) const { return fmap ? nmv_own : (nth == 1 ? 1 : (xm_cplx ? nth : 2 * nmodes)); }
+    int fold(bool xm_cplx) const { return fmap ? 3 : (nth == 1 ? 0 : (xm_cplx ? 1 : 2)); }
+    // mode-sharded factors (z-slab / multi-GPU solve of one system): this rank stores `nmodes` of the factors and solves the
+    // `nmv_own` mode vectors that use them; fmap[mm] = index of the stored factor of local mode vector mm (device array)
+    const int* fmap = nullptr;
+    int nmv_own = 0;
 };
 
 // block size (16 or 32) for a plan with half bandwidth p
@@ -107,6 +111,7 @@ int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, cons
 int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long long n3d, double* w, cudaStream_t st);
 // LU[f][mode] = Kband[mode] + s[f] * diag(mdiag)   (f = 0..nshift-1)
 int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shift*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
+int band_form_shifted_mode(const BandPlan& bp, int mode, const double* s_d, void* LU, cudaStream_t st);
 // in-place blocked LU without pivoting of nsys_tot = nshift*nmodes band matrices
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st);
 int band_form_and_factor(const BandPlan& bp, const double* s_d /*device*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);

@@ -10,7 +10,7 @@ static const int DOT_BLOCKS = 256;   // partial sums per system
 
 template <typename T, bool CONJ>
 __global__ void k_dot_partial(const T* __restrict__ a, const T* __restrict__ b, long long n, double* __restrict__ part,
-                              const double* __restrict__ wt, const int* __restrict__ wsel, int winv) {
+                              const double* __restrict__ wt, const int* __restrict__ wsel, int winv, const double* __restrict__ mask) {
     int sys = blockIdx.y;
     a += sys * n;
     b += sys * n;
@@ -21,6 +21,7 @@ __global__ void k_dot_partial(const T* __restrict__ a, const T* __restrict__ b, 
         if (CONJ) av = Sc<T>::conj(av);
         T pr = av * bv;
         double ww = wt ? (winv ? 1.0 / wt[t] : wt[t]) : 1.0;
+        if (mask) ww *= mask[t];                               // z-slab decomposition: owned entries only
         re += ww * Sc<T>::re(pr);
         im += ww * Sc<T>::im(pr);
     }
@@ -71,17 +72,17 @@ __global__ void k_dot_final(const double* __restrict__ part, int nblk, double* _
 
 // scratch: at least 2*nsys*DOT_BLOCKS doubles, lives right after dots_d (caller provides 2*nsys*(1+DOT_BLOCKS))
 int launch_dot(const void* a, const void* b, long long n, int nsys, bool cplx_vec, bool conj_a, double* dots_d, cudaStream_t st,
-               const double* w, const int* wsel, int winv) {
+               const double* w, const int* wsel, int winv, const double* mask) {
     double* part = dots_d + 2 * (size_t)nsys;
     int nblk = (int)((n + TPB - 1) / TPB);
     if (nblk > DOT_BLOCKS) nblk = DOT_BLOCKS;
     if (nblk < 1) nblk = 1;
     dim3 g(nblk, nsys);
     if (cplx_vec) {
-        if (conj_a) k_dot_partial<cplx, true><<<g, TPB, 0, st>>>((const cplx*)a, (const cplx*)b, n, part, w, wsel, winv);
-        else k_dot_partial<cplx, false><<<g, TPB, 0, st>>>((const cplx*)a, (const cplx*)b, n, part, w, wsel, winv);
+        if (conj_a) k_dot_partial<cplx, true><<<g, TPB, 0, st>>>((const cplx*)a, (const cplx*)b, n, part, w, wsel, winv, mask);
+        else k_dot_partial<cplx, false><<<g, TPB, 0, st>>>((const cplx*)a, (const cplx*)b, n, part, w, wsel, winv, mask);
     } else {
-        k_dot_partial<double, false><<<g, TPB, 0, st>>>((const double*)a, (const double*)b, n, part, w, wsel, winv);
+        k_dot_partial<double, false><<<g, TPB, 0, st>>>((const double*)a, (const double*)b, n, part, w, wsel, winv, mask);
     }
     k_dot_final<<<nsys, 256, 0, st>>>(part, nblk, dots_d);
     CS_CUDA(cudaGetLastError());

@@ -61,6 +61,23 @@ int cs_ctx_set_refine(cs_ctx* ctx, int max_dd_steps);
  * of the factorisation's FP64 roofline in bench.py */
 int cs_fp64_peak(cs_ctx* ctx, double* tflops_h);
 
+/* ---- one large system over several GPUs: z-slab decomposition with NCCL halo exchange (BASELINE config 5) ----
+ * No reference counterpart (run.py:50-53: `num_threads` is its only, unused, parallel knob).  One process per GPU.
+ * Rank 0 draws an id (cs_comm_unique_id, 128 bytes) and hands it to the others out of band (torch.distributed, MPI,
+ * a file); every rank then calls cs_comm_init BEFORE cs_mesh_set with the global cell levels [z_lo, z_hi) it owns
+ * (contiguous, ascending with the rank, >= 2 levels each, covering 0 .. nz).  From then on cs_mesh_set takes the GLOBAL
+ * mesh and the context works on its slab: the cells [max(z_lo-1, 0), z_hi) -- cs_comm_local_range -- in the usual vector
+ * layout (cs_mesh_counts returns the LOCAL counts).  Vectors handed in (s_e) must be valid on that whole local range;
+ * solutions come back valid on it.  Implemented for cs_solve_fdem(form 'h'): stencil applies exchange one packed halo
+ * message per neighbour, all inner products of a Krylov phase travel in one all-reduce, and the theta-mode factors are
+ * sharded by mode (each rank factors the modes it owns over the full z range; mode vectors are transposed between the
+ * slab and the mode layout with grouped ncclSend / ncclRecv). */
+int cs_comm_unique_id(void* id128_h);
+int cs_comm_init(cs_ctx* ctx, const void* nccl_unique_id_h, int rank, int nranks, int z_lo, int z_hi);
+int cs_comm_local_range(cs_ctx* ctx, int* k0_k1_h);
+/* refresh the ghost levels of nvec local vectors (family: 0 cells, 1 edges, 2 faces) from the neighbouring slabs */
+int cs_comm_halo(cs_ctx* ctx, int family, void* vec_d, int nvec, int is_complex);
+
 /* discretize.CylMesh([hx, hy, hz], x0)            mesh.py:87-99, 518, 563 */
 int cs_mesh_set(cs_ctx* ctx, int nx, int nth, int nz, const double* hx_h, const double* hth_h,
                 const double* hz_h, double z0, double axis_weight_edge, double axis_weight_face);
