@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 METRIC = "fdem3d_casing_solve_seconds_per_frequency"
 UNIT = "s/frequency"
 NFREQ_PER_GPU = 2
+NFREQ_STRONG = 16                                      # --mode strong: frequencies of the whole sweep, sharded over the GPUs
 MESH_OURS = dict(nth=32, csz=0.75, npadz=25)          # 109 x 32 x 1394 (C3 mesh)
 MESH_REF = dict(nth=4, csz=50.0, npadz=5)             # 109 x 4 x 40: ~8 s SuperLU per frequency and core
 WORKLOAD = ("3-D FDEM-h, CasingInHalfspace (sigma_casing 5.5e6 S/m, mu_r 100, 1 km casing), CasingMeshGenerator "
@@ -274,8 +275,10 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)               # torch copies, events and our kernels share one stream
 
-    all_freqs = np.logspace(0, 1, NFREQ_PER_GPU * world)
-    freqs = np.ascontiguousarray(all_freqs[rank::world])          # this rank's frequencies
+    strong = getattr(args, "mode", "weak") == "strong"
+    nfreq_total = NFREQ_STRONG if strong else NFREQ_PER_GPU * world
+    all_freqs = np.logspace(0, 1, nfreq_total)
+    freqs = np.ascontiguousarray(all_freqs[rank::world])          # this rank's frequencies (round robin)
     mp, mg, src = build_inputs(MESH_OURS, freqs)
     m = mg.mesh
     params = mp.paint_params()
@@ -356,7 +359,6 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(tt[0]), float(tt[1])
-    nfreq_total = NFREQ_PER_GPU * world
 
     if rank == 0:
         def avg(key):
@@ -365,7 +367,7 @@ def run_ours(args, rank, world, local_rank):
         # band LU of the theta-mode systems: nth/2+1 complex band matrices of order n2, half bandwidth p, per frequency
         nx, nth, nz = (int(v) for v in m.vnC)
         n2, p, nsys = (3 * nx + 1) * (nz + 1), 3 * nx + 3, nth // 2 + 1
-        flops = 8.0 * n2 * float(p) ** 2 * nsys * NFREQ_PER_GPU           # complex LU without pivoting, 8 flop per complex FMA
+        flops = 8.0 * n2 * float(p) ** 2 * nsys * len(freqs)              # complex LU without pivoting, 8 flop per complex FMA
         ach = flops / (ms_factor * 1e-3) / 1e12
         roof = {"bound": "fp64", "kernel": "band LU of the {} theta-mode systems per frequency (k_lu_panel + k_lu_update, {} dependent "
                                             "16-column block steps replayed as one CUDA graph): {:.0f} % of the step's device time"
@@ -396,8 +398,10 @@ def run_ours(args, rank, world, local_rank):
         value = t_dev / (args.steps * nfreq_total)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": False,
-                "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "mesh": mesh_name(mg), "frequencies_per_gpu": NFREQ_PER_GPU,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                "config": {"workload": WORKLOAD if not strong else WORKLOAD.replace("{} frequencies 1-10 Hz per GPU".format(NFREQ_PER_GPU),
+                                                                                     "{} frequencies 1-10 Hz in total".format(NFREQ_STRONG)),
+                           "mesh": mesh_name(mg), "frequencies_per_gpu": len(freqs),
                            "unknowns_per_frequency": nE, "l2": "256 MB buffer written between timed iterations", "rtol": 1e-10,
                            "reference_arm_mesh": "109x4x40 = 17440 cells (largest the host solves in seconds; see cpu_baseline.sample)"},
                 "frequencies_per_s": 1.0 / value,
@@ -418,18 +422,54 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# one system too big for one GPU, per GPU count: (nth, csz, npadz) -> mesh; the last is BASELINE configs[4]
+ONE_SYSTEM = {1: (32, 0.75, 25), 2: (64, 0.75, 25), 4: (128, 0.75, 25), 8: (128, 0.3, 25)}
+
+
+def run_one_system(args, rank, world, local_rank):
+    """--mode one-system: ONE 3-D FDEM-h system over all N GPUs (z-slab decomposition, NCCL halo exchange, mode-sharded
+    factors; tools/dist_fdem.py).  N = 2: 109x64x1394 (9.7 M cells), 4: 109x128x1394 (19.4 M), 8: 109x128x3394 = BASELINE
+    configs[4] (47.4 M cells, 142 M complex unknowns) -- each needs more band storage than one B200 has."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from dist_fdem import solve_one_system
+    nth, csz, npadz = ONE_SYSTEM.get(world, ONE_SYSTEM[8])
+    res = solve_one_system(nth, csz, npadz, compare=False, reps=max(args.steps, 1) + 1)
+    if rank == 0:
+        line = {"metric": METRIC, "mode": "one-system", "value": res["s_per_frequency"], "unit": UNIT, "n_gpus": world,
+                "steps": max(args.steps, 1), "warmup": 1, "ms_per_step": res["s_per_frequency"] * 1e3, "higher_is_better": False,
+                "scaling": "one system partitioned over all GPUs (size grows with N)", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                "config": {"workload": "ONE 3-D FDEM-h casing system at 1 Hz, mesh {}x{}x{} = {} cells, {} complex edge unknowns, z slabs {}"
+                           .format(res["mesh"][0], res["mesh"][1], res["mesh"][2], res["cells"], res["edges"], res["zsplit"])},
+                "solve_info": res["info"], "gpu_mem_used_GB_rank0": res["gpu_mem_used_GB_rank0"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong", "one-system"],
+                    help="weak (default, the driver's contract): NFREQ_PER_GPU frequencies per GPU; strong: NFREQ_STRONG frequencies "
+                         "in total, sharded over the GPUs; one-system: ONE system too big for one GPU, z slabs over all GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.mode == "one-system":
+        run_one_system(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 

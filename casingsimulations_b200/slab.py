@@ -58,6 +58,26 @@ def to_local(vec, mesh, family, k0, k1):
     return np.concatenate(parts)
 
 
+def to_local_sparse(idx, val, mesh, family, k0, k1):
+    """to_local for a sparse global vector (indices idx, values val; e.g. a source s_e with a handful of wire faces): the
+    dense LOCAL vector, without ever forming the global one (config 5: 142 M faces)"""
+    idx, val = np.asarray(idx, dtype=np.int64), np.asarray(val)
+    nz = int(mesh.vnC[2])
+    out, g_off, l_off = [], 0, 0
+    pieces = []
+    for per, node in blocks(mesh, family):
+        nlev_g = nz + 1 if node else nz
+        lo, hi = k0, k1 + (1 if node else 0)
+        sel = (idx >= g_off + lo * per) & (idx < g_off + hi * per)
+        pieces.append((l_off + idx[sel] - g_off - lo * per, val[sel]))
+        g_off += per * nlev_g
+        l_off += per * (hi - lo)
+    loc = np.zeros(l_off, dtype=val.dtype if val.size else float)
+    for li, lv in pieces:
+        loc[li] = lv
+    return loc
+
+
 def owned_part(local_vec, mesh, family, zsplit, rank):
     """per block, the owned levels of a LOCAL vector (what a gather collects)"""
     k0, k1 = local_range(zsplit, rank)
