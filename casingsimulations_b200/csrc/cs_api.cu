@@ -550,6 +550,7 @@ extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int c
     CS_CUDA(cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     op->ms_factor = ms;
+    if (getenv("CS_FACTOR_LOG")) fprintf(stderr, "[factor] %d shift(s), n2 %lld, p %d: %.3f ms\n", nshift, bp.n2, bp.p, ms);
     return CS_OK;
 }
 

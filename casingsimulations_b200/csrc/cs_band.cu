@@ -566,15 +566,20 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
 
 template <typename T, int NB>
 __global__ void __launch_bounds__(256)
-k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, const T* __restrict__ scratch) {
+k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, const T* __restrict__ scratch, int part, int tiles) {
     __shared__ T Ls[NB][32];
     __shared__ T Us[NB][33];
     T* A = LU + (size_t)blockIdx.z * nel + pw;
     int nbe = (int)min((long long)NB, n2 - t);
     int R = (int)min((long long)p, n2 - (t + nbe));
-    int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    // part 0: the whole R x R trailing block (grid tiles x tiles).  Look-ahead split: part 1 = the first tile row and tile
+    // column (all the NEXT block step reads; 1-D grid of 2 tiles - 1), part 2 = the rest (grid (tiles-1) x (tiles-1))
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (part == 1) { if (bx < tiles) by = 0; else { by = bx - tiles + 1; bx = 0; } }
+    else if (part == 2) { bx += 1; by += 1; }
+    int a0 = bx * 32, b0 = by * 32;
     int tid = threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
+    if (bx == 0 && by == 0) {
         // put the factored diagonal block (parked by the panel kernel) in place
         const T* S = scratch + (size_t)blockIdx.z * NB * NB;
         for (int e = tid; e < nbe * nbe; e += 256) {
@@ -677,18 +682,41 @@ struct FactorGraph { FactorGraphKey key; cudaGraphExec_t exec; unsigned long lon
 static std::vector<FactorGraph> g_graphs;
 static unsigned long long g_stamp = 0;
 
+// stB == nullptr: one stream, panel -> update per step.  Otherwise (inside stream capture) the look-ahead schedule:
+//   stA:  P(t) -> [wait U2(t-1)] -> U1(t) -> P(t+1) ...        stB:  [wait P(t)] -> U2(t) ...
+// U1(t) = the first tile row / column of the trailing update (everything panel t+1 reads), U2(t) = the rest, so the
+// latency-bound panel of step t+1 runs concurrently with the throughput-bound bulk update of step t.
 template <typename T, int NB>
-static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, cudaStream_t st) {
+static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, cudaStream_t st, cudaStream_t stB = nullptr,
+                               cudaEvent_t evP = nullptr, cudaEvent_t evU = nullptr) {
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
     int tiles = (bp.p + 31) / 32;
     int chunks = (bp.p + 63) / 64;
+    // (timing experiments only: CS_LU_SKIP=panel|update drops one of the two kernels of every step -- wrong factors)
+    static const int skip = [] { const char* e = getenv("CS_LU_SKIP"); return !e ? 0 : (!strcmp(e, "panel") ? 1 : (!strcmp(e, "update") ? 2 : 0)); }();
+    const bool la = stB != nullptr && tiles >= 2;
+    bool have_u2 = false;
     for (long long t = 0; t < bp.n2; t += NB) {
         dim3 gp(chunks, nsys);
-        k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch);
-        dim3 g(tiles, tiles, nsys);
-        k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch);
+        if (skip != 1) k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch);
+        if (skip == 2) continue;
+        if (!la) {
+            dim3 g(tiles, tiles, nsys);
+            k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 0, tiles);
+            continue;
+        }
+        if (cudaEventRecord(evP, st) != cudaSuccess) return CS_ERR;
+        if (have_u2 && cudaStreamWaitEvent(st, evU, 0) != cudaSuccess) return CS_ERR;       // U1(t) overlaps the region U2(t-1) wrote
+        dim3 g1(2 * tiles - 1, 1, nsys);
+        k_lu_update<T, NB><<<g1, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 1, tiles);
+        if (cudaStreamWaitEvent(stB, evP, 0) != cudaSuccess) return CS_ERR;
+        dim3 g2(tiles - 1, tiles - 1, nsys);
+        k_lu_update<T, NB><<<g2, 256, 0, stB>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 2, tiles);
+        if (cudaEventRecord(evU, stB) != cudaSuccess) return CS_ERR;
+        have_u2 = true;
     }
+    if (la && have_u2 && cudaStreamWaitEvent(st, evU, 0) != cudaSuccess) return CS_ERR;      // join
     dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
     k_invert_diag<T, NB><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
     return CS_OK;
@@ -704,6 +732,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_CUDA(cudaGetDevice(&dev_key));
     int groups_key = 0;
     { const char* e = getenv("CS_BAND_GROUPS"); if (e) groups_key = atoi(e); }
+    { const char* e = getenv("CS_LU_LOOKAHEAD"); if (e && atoi(e) == 1) groups_key += 100; }
     FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
@@ -719,7 +748,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     // (inside the captured graph: parallel branches) and hide each other's latency.
     // (capture streams / events belong to a device: one set per device, created on first use under g_band_mu)
     static const int MAXG = 32;
-    struct AuxSet { cudaStream_t aux[MAXG - 1] = {}; cudaEvent_t ev_fork = nullptr, ev_join[MAXG - 1] = {}; };
+    struct AuxSet { cudaStream_t aux[MAXG - 1] = {}, auxB[MAXG] = {}; cudaEvent_t ev_fork = nullptr, ev_join[MAXG - 1] = {}, evP[MAXG] = {}, evU[MAXG] = {}; };
     static std::map<int, AuxSet> aux_sets;
     int dev_now = 0;
     CS_CUDA(cudaGetDevice(&dev_now));
@@ -727,7 +756,15 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     if (!as.ev_fork) {
         cudaEventCreateWithFlags(&as.ev_fork, cudaEventDisableTiming);
         for (int g = 0; g < MAXG - 1; ++g) { cudaStreamCreateWithFlags(&as.aux[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&as.ev_join[g], cudaEventDisableTiming); }
+        for (int g = 0; g < MAXG; ++g) {
+            cudaStreamCreateWithFlags(&as.auxB[g], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&as.evP[g], cudaEventDisableTiming); cudaEventCreateWithFlags(&as.evU[g], cudaEventDisableTiming);
+        }
     }
+    // measured on the 109x32x460 mesh (17 systems, p = 330): 271-273 ms with and without the look-ahead schedule, for 1, 2
+    // and 4 stream groups -- the step time is the sum of the panel chain (11.6 us) and the update chain (17.8 us) either
+    // way, so the simpler two-kernel schedule stays the default (CS_LU_LOOKAHEAD=1 opts in)
+    static const bool lookahead = [] { const char* e = getenv("CS_LU_LOOKAHEAD"); return e && atoi(e) == 1; }();
     cudaStream_t* aux = as.aux; cudaEvent_t ev_fork = as.ev_fork; cudaEvent_t* ev_join = as.ev_join;
     int groups = (nsys >= 16) ? 4 : (nsys >= 6 ? 2 : 1);
     { const char* e = getenv("CS_BAND_GROUPS"); if (e && atoi(e) >= 1) groups = std::min(std::min(atoi(e), nsys), MAXG); }
@@ -740,7 +777,8 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
         for (int g = 0; g < groups && okq; ++g) {
             int s0 = (int)((long long)nsys * g / groups), s1 = (int)((long long)nsys * (g + 1) / groups);
             cudaStream_t sg = (g == 0) ? st : aux[g - 1];
-            okq = okq && band_factor_enqueue<T, NB>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NB * NB, sg) == CS_OK;
+            okq = okq && band_factor_enqueue<T, NB>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NB * NB, sg,
+                                                    lookahead ? as.auxB[g] : nullptr, as.evP[g], as.evU[g]) == CS_OK;
         }
         for (int g = 1; g < groups; ++g) {
             okq = okq && cudaEventRecord(ev_join[g - 1], aux[g - 1]) == cudaSuccess;
