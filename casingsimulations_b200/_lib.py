@@ -70,6 +70,8 @@ def load_library():
         "cs_curlT": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_div": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_divT": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_ave_f2ccv": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_ave_e2ccv": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_op_get": (c.c_int, [vp, c.c_int, c.POINTER(vp)]),
         "cs_op_get_noplan": (c.c_int, [vp, c.c_int, c.POINTER(vp)]),
         "cs_op_apply_timed": (c.c_int, [vp, dp, vp, vp, c.c_int, c.c_int, c.c_int, dp]),
@@ -82,6 +84,7 @@ def load_library():
         "cs_solve_dc": (c.c_int, [vp, vp, vp, c.c_int, c.c_double, c.c_int, dp]),
         "cs_solve_fdem": (c.c_int, [vp, c.c_int, dp, c.c_int, vp, vp, c.c_double, c.c_int, dp]),
         "cs_tdem_run": (c.c_int, [vp, c.c_int, dp, c.c_int, vp, vp, c.c_double, c.c_int, dp]),
+        "cs_tdem_run_multi": (c.c_int, [vp, c.c_int, dp, c.c_int, vp, c.c_int, vp, c.c_double, c.c_int, dp]),
         "cs_fields_fdem": (c.c_int, [vp, c.c_int, c.c_int, c.c_double, vp, vp, vp]),
         "cs_fields_dc": (c.c_int, [vp, c.c_int, vp, vp, c.c_int]),
         "cs_casing_currents": (c.c_int, [vp, vp, c.c_int, c.c_double, c.c_double, c.c_double, c.c_double, vp, vp]),
@@ -99,8 +102,8 @@ EXPORTED_SYMBOLS = [
     "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_fp64_peak", "cs_ctx_set_refine",
     "cs_comm_unique_id", "cs_comm_init", "cs_comm_local_range", "cs_comm_halo", "cs_mesh_set",
     "cs_mesh_counts", "cs_model_paint", "cs_model_set", "cs_face_inner_product", "cs_edge_inner_product",
-    "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_op_get", "cs_op_get_noplan", "cs_op_apply_timed", "cs_op_from_csr", "cs_op_size", "cs_op_apply", "cs_op_factor",
-    "cs_op_solve", "cs_op_clean", "cs_solve_dc", "cs_solve_fdem", "cs_tdem_run", "cs_fields_fdem",
+    "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_ave_f2ccv", "cs_ave_e2ccv", "cs_op_get", "cs_op_get_noplan", "cs_op_apply_timed", "cs_op_from_csr", "cs_op_size", "cs_op_apply", "cs_op_factor",
+    "cs_op_solve", "cs_op_clean", "cs_solve_dc", "cs_solve_fdem", "cs_tdem_run", "cs_tdem_run_multi", "cs_fields_fdem",
     "cs_fields_dc", "cs_casing_currents", "cs_casing_charges",
 ]
 
@@ -378,6 +381,14 @@ class Context(object):
     def divT(self, xC):
         return self._unary(self.lib.cs_divT, xC, self.nC, self.nF)
 
+    def ave_f2ccv(self, xF):
+        """mesh.aveF2CCV * xF: cell-centred vector, blocks [x | y | z] ([x | z] on a symmetric mesh)"""
+        return self._unary(self.lib.cs_ave_f2ccv, xF, self.nF, self.nC * (2 if self.nth == 1 else 3))
+
+    def ave_e2ccv(self, xE):
+        """mesh.aveE2CCV * xE: cell-centred vector, blocks [x | y | z] ([y] on a symmetric mesh)"""
+        return self._unary(self.lib.cs_ave_e2ccv, xE, self.nE, self.nC * (1 if self.nth == 1 else 3))
+
     def op(self, kind, plan=True):
         if plan:
             return Op(self, kind)
@@ -436,16 +447,21 @@ class Context(object):
         return u
 
     def tdem_run(self, form, dts, s_e, rtol=1e-10, maxit=50):
+        """s_e: (nF,) -> (nsteps+1, nF), or (nsrc, nF) -> (nsteps+1, nsrc, nF): all sources share the factorisations"""
         dts = np.ascontiguousarray(dts, dtype=np.float64)
-        out = self.empty(self.nF, False, cols=len(dts) + 1)
+        multi = s_e.dim() == 2
+        se2 = s_e.reshape(-1, self.nF).contiguous()
+        nsrc = se2.shape[0]
+        torch = _torch()
+        out = torch.empty((len(dts) + 1, nsrc, self.nF), dtype=torch.float64, device=self.device)
         info = np.zeros(INFO_LEN)
         self._enter()
-        rc = self.lib.cs_tdem_run(self.h, ord(form), _dptr(dts), len(dts), _tptr(s_e.contiguous()), _tptr(out),
-                                  rtol, maxit, info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        rc = self.lib.cs_tdem_run_multi(self.h, ord(form), _dptr(dts), len(dts), _tptr(se2), nsrc, _tptr(out),
+                                        rtol, maxit, info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
         self._exit()
         self._info(info)
         check(rc)
-        return out
+        return out if multi else out[:, 0, :]
 
     def fields_fdem(self, form, which, freq, u, s_e):
         n = self.nF if which in ("j", "e") else self.nE

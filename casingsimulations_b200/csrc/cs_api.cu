@@ -1456,6 +1456,16 @@ extern "C" int cs_curlT(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c 
 extern "C" int cs_div(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_div(c->m, x, y, ic != 0, c->st); }
 extern "C" int cs_divT(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_divT(c->m, x, y, ic != 0, c->st); }
 
+// mesh.aveF2CCV * v / mesh.aveE2CCV * v (view.py:300-308): cell-centred vector blocks [x | y | z] of nC each
+extern "C" int cs_ave_f2ccv(cs_ctx* c, const void* xF_d, void* yCCV_d, int ic) {
+    CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1;
+    return launch_ave_ccv(c->m, true, xF_d, yCCV_d, ic != 0, c->st);
+}
+extern "C" int cs_ave_e2ccv(cs_ctx* c, const void* xE_d, void* yCCV_d, int ic) {
+    CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1;
+    return launch_ave_ccv(c->m, false, xE_d, yCCV_d, ic != 0, c->st);
+}
+
 // ------------------------------------------------------- physics drivers ------
 static void info_begin(double* info) { if (info) memset(info, 0, CS_INFO_LEN * sizeof(double)); }
 
@@ -1555,34 +1565,40 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
     return rc;
 }
 
-extern "C" int cs_tdem_run(cs_ctx* c, int form, const double* dts_h, int nsteps, const double* s_e_d,
-                           double* out_d, double rtol, int maxit, double* info) {
+// Backward Euler for nsrc sources at once: they share every factorisation (one per distinct dt) and travel as columns
+// of one batched solve, like SimPEG's (n x nSrc) right-hand sides.  s_e_d: [nsrc][nF]; out_d: [nsteps+1][nsrc][nF].
+extern "C" int cs_tdem_run_multi(cs_ctx* c, int form, const double* dts_h, int nsteps, const double* s_e_d, int nsrc,
+                                 double* out_d, double rtol, int maxit, double* info) {
     CS_CHECK(c && c->has_model, "model not set");
     CS_CHECK(form == 'j', "cs_tdem_run implements the (default) j formulation");
+    CS_CHECK(nsrc >= 1 && nsteps >= 0, "bad arguments");
     long long l0 = g_launches;
     info_begin(info);
     const MeshD& m = c->m;
-    long long nF = m.nF, nC = m.nC;
+    const long long nF = m.nF, nC = m.nC;
+    const long long NF = nF * nsrc, NC = nC * nsrc;
     cs_op *dc = nullptr, *op = nullptr;
     CS_TRY(cs_op_get(c, CS_KIND_DC_GROUNDED, &dc));
     CS_TRY(cs_op_get(c, CS_KIND_FACE_J, &op));
     double inf2[CS_INFO_LEN];
     DevBuf b1, b2, b3;
     b1.pool = b2.pool = b3.pool = &c->pool;
-    CS_TRY(b1.ensure((size_t)nC * 8)); CS_TRY(b2.ensure((size_t)nC * 8)); CS_TRY(b3.ensure((size_t)nF * 8));
+    CS_TRY(b1.ensure((size_t)NC * 8)); CS_TRY(b2.ensure((size_t)NC * 8)); CS_TRY(b3.ensure((size_t)NF * 8));
     double ms_fac = 0, ms_sol = 0, worst = 0;
+    auto div_all = [&](const double* xF, double* yC) -> int { for (int s = 0; s < nsrc; ++s) CS_TRY(launch_div(m, xF + s * nF, yC + s * nC, false, c->st)); g_launches += nsrc; return CS_OK; };
+    auto divT_all = [&](const double* xC, double* yF) -> int { for (int s = 0; s < nsrc; ++s) CS_TRY(launch_divT(m, xC + s * nC, yF + s * nF, false, c->st)); g_launches += nsrc; return CS_OK; };
     // initial DC state: phi = Adc^-1 (Dt s_e); j0 = -MfRhoI Dt^T phi     (A.7)
     { double z[2] = {0, 0}; CS_TRY(cs_op_factor(dc, z, 1, 0)); ms_fac += dc->ms_factor; }
-    CS_TRY(launch_div(m, s_e_d, b1.p, false, c->st));
+    CS_TRY(div_all(s_e_d, (double*)b1.p));
     memset(inf2, 0, sizeof inf2);
-    int rc = krylov_solve(dc, b1.p, b2.p, 1, nullptr, false, rtol, maxit, inf2);
-    if (rc) { b1.release(); b2.release(); b3.release(); return rc; }
+    int rc = krylov_solve(dc, b1.p, b2.p, nsrc, nullptr, false, rtol, maxit, inf2);
+    if (rc) return rc;
     worst = std::max(worst, inf2[CS_INFO_RELRES]);
-    CS_TRY(launch_divT(m, b2.p, b3.p, false, c->st));
-    CS_TRY(launch_mul_real(b3.p, b3.p, op->mass, nF, 1, false, 1, c->st));      // / MfRho
-    k_scale_add<<<cdiv(nF, 256), 256, 0, c->st>>>(out_d, (const double*)b3.p, nF, -1.0, 0.0);
+    CS_TRY(divT_all((const double*)b2.p, (double*)b3.p));
+    CS_TRY(launch_mul_real(b3.p, b3.p, op->mass, nF, nsrc, false, 1, c->st));      // / MfRho
+    k_scale_add<<<cdiv(NF, 256), 256, 0, c->st>>>(out_d, (const double*)b3.p, NF, -1.0, 0.0);
     CS_CUDA(cudaGetLastError());
-    g_launches += 4;
+    g_launches += 2;
     // the DC factors stay alive: they drive the divergence cleaning below
     double dt_prev = -1.0;
     CS_CUDA(cudaEventRecord(c->ev0, c->st));
@@ -1597,15 +1613,16 @@ extern "C" int cs_tdem_run(cs_ctx* c, int form, const double* dts_h, int nsteps,
             dt_prev = dt;
         }
         // rhs = MfRho .* (j^n + [t == 0] s_e) / dt
-        const double* jn = out_d + (size_t)t * nF;
+        const double* jn = out_d + (size_t)t * NF;
         double* rhs = (double*)b3.p;
         cudaEventRecord(e0, c->st);
-        k_scale_add<<<cdiv(nF, 256), 256, 0, c->st>>>(rhs, jn, nF, 1.0 / dt_prev, 0.0);
-        if (t == 0) k_scale_add<<<cdiv(nF, 256), 256, 0, c->st>>>(rhs, s_e_d, nF, 1.0 / dt_prev, 1.0);
-        CS_TRY(launch_mul_real(rhs, rhs, op->mass, nF, 1, false, 0, c->st));
+        k_scale_add<<<cdiv(NF, 256), 256, 0, c->st>>>(rhs, jn, NF, 1.0 / dt_prev, 0.0);
+        if (t == 0) k_scale_add<<<cdiv(NF, 256), 256, 0, c->st>>>(rhs, s_e_d, NF, 1.0 / dt_prev, 1.0);
+        rc = launch_mul_real(rhs, rhs, op->mass, nF, nsrc, false, 0, c->st);
+        if (rc) break;
         g_launches += 3;
         memset(inf2, 0, sizeof inf2);
-        rc = krylov_solve(op, rhs, out_d + (size_t)(t + 1) * nF, 1, nullptr, false, rtol, maxit, inf2);
+        rc = krylov_solve(op, rhs, out_d + (size_t)(t + 1) * NF, nsrc, nullptr, false, rtol, maxit, inf2);
         cudaEventRecord(e1, c->st); cudaStreamSynchronize(c->st);
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms_sol += ms;
         worst = std::max(worst, inf2[CS_INFO_RELRES]);
@@ -1618,26 +1635,31 @@ extern "C" int cs_tdem_run(cs_ctx* c, int form, const double* dts_h, int nsteps,
         // junk that backward Euler never damps.  Project it out in the MfRho inner product:
         //   j <- j - MfRhoI Dt^T (Dt MfRhoI Dt^T)^-1 Dt j        (a no-op on the exact solution)
         {
-            double* jn1 = out_d + (size_t)(t + 1) * nF;
-            CS_TRY(launch_div(m, jn1, b1.p, false, c->st));
+            double* jn1 = out_d + (size_t)(t + 1) * NF;
+            rc = div_all(jn1, (double*)b1.p);
+            if (rc) break;
             memset(inf2, 0, sizeof inf2);
-            int rcc = krylov_solve(dc, b1.p, b2.p, 1, nullptr, false, rtol, maxit, inf2);
-            if (rcc != CS_OK) { rc = rcc; break; }          // a failed cleaning solve is an error, not a skip
-            CS_TRY(launch_divT(m, b2.p, b3.p, false, c->st));
-            CS_TRY(launch_mul_real(b3.p, b3.p, op->mass, nF, 1, false, 1, c->st));      // / MfRho
-            k_scale_add<<<cdiv(nF, 256), 256, 0, c->st>>>(jn1, (const double*)b3.p, nF, -1.0, 1.0);
-            CS_CUDA(cudaGetLastError());
-            g_launches += 4;
+            rc = krylov_solve(dc, b1.p, b2.p, nsrc, nullptr, false, rtol, maxit, inf2);
+            if (rc != CS_OK) break;                             // a failed cleaning solve is an error, not a skip
+            rc = divT_all((const double*)b2.p, (double*)b3.p);
+            if (rc) break;
+            rc = launch_mul_real(b3.p, b3.p, op->mass, nF, nsrc, false, 1, c->st);      // / MfRho
+            if (rc) break;
+            k_scale_add<<<cdiv(NF, 256), 256, 0, c->st>>>(jn1, (const double*)b3.p, NF, -1.0, 1.0);
+            g_launches += 2;
         }
     }
     cs_op_clean(dc);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    b1.release(); b2.release(); b3.release();
     if (info) {
         info[CS_INFO_RELRES] = worst; info[CS_INFO_MS_FACTOR] = ms_fac; info[CS_INFO_MS_SOLVE] = ms_sol;
         info[CS_INFO_MS_ASSEMBLE] = op->ms_assemble + dc->ms_assemble; info[CS_INFO_N_LAUNCH] = (double)(g_launches - l0); info[CS_INFO_CONVERGED] = rc == CS_OK;
     }
     return rc;
+}
+extern "C" int cs_tdem_run(cs_ctx* c, int form, const double* dts_h, int nsteps, const double* s_e_d,
+                           double* out_d, double rtol, int maxit, double* info) {
+    return cs_tdem_run_multi(c, form, dts_h, nsteps, s_e_d, 1, out_d, rtol, maxit, info);
 }
 
 // derived fields (SURVEY A.5 / A.6 last columns) --------------------------------

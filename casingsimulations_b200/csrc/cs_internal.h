@@ -24,6 +24,8 @@ int launch_divT(const MeshD& m, const void* xC, void* yF, bool cplx_vec, cudaStr
 // y_F = edgeCurl x_E ; y_E = edgeCurl^T x_F
 int launch_curl(const MeshD& m, const void* xE, void* yF, bool cplx_vec, cudaStream_t st);
 int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaStream_t st);
+// mesh.aveF2CCV / aveE2CCV: face / edge vector -> cell-centred vector, blocks [x | y | z] (view.py:300-308)
+int launch_ave_ccv(const MeshD& m, bool from_faces, const void* x, void* y, bool cplx_vec, cudaStream_t st);
 // K4 edge form: y = C^T diag(alpha) C x + s[sys] * beta .* x, wF = alpha/area^2
 int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const double* s_d /*2 doubles per sys*/,
                    const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);

@@ -318,6 +318,53 @@ int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaSt
     return CS_OK;
 }
 
+// ============================ face / edge -> cell-centre vector averages ==========
+// discretize mesh.aveF2CCV / aveE2CCV as used by the viewer's re-gridding (view.py:300-308): per cell the average of the
+// faces (2) / edges (4) of each component around it, output blocks [x | y | z] of nC (symmetric mesh: [x | z] for faces,
+// [y] for edges).  Same radial axis weights as the inner products.
+template <typename T>
+__global__ void k_ave_f2ccv(MeshD m, const T* __restrict__ xF, T* __restrict__ y) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz, s)) return;
+    const int i = s.i, j = s.j, k = s.k;
+    const long long c = m.cidx(i, j, k);
+    const T* fx = xF; const T* fy = xF + m.nFx; const T* fz = xF + m.nFx + m.nFy;
+    y[c] = (i > 0) ? 0.5 * (fx[c - 1] + fx[c]) : m.w_axis_face * fx[c];
+    long long o = m.nC;
+    if (!m.sym) { y[o + c] = 0.5 * (fy[c] + fy[m.cidx(i, m.jp(j), k)]); o += m.nC; }
+    y[o + c] = 0.5 * (fz[c] + fz[c + m.nxy]);
+}
+template <typename T>
+__global__ void k_ave_e2ccv(MeshD m, const T* __restrict__ xE, T* __restrict__ y) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz, s)) return;
+    const int i = s.i, j = s.j, k = s.k;
+    const long long c = m.cidx(i, j, k), cu = c + m.nxy;      // node levels k and k + 1
+    const T* ey = xE + m.nEx;
+    T vy = (i > 0) ? 0.25 * (ey[c - 1] + ey[c] + ey[cu - 1] + ey[cu]) : (0.5 * m.w_axis_edge) * (ey[c] + ey[cu]);
+    if (m.sym) { y[c] = vy; return; }
+    const T* ex = xE; const T* ez = xE + m.nEx + m.nEy;
+    const int jp = m.jp(j);
+    const long long cj = m.cidx(i, jp, k);
+    y[c] = 0.25 * (ex[c] + ex[cj] + ex[cu] + ex[cj + m.nxy]);
+    y[m.nC + c] = vy;
+    T zin0 = (i > 0) ? ez[m.ez(i - 1, j, k)] : ez[m.ezaxis(k)], zin1 = (i > 0) ? ez[m.ez(i - 1, jp, k)] : ez[m.ezaxis(k)];
+    y[2 * m.nC + c] = 0.25 * (zin0 + ez[m.ez(i, j, k)] + zin1 + ez[m.ez(i, jp, k)]);
+}
+int launch_ave_ccv(const MeshD& m, bool from_faces, const void* x, void* y, bool cplx_vec, cudaStream_t st) {
+    if (from_faces) {
+        if (cplx_vec) k_ave_f2ccv<cplx><<<grid1(m.nC), TPB, 0, st>>>(m, (const cplx*)x, (cplx*)y);
+        else k_ave_f2ccv<double><<<grid1(m.nC), TPB, 0, st>>>(m, (const double*)x, (double*)y);
+    } else {
+        if (cplx_vec) k_ave_e2ccv<cplx><<<grid1(m.nC), TPB, 0, st>>>(m, (const cplx*)x, (cplx*)y);
+        else k_ave_e2ccv<double><<<grid1(m.nC), TPB, 0, st>>>(m, (const double*)x, (double*)y);
+    }
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
 // ============================ K4: fused edge-form operator =======================
 // y = C^T diag(alpha) C x + s * beta .* x  with C = diag(1/area) C_topo diag(len):
 //   y_e = len_e * sum_{f around e} +-[ wF_f * circ_f(len .* x) ] + s beta_e x_e,

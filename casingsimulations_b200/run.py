@@ -281,14 +281,11 @@ class _ProblemTDEM(_Problem):
         self._set_model(m)
         ctx = self.ctx
         srcs = self.survey.srcList
-        sol = np.zeros((self.mesh.nF, len(srcs), len(self.timeSteps) + 1))
-        info = {}
-        for i, s in enumerate(srcs):
-            out = ctx.tdem_run(self.form, self.timeSteps, ctx.to_device(np.real(s.s_e), complex_=False),
-                               rtol=self.rtol, maxit=self.maxit)
-            sol[:, i, :] = out.cpu().numpy().T
-            for key, val in ctx.info.items():
-                info[key] = max(info.get(key, 0.0), val) if key == "relres" else info.get(key, 0.0) + val
+        # all sources of the survey at once: (n x nSrc) right-hand sides sharing every factorisation
+        se = np.ascontiguousarray(np.stack([np.real(s.s_e) for s in srcs]))
+        out = ctx.tdem_run(self.form, self.timeSteps, ctx.to_device(se, complex_=False), rtol=self.rtol, maxit=self.maxit)
+        sol = np.ascontiguousarray(out.cpu().numpy().transpose(2, 1, 0))             # (nF, nSrc, nT+1)
+        info = dict(ctx.info)
         self.info = info
         return Fields(self, sol, srcs, times=self.times)
 

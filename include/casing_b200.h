@@ -101,6 +101,11 @@ int cs_curlT(cs_ctx* ctx, const void* xF_d, void* yE_d, int is_complex);
 int cs_div(cs_ctx* ctx, const void* xF_d, void* yC_d, int is_complex);
 int cs_divT(cs_ctx* ctx, const void* xC_d, void* yF_d, int is_complex);
 
+/* mesh.aveF2CCV / mesh.aveE2CCV applied to a vector: the viewer's re-gridding to cell centres (view.py:300-308).
+ * Output blocks [x | y | z] of nC entries (symmetric mesh: [x | z] from faces, [y] from edges). */
+int cs_ave_f2ccv(cs_ctx* ctx, const void* xF_d, void* yCCV_d, int is_complex);
+int cs_ave_e2ccv(cs_ctx* ctx, const void* xE_d, void* yCCV_d, int is_complex);
+
 /* operator objects: weights (K2) + band plan + probed theta-mode band matrices.
  * Cached per kind inside the context; invalidated by cs_model_* / cs_mesh_set. */
 int cs_op_get(cs_ctx* ctx, int kind, cs_op** out);
@@ -135,6 +140,11 @@ int cs_solve_fdem(cs_ctx* ctx, int form, const double* freqs_h, int nfreq, const
  * (nF x (nsteps+1)) column-major                                     run.py:205, 284-301 */
 int cs_tdem_run(cs_ctx* ctx, int form, const double* dts_h, int nsteps, const double* s_e_d,
                 double* out_d, double rtol, int maxit, double* info_h);
+
+/* the same for nsrc sources at once (SimPEG's (n x nSrc) right-hand sides): they share every factorisation.
+ * s_e_d: [nsrc][nF]; out_d: [nsteps+1][nsrc][nF]                                  sources.py:948-973 (SourceList) */
+int cs_tdem_run_multi(cs_ctx* ctx, int form, const double* dts_h, int nsteps, const double* s_e_d, int nsrc,
+                      double* out_d, double rtol, int maxit, double* info_h);
 
 /* Fields derived quantities (tests/test_cyl2D3D.py:212,266; run.py:211)
  * which: 'j','e','h','b' ; kind: the formulation the solution u came from */

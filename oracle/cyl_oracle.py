@@ -355,6 +355,29 @@ class OracleCylMesh(object):
         AvEz = AvEz_full @ self._ez_full_to_deflated().T        # nC x deflated
         return sp.vstack([AvEx.T, AvEy.T, AvEz.T], format="csr")
 
+    # ---- vector averages to cell centres (view.py:300-308: mesh.aveF2CCV, mesh.aveE2CCV) [3P-recall] ----
+    @property
+    def aveF2CCV(self):
+        """block diagonal of the face -> cell averages of each component: (2|3) nC x nF"""
+        nx, nth, nz = self.nx, self.nth, self.nz
+        Ix, It, Iz = sp.identity(nx), sp.identity(nth), sp.identity(nz)
+        AvFx = _kron3(Iz, It, self._avR(self.axis_weight_face))
+        AvFz = _kron3(_av(nz), It, Ix)
+        if self.isSymmetric:
+            return sp.block_diag([AvFx, AvFz], format="csr")
+        return sp.block_diag([AvFx, _kron3(Iz, _av_periodic(nth), Ix), AvFz], format="csr")
+
+    @property
+    def aveE2CCV(self):
+        """block diagonal of the edge -> cell averages of each component: (1|3) nC x nE"""
+        return sp.block_diag([b.T for b in self._edge_average_blocks()], format="csr")
+
+    def _edge_average_blocks(self):
+        full = self.edge_average_transpose()
+        if self.isSymmetric:
+            return [full]
+        return [full[:self.nEx], full[self.nEx:self.nEx + self.nEy], full[self.nEx + self.nEy:]]
+
     def getFaceInnerProduct(self, prop=None, invProp=False, invMat=False):
         p = np.ones(self.nC, dtype=self.dtype) if prop is None else np.asarray(prop, dtype=self.dtype)
         if invProp:

@@ -395,3 +395,24 @@ def test_nonuniform_azimuthal_widths():
     with pytest.raises(_lib.CasingB200Error):
         ctx.solve_fdem("h", [100.0], ctx.to_device(se), rtol=1e-10, maxit=60)
     ctx.close()
+
+
+@pytest.mark.parametrize("nth", [1, 4])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_cell_centre_vector_averages(gpu_ctx, nth, cplx):
+    """mesh.aveF2CCV / mesh.aveE2CCV (view.py:300-308) on the GPU against the oracle's averaging matrices"""
+    om, *_ = setup(gpu_ctx, nth)
+    xF, xE = rnd(om.nF, cplx, 3), rnd(om.nE, cplx, 5)
+    yF = gpu_ctx.ave_f2ccv(gpu_ctx.to_device(xF)).cpu().numpy()
+    yE = gpu_ctx.ave_e2ccv(gpu_ctx.to_device(xE)).cpu().numpy()
+    assert yF.shape[0] == om.nC * (2 if nth == 1 else 3) and yE.shape[0] == om.nC * (1 if nth == 1 else 3)
+    assert rel(yF, om.aveF2CCV @ xF) < 1e-14 and rel(yE, om.aveE2CCV @ xE) < 1e-14
+    import casingsimulations_b200 as cs
+    from conftest import small_casing_mesh
+    hx, hy, hz, z0 = small_casing_mesh(nth)
+    mesh = cs.CylMesh([hx, hy, hz], x0=[0, 0, z0])
+    ccv = cs.utils.average_to_cell_centers(xF, mesh)
+    assert ccv.shape == (om.nC, 2 if nth == 1 else 3) and rel(ccv.reshape(-1, order="F"), om.aveF2CCV @ xF) < 1e-14
+    cart = cs.utils.cyl_to_cart(ccv, mesh)
+    assert cart.shape == (om.nC, 3) and np.allclose(np.abs(cart[:, 0]) ** 2 + np.abs(cart[:, 1]) ** 2,
+                                                     np.abs(ccv[:, 0]) ** 2 + (np.abs(ccv[:, 1]) ** 2 if nth > 1 else 0.0))

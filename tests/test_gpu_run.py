@@ -792,3 +792,26 @@ def test_z_slab_solve_two_gpus_matches_single_gpu():
     print(res)
     assert res["n_gpus"] == 2 and res["info"]["relres"] <= 1e-10
     assert res["rel_diff_vs_single_gpu_j"] < 1e-9 and res["rel_diff_vs_single_gpu_h"] < 1e-6
+
+
+def test_tdem_source_list_shares_factorisations(tmp_path):
+    """run.py:284-301 with a SourceList (sources.py:948-973): the sources of a TDEM survey are columns of one batched
+    backward-Euler run that share every factorisation; each column equals the single-source run."""
+    tmp = str(tmp_path / "simTL")
+    mp, mg = _casing_sim(tmp, 1, npadx=4, npadz=5, csz=10.0)
+    s1 = sources.TopCasingSrc(directory=tmp, modelParameters=mp, meshGenerator=mg, physics="tdem")
+    s2 = sources.DownHoleCasingSrc(directory=tmp, modelParameters=mp, meshGenerator=mg, physics="tdem",
+                                   src_a=np.r_[0.0, 0.0, -50.0], src_b=np.r_[500.0, 0.0, 0.0])
+    sl = sources.SourceList(directory=tmp, sources=[s1, s2])
+    sim = run.SimulationTDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, srcList=sl)
+    f = sim.run(save=False)
+    both = f[:, "jSolution"]
+    assert both.shape == (mg.mesh.nF, 2, 7)
+    t_fac_both = sim.prob.info["ms_factor"]
+    sim.prob.clean()
+    for k, s in enumerate((s1, s2)):
+        one = run.SimulationTDEM(directory=tmp, modelParameters=mp, meshGenerator=mg, src=s)
+        f1 = one.run(save=False)
+        assert rel(both[:, k, :], f1[:, "jSolution"]) < 1e-9, k
+        one.prob.clean()
+    print("factor ms for both sources", t_fac_both)
