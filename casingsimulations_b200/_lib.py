@@ -435,7 +435,11 @@ class Context(object):
     def solve_fdem(self, form, freqs, s_e, rtol=1e-10, maxit=50):
         """s_e: real face vector (device); returns (nfreq, n) complex solutions."""
         freqs = np.ascontiguousarray(np.atleast_1d(freqs), dtype=np.float64)
-        n = self.nE if form == "h" else self.nF
+        n = self.nE if form in ("h", "e") else self.nF
+        nsrc = self.nE if form in ("e", "b") else self.nF        # E-B forms take an EDGE source vector (SURVEY A.6)
+        if s_e.numel() != nsrc:
+            raise CasingB200Error("the {} formulation takes a source vector on {} ({} entries), got {}".format(
+                form, "edges" if form in ("e", "b") else "faces", nsrc, s_e.numel()))
         u = self.empty(n, True, cols=len(freqs))
         info = np.zeros(INFO_LEN)
         self._enter()
@@ -464,7 +468,10 @@ class Context(object):
         return out if multi else out[:, 0, :]
 
     def fields_fdem(self, form, which, freq, u, s_e):
-        n = self.nF if which in ("j", "e") else self.nE
+        if form in ("e", "b"):
+            n = self.nF if which == "b" else self.nE              # E-B forms: e, j on edges, b on faces
+        else:
+            n = self.nF if which in ("j", "e") else self.nE
         out = self.empty(n, True)
         self._enter()
         check(self.lib.cs_fields_fdem(self.h, ord(form), ord(which), float(freq), _tptr(u.contiguous()),

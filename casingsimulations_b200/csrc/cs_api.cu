@@ -171,7 +171,7 @@ __global__ void k_rhs_fdem_j(const double* __restrict__ alpha, const double* __r
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n) return;
     int f = blockIdx.y;
-    out[f * n + t] = mk(0.0, -w[f] * alpha[t] * se[t]);
+    out[f * n + t] = mk(0.0, -w[f] * (alpha ? alpha[t] : 1.0) * se[t]);
 }
 // K9: masked area-weighted sums over (r, theta) per z level (physics.py:29-57)
 template <typename T>
@@ -1484,16 +1484,23 @@ extern "C" int cs_solve_dc(cs_ctx* c, const double* q_d, double* phi_d, int nrhs
     return rc;
 }
 
+static inline bool m_is_sym(cs_ctx* c) { return c && c->has_mesh && c->m.sym; }
+
 extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfreq, const double* s_e_d,
                              void* u_d, double rtol, int maxit, double* info) {
     CS_CHECK(c && c->has_model, "model not set");
-    CS_CHECK(form == 'h' || form == 'j', "cs_solve_fdem supports the face-source formulations 'h' and 'j'");
+    CS_CHECK(form == 'h' || form == 'j' || form == 'e' || form == 'b', "formulation must be one of e, b, h, j");
     CS_CHECK(nfreq >= 1, "no frequencies");
+    CS_CHECK(!(m_is_sym(c) && (form == 'e' || form == 'b')), "the e / b formulations need a 3-D mesh: a cylindrically symmetric mesh has E_theta edges only "
+             "(TE mode), a galvanic casing source drives the TM mode of the h / j formulations");
     long long l0 = g_launches;
     info_begin(info);
     const MeshD& m = c->m;
     cs_op* op = nullptr;
-    CS_TRY(cs_op_get(c, form == 'h' ? CS_KIND_EDGE_H : CS_KIND_FACE_J, &op));
+    // h, j: s_e is the FACE current density of casingSimulations' sources (sources.py:236); e, b: an EDGE vector, the
+    // integrated source of SimPEG's RawVec_e for the E-B formulations
+    const int kind = form == 'h' ? CS_KIND_EDGE_H : (form == 'j' ? CS_KIND_FACE_J : (form == 'e' ? CS_KIND_EDGE_E : CS_KIND_FACE_B));
+    CS_TRY(cs_op_get(c, kind, &op));
     long long n = op->n;
     // how many frequencies fit at once (driver queries only when the cached buffers are too small:
     // cudaMemGetInfo / cudaMalloc / cudaFree serialise against concurrent nvidia-smi polling)
@@ -1531,11 +1538,22 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
             CS_TRY(launch_curlT(m, a, c->tmp2.p, false, c->st));
             for (int f = 0; f < nf; ++f) CS_TRY(launch_real_to_cplx((const double*)c->tmp2.p, (cplx*)rhs.p + (size_t)f * n, n, c->st));
             g_launches += 4 + nf;
+        } else if (form == 'b') {
+            // rhs = MfMui .* (C (MeSigmaI .* s_e)), identical for every frequency
+            CS_TRY(c->tmp1.ensure((size_t)std::max(m.nF, m.nE) * 8)); CS_TRY(c->tmp2.ensure((size_t)m.nF * 8));
+            double* a = (double*)c->tmp1.p;
+            CS_TRY(launch_edge_ip(m, c->sigma, 0, 1, a, c->st));                        // 1 / MeSigma
+            CS_TRY(launch_mul_real(a, s_e_d, a, m.nE, 1, false, 0, c->st));
+            CS_TRY(launch_curl(m, a, c->tmp2.p, false, c->st));
+            CS_TRY(launch_mul_real(c->tmp2.p, c->tmp2.p, op->mass, m.nF, 1, false, 0, c->st));   // .* MfMui
+            for (int f = 0; f < nf; ++f) CS_TRY(launch_real_to_cplx((const double*)c->tmp2.p, (cplx*)rhs.p + (size_t)f * n, n, c->st));
+            g_launches += 4 + nf;
         } else {
+            // j: rhs = MfRho .* (-i w s_e)    e: rhs = -i w s_e
             CS_TRY(c->scal.ensure(std::max<size_t>(4096, nf * 8)));
             CS_CUDA(cudaMemcpyAsync(c->scal.p, w.data(), nf * 8, cudaMemcpyHostToDevice, c->st));
             dim3 g((unsigned)cdiv(n, 256), nf);
-            k_rhs_fdem_j<<<g, 256, 0, c->st>>>(op->mass, s_e_d, n, (const double*)c->scal.p, (cplx*)rhs.p);
+            k_rhs_fdem_j<<<g, 256, 0, c->st>>>(form == 'j' ? op->mass : nullptr, s_e_d, n, (const double*)c->scal.p, (cplx*)rhs.p);
             CS_CUDA(cudaGetLastError());
             CS_CUDA(cudaStreamSynchronize(c->st));
             g_launches += 1;
@@ -1683,11 +1701,42 @@ static int ratio_scale(cs_ctx* c, bool face, const double* prop_num, int inv_num
 
 extern "C" int cs_fields_fdem(cs_ctx* c, int form, int which, double freq, const void* u_d, const double* s_e_d, void* out_d) {
     CS_CHECK(c && c->has_model, "model not set");
-    CS_CHECK(form == 'h' || form == 'j', "fields implemented for the formulations h and j");
+    CS_CHECK(form == 'h' || form == 'j' || form == 'e' || form == 'b', "formulation must be one of e, b, h, j");
     CS_CUDA(cudaSetDevice(c->device));
     const MeshD& m = c->m;
     double w = 2 * M_PI * freq;
     cplx* out = (cplx*)out_d;
+    if (form == 'e' || form == 'b') {
+        // E-B formulations (s_e_d is an EDGE vector): e on edges, b on faces, j = Me^-1 MeSigma e on edges
+        const double* none = nullptr;
+        if (form == 'e') {
+            if (which == 'e' || which == 'j') {
+                CS_CUDA(cudaMemcpyAsync(out, u_d, m.nE * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
+                if (which == 'j') CS_TRY(ratio_scale(c, false, c->sigma, 0, out, true));
+                return CS_OK;
+            }
+            CS_CHECK(which == 'b', "the e formulation provides e, j (edges) and b (faces)");
+            CS_TRY(launch_curl(m, u_d, out, true, c->st));                              // b = -(C e) / (i w) = (i / w) C e
+            k_cscale<<<cdiv(m.nF, 256), 256, 0, c->st>>>(out, m.nF, 0.0, 1.0 / w);
+            CS_CUDA(cudaGetLastError());
+            g_launches += 2;
+            return CS_OK;
+        }
+        if (which == 'b') { CS_CUDA(cudaMemcpyAsync(out, u_d, m.nF * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st)); return CS_OK; }
+        CS_CHECK(which == 'e' || which == 'j', "the b formulation provides b (faces) and e, j (edges)");
+        // e = MeSigmaI (C^T MfMui b - s_e)
+        CS_TRY(c->tmp2.ensure((size_t)m.nF * sizeof(cplx)));
+        CS_TRY(c->tmp1.ensure((size_t)std::max(m.nF, m.nE) * 8));
+        CS_TRY(launch_face_ip(m, c->mu, 1, 0, (double*)c->tmp1.p, c->st));
+        CS_TRY(launch_mul_real(c->tmp2.p, u_d, (double*)c->tmp1.p, m.nF, 1, true, 0, c->st));
+        CS_TRY(launch_curlT(m, c->tmp2.p, out, true, c->st));
+        k_sub_real_from_cplx<<<cdiv(m.nE, 256), 256, 0, c->st>>>(out, s_e_d, m.nE);
+        CS_TRY(launch_edge_ip(m, which == 'e' ? c->sigma : none, 0, 1, (double*)c->tmp1.p, c->st));   // MeSigmaI (e) or Me^-1 (j)
+        CS_TRY(launch_mul_real(out, out, (double*)c->tmp1.p, m.nE, 1, true, 0, c->st));
+        CS_CUDA(cudaGetLastError());
+        g_launches += 6;
+        return CS_OK;
+    }
     if (form == 'h') {
         if (which == 'h' || which == 'b') {
             CS_CUDA(cudaMemcpyAsync(out, u_d, m.nE * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));

@@ -200,7 +200,16 @@ class _ProblemFDEM(_Problem):
         ctx = self.ctx
         torch = _lib._torch()
         srcs = self.survey.srcList
-        n = self.mesh.nE if self.form == "h" else self.mesh.nF
+        n = self.mesh.nE if self.form in ("h", "e") else self.mesh.nF
+        nsrc_vec = self.mesh.nE if self.form in ("e", "b") else self.mesh.nF
+        for s in srcs:
+            if np.size(s.s_e) != nsrc_vec:
+                # what SimPEG does with such a source is a shape error deep inside getRHS; say it up front
+                raise NotImplementedError(
+                    "Problem3D_{f}: source vectors must live on {w} ({n} entries, got {g}).  casingSimulations sources are face "
+                    "vectors (sources.py:236), which only the h and j formulations accept; the e / b formulations take an "
+                    "edge vector (RawVec_e of the E-B formulation).".format(f=self.form, w="edges" if self.form in ("e", "b") else "faces",
+                                                                          n=nsrc_vec, g=np.size(s.s_e)))
         # one contiguous column per source (Fortran order, like the (n, nSrc) arrays SimPEG fields hold)
         sol = np.zeros((len(srcs), n), dtype=complex).T
         # sources that share one s_e vector (casingSimulations: one source per frequency,
@@ -235,7 +244,7 @@ class _ProblemFDEM(_Problem):
 
     def _fields_from_array(self, sol):
         srcs = self.survey.srcList
-        n = self.mesh.nE if self.form == "h" else self.mesh.nF
+        n = self.mesh.nE if self.form in ("h", "e") else self.mesh.nF
         assert sol.size == n * len(srcs), "fields file does not match mesh / number of sources"
         sol = sol.reshape(n, -1).astype(complex)
         self._se_d, self._u_d = {}, {}
@@ -261,6 +270,17 @@ class Problem3D_h(_ProblemFDEM):
 
 class Problem3D_j(_ProblemFDEM):
     form = "j"
+
+
+class Problem3D_e(_ProblemFDEM):
+    """fdem.Problem3D_e (run.py:240-242 with formulation='e'): C^T MfMui C + i w MeSigma, rhs -i w s_e with s_e an EDGE
+    vector; fields e, j (edges), b (faces).  3-D meshes only."""
+    form = "e"
+
+
+class Problem3D_b(_ProblemFDEM):
+    """fdem.Problem3D_b: MfMui (C MeSigmaI C^T MfMui + i w), rhs MfMui C MeSigmaI s_e with s_e an EDGE vector"""
+    form = "b"
 
 
 class _ProblemTDEM(_Problem):
@@ -412,11 +432,12 @@ class SimulationFDEM(BaseSimulation):
     @property
     def prob(self):
         if getattr(self, "_prob", None) is None:
-            if self.formulation not in ("h", "j"):
+            klass = {"h": Problem3D_h, "j": Problem3D_j, "e": Problem3D_e, "b": Problem3D_b}[self.formulation]
+            some = self.srcList.srcList if self.srcList is not None else (self.src.srcList if self.src is not None else [])
+            if self.formulation in ("e", "b") and some and np.size(some[0].s_e) != self.meshGenerator.mesh.nE:
                 raise NotImplementedError(
-                    "casingSimulations sources are face vectors (sources.py:236); only the h and j formulations "
-                    "accept them.  The e / b operators exist at the operator level (cs_op_get kinds EDGE_E, FACE_B).")
-            klass = {"h": Problem3D_h, "j": Problem3D_j}[self.formulation]
+                    "casingSimulations sources are face vectors (sources.py:236); only the h and j formulations accept "
+                    "them.  The e / b formulations (Problem3D_e / Problem3D_b) take an edge source vector.")
             prob = klass(self.meshGenerator.mesh, Solver=Solver, verbose=self.verbose, device=self.device,
                          solver_opts=self.solver_opts)
             if self.srcList is not None:

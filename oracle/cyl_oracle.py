@@ -612,7 +612,12 @@ class OracleFDEM(object):
             return C.T @ (self.MfRho @ s_e)
         if self.form == "j":
             return self.MfRho @ (-1j * w * s_e)
-        raise NotImplementedError("oracle RHS only for the face-source forms h, j")
+        # E-B formulations: s_e is an EDGE vector (SimPEG RawVec_e, integrate=False)
+        if self.form == "e":
+            return -1j * w * s_e
+        if self.form == "b":
+            return self.MfMui @ (C @ (self.MeSigmaI @ s_e))
+        raise ValueError(self.form)
 
     def solve(self, freq, s_e, refine=False):
         A = self.getA(freq)
@@ -624,6 +629,20 @@ class OracleFDEM(object):
         return u
 
     # derived fields (A.6 last column)
+    def e_from_eb(self, freq, u, s_e):
+        """E-B formulations: e on edges"""
+        if self.form == "e":
+            return u
+        return self.MeSigmaI @ (self.C.T @ (self.MfMui @ u) - np.asarray(s_e, dtype=complex))
+
+    def b_from_eb(self, freq, u, s_e):
+        if self.form == "b":
+            return u
+        return -(self.C @ u) / (1j * 2 * np.pi * freq)
+
+    def j_from_eb(self, freq, u, s_e):
+        return _sdiag(1.0 / self.Me.diagonal()) @ (self.MeSigma @ self.e_from_eb(freq, u, s_e))
+
     def j_from(self, freq, u, s_e):
         if self.form == "h":
             return self.C @ u - np.asarray(s_e, dtype=complex)
