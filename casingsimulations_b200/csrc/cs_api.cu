@@ -305,6 +305,15 @@ static int build_plan(cs_op* op) {
         }
     }
     if (bp.p > bp.n2 - 1) bp.p = (int)std::max(1LL, bp.n2 - 1);
+    bp.Lrow = L;
+    bp.tma_real = false;
+    if (nth > 1 && bp.n2 > 64) {
+        // 3-D: an even half bandwidth (extra zeros) and an even system size (one decoupled dummy unknown at the end) make
+        // every staged column segment of REAL factors 16-byte aligned, so the substitution kernel can use its TMA producer
+        if (bp.p & 1) bp.p += 1;
+        if (bp.n2 & 1) { bp.n2 += 1; map.push_back(-1); js.push_back(nx); }
+        bp.tma_real = true;
+    }
     bp.scalar_field = (op->family == 0) || (op->family == 1 && m.sym);
     bp.jprobe = 0;
     if (nth > 1) {
@@ -530,6 +539,10 @@ extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int c
     CS_CUDA(cudaSetDevice(c->device));
     BandPlan& bp = op->bp;
     bool lc = bp.cplx_band || complex_shift != 0;
+    // CS_REAL_LU=0: complex factors even for a real shift on a 3-D mesh (the round-1 behaviour: twice the factor bytes,
+    // but the substitution kernel stages complex factors with a TMA producer warp) -- A/B switch, see DESIGN.md
+    static const bool real_lu = [] { const char* e = getenv("CS_REAL_LU"); return !(e && atoi(e) == 0); }();
+    if (!real_lu && bp.nth > 1) lc = true;
     size_t need = (size_t)nshift * bp.nmodes * bp.band_elems() * esz(lc);
     if (!c->dist.on) CS_TRY(op->LU.ensure(need));
     op->lu_cplx = lc;
@@ -583,7 +596,7 @@ static int mode_exchange(cs_op* op, void* xm_l, void* xm_g, int nvec, bool forwa
     CS_CHECK(R == 1 || nc, "NCCL is not available");
     auto rows_owned = [&](int r, long long& row0, long long& cnt) {
         row0 = (long long)d.zsplit[r] * L;
-        long long row1 = (r == R - 1) ? bg.n2 : (long long)d.zsplit[r + 1] * L;
+        long long row1 = (long long)(r == R - 1 ? d.g.gnz + 1 : d.zsplit[r + 1]) * L;     // (the padding dummy row stays zero)
         cnt = row1 - row0;
     };
     auto rows_local = [&](int r, long long& row0, long long& cnt) {
@@ -644,10 +657,12 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     CS_CHECK(op->family == 1 && !op->is_csr, "the z-slab solve is implemented for the edge-form operators (FDEM-h / -e)");
     CS_CHECK(lc && !bl.cplx_band, "the z-slab solve needs a complex shift (FDEM) on a real operator");
     const int R = d.g.nranks, me = d.g.rank, H = bl.nmodes, nth = bl.nth;
-    const long long L = bl.n2 / (m.nz + 1);
+    const long long L = bl.Lrow;
     op->Lrow = L;
     bg = bl;
     bg.n2 = L * (d.g.gnz + 1);
+    const long long n2g_true = bg.n2;             // without the padding dummy
+    if (bl.tma_real && (bg.n2 & 1)) bg.n2 += 1;
     int n_own = 0;
     for (int h = me; h < H; h += R) ++n_own;
     CS_CHECK(n_own >= 1, "more ranks than theta modes: nothing to own");
@@ -672,6 +687,7 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     CS_CUDA(cudaMemcpyAsync(jsl.data(), bl.jstr, bl.n2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CS_CUDA(cudaStreamSynchronize(c->st));
     std::vector<long long> mapg(bg.n2); std::vector<int> jsg(bg.n2);
+    for (long long q = n2g_true; q < bg.n2; ++q) { mapg[q] = -1; jsg[q] = jsl[0]; }
     for (int k = 0; k <= d.g.gnz; ++k)
         for (long long r = 0; r < L; ++r) {
             // level 0 of the local plan is a regular level (nz_l >= 2), its last level the pattern of a top level
@@ -685,7 +701,7 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     bg.map3d = (long long*)op->gmap.p; bg.jstr = (int*)op->gjstr.p; bg.mdiag = (double*)op->gmdiag.p; bg.hs = nullptr;
     CS_CUDA(cudaStreamSynchronize(c->st));                      // (host vectors go out of scope)
     // global mass diagonal: every rank contributes its owned rows, summed over the ranks
-    const long long g0 = (long long)d.g.z_lo * L, g1 = (me == R - 1) ? bg.n2 : (long long)d.g.z_hi * L;
+    const long long g0 = (long long)d.g.z_lo * L, g1 = (me == R - 1) ? n2g_true : (long long)d.g.z_hi * L;
     const long long l0 = g0 - (long long)d.g.k0 * L;
     CS_CUDA(cudaMemsetAsync(bg.mdiag, 0, bg.n2 * sizeof(double), c->st));
     k_fill_rows<<<cdiv(g1 - g0, 256), 256, 0, c->st>>>(bg.mdiag + g0, bl.mdiag + l0, g1 - g0);
@@ -695,6 +711,7 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     CS_TRY(op->LU.ensure((size_t)nshift * n_own * nel_g * sizeof(cplx)));
     CS_TRY(op->gstage.ensure(nel_g * sizeof(double)));
     double* stage = (double*)op->gstage.p;
+    CS_CUDA(cudaMemsetAsync(stage, 0, nel_g * sizeof(double), c->st));     // (the padding dummy's column is never received)
     const NcclApi* nc = R > 1 ? nccl_api() : nullptr;
     CS_CHECK(R == 1 || nc, "NCCL is not available");
     const double* Kl = (const double*)bl.Kband;
@@ -709,7 +726,7 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
         if (owner == me) {
             CS_CUDA(cudaMemcpyAsync(stage + (size_t)g0 * bg.ldab, src, cnt_me * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
             for (int r = 0; r < R; ++r) if (r != me) {
-                long long r0 = (long long)d.zsplit[r] * L, r1 = (r == R - 1) ? bg.n2 : (long long)d.zsplit[r + 1] * L;
+                long long r0 = (long long)d.zsplit[r] * L, r1 = (r == R - 1) ? n2g_true : (long long)d.zsplit[r + 1] * L;
                 rc = nc->Recv(stage + (size_t)r0 * bg.ldab, (size_t)(r1 - r0) * bg.ldab, ncclDouble, r, (ncclComm_t)d.comm, c->st);
             }
         } else rc = nc->Send(src, cnt_me, ncclDouble, owner, (ncclComm_t)d.comm, c->st);
@@ -926,8 +943,12 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
                         double rtol, int maxit, double* info) {
     cs_ctx* c = op->ctx;
     CS_CHECK(op->LU.p && !op->shifts.empty(), "cs_op_factor must be called before cs_op_solve");
-    CS_CHECK(cv == op->lu_cplx, cv ? "complex vectors need factors of a complex shift (cs_op_factor(..., complex_shift = 1))"
-                                        : "complex factors (complex shift or matrix) need complex vectors");
+    CS_CHECK(!(cv && !op->lu_cplx), "complex vectors need factors of a complex shift (cs_op_factor(..., complex_shift = 1))");
+    {
+        bool true_cplx = op->bp.cplx_band;
+        for (auto& sft : op->shifts) true_cplx = true_cplx || sft.imag() != 0.0;
+        CS_CHECK(cv || !true_cplx, "complex factors (complex shift or matrix) need complex vectors");
+    }
     CS_CHECK(nvec >= 1 && nvec <= 1024, "nvec out of range");
     long long n = op->n;
     Krylov K;
@@ -945,7 +966,8 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
     CS_TRY(c->modes.ensure((size_t)nvec * op->bp.nmv(op->lu_cplx) * op->bp.n2 * esz(op->lu_cplx)));
     if (c->dist.on) {
         CS_CHECK(cv && op->lu_cplx && op->bpg.fmap, "the z-slab solve needs the factors of cs_op_factor in slab mode and complex vectors");
-        CS_TRY(op->gmodes.ensure((size_t)nvec * op->bpg.nmv_own * op->bpg.n2 * sizeof(cplx)));
+        size_t gb = (size_t)nvec * op->bpg.nmv_own * op->bpg.n2 * sizeof(cplx);
+        if (gb > op->gmodes.bytes) { CS_TRY(op->gmodes.ensure(gb)); CS_CUDA(cudaMemsetAsync(op->gmodes.p, 0, op->gmodes.bytes, c->st)); }
     }
     // per-vector shifts
     std::vector<int> sov(nvec, 0);

@@ -1421,9 +1421,11 @@ __device__ __forceinline__ void bar_sync0() { asm volatile("bar.sync 0;" ::: "me
 template <typename TL, typename TV, int TPR, int NB, bool HP>
 __global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, int nmv, int fold, int nth, const int* __restrict__ fmap, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0) {
+                             int nmodes, int nmv, int fold, int nth, const int* __restrict__ fmap, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0, int use_tma) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr bool USE_TMA = sizeof(TL) == 16;                // complex: TMA bulk copies, real: cp.async
+    // TMA bulk copies need 16-byte aligned column segments: always true for complex factors, for real ones when the plan
+    // has an even half bandwidth and an even system size (BandPlan::tma_real); otherwise cp.async
+    const bool USE_TMA = use_tma != 0;
     __shared__ unsigned long long full_bar[8];
     __shared__ TV yw[32][NB];                                 // per-warp copy of the block solution
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1629,14 +1631,15 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
     // (C1 DC, 4 band solves: 141 ms with a producer warp vs 54 ms without).
     const int bound = TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640);
     const char* e = getenv("CS_SOLVE_PROD");
-    const bool hp = (sizeof(T) == 16 || (e && atoi(e) > 0)) && (th + 32 <= bound) && !(e && atoi(e) == 0);
+    const bool tma = sizeof(T) == 16 || bp.tma_real;
+    const bool hp = (tma || (e && atoi(e) > 0)) && (th + 32 <= bound) && !(e && atoi(e) == 0);
     if (hp) CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     else CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     const bool xc = sizeof(T) == sizeof(cplx);
     const int nmv = bp.nmv(xc), fold = bp.fold(xc);
     dim3 g(nmv, nvec);
-    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, th);
-    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, 0);
+    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, th, tma ? 1 : 0);
+    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, 0, 0);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

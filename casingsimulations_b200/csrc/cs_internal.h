@@ -82,6 +82,10 @@ struct BandPlan {
     bool scalar_field = false;
     // theta column the band matrices are probed at: 0 for uniform azimuthal widths, otherwise the column whose
     // width is closest to the mean (the circulant preconditioner then models an "average" column)
+    long long Lrow = 0;        // band rows per z level (n2 = Lrow * levels + an optional padding dummy)
+    // real factors can be staged with TMA bulk copies in the substitution kernel: every column segment starts at an even
+    // element and has an even length (p even, n2 even -- build_plan pads both on 3-D meshes)
+    bool tma_real = false;
     int jprobe = 0;
     // the probing response is confined to theta columns jprobe-1 .. jprobe+1 (three-term DFT).  Not for face unknowns:
     // the Fy faces of the innermost cells share the single axis Ez edge, so C C^T couples them across ALL theta columns
