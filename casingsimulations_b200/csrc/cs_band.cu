@@ -618,6 +618,74 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     if (m1 && n1) c01[16] = old11 - acc11;
 }
 
+// Wide bands (p >= 128: the 3-D edge / face forms): 64 x 64 tiles with a 4 x 4 register block per thread.  A CTA of the 32 x 32
+// kernel lives for 16 k-steps of 4 complex FMAs per thread -- its time is the load latency of its prologue; four times
+// the work per CTA and per staged L / U element amortises it.  MEASURED: no gain (update chain 168 ms with either tile shape
+// on 109x32x460; the chain costs 12.5 us per step + 0.95 us per system regardless of the tile) -- kept behind CS_LU_TILE=64.
+template <typename T, int NB>
+__global__ void __launch_bounds__(256, 2)
+k_lu_update64(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, const T* __restrict__ scratch, int part, int tiles) {
+    __shared__ T Ls[NB][64];
+    __shared__ T Us[NB][65];
+    T* A = LU + (size_t)blockIdx.z * nel + pw;
+    const int nbe = (int)min((long long)NB, n2 - t);
+    const int R = (int)min((long long)p, n2 - (t + nbe));
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (part == 1) { if (bx < tiles) by = 0; else { by = bx - tiles + 1; bx = 0; } }
+    else if (part == 2) { bx += 1; by += 1; }
+    const int a0 = bx * 64, b0 = by * 64;
+    const int tid = threadIdx.x;
+    if (bx == 0 && by == 0) {
+        // put the factored diagonal block (parked by the panel kernel) in place
+        const T* S = scratch + (size_t)blockIdx.z * NB * NB;
+        for (int e = tid; e < nbe * nbe; e += 256) {
+            int r = e % nbe, c = e / nbe;
+            A[(t + r) + (t + c) * (long long)ld] = S[r + c * NB];
+        }
+    }
+    if (a0 >= R || b0 >= R) return;
+    const long long r0 = t + nbe + a0, c0 = t + nbe + b0;
+    for (int e = tid; e < NB * 64; e += 256) {
+        int a = e % 64, c = e / 64;
+        Ls[c][a] = (a0 + a < R && c < nbe) ? A[(r0 + a) + (t + c) * (long long)ld] : Sc<T>::zero();
+    }
+    for (int e = tid; e < NB * 64; e += 256) {
+        int c = e % NB, b = e / NB;
+        Us[c][b] = (b0 + b < R && c < nbe) ? A[(t + c) + (c0 + b) * (long long)ld] : Sc<T>::zero();
+    }
+    const int ta = tid % 16, tb = tid / 16;           // rows ta + 16 i, columns tb + 16 j
+    __syncthreads();
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = Sc<T>::zero();
+#pragma unroll 4
+    for (int c = 0; c < NB; ++c) {
+        T l[4], u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l[i] = Ls[c][ta + 16 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = Us[c][tb + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fmacc(acc[i][j], l[i], u[j]);
+    }
+    // read-modify-write of the tile, one column of the register block at a time (the other resident CTA covers the latency;
+    // holding all 16 old values through the k loop would spill at the 128-register cap of two CTAs per SM)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b = b0 + tb + 16 * j;
+        T* col = A + r0 + ta + (c0 + tb + 16 * j) * (long long)ld;
+        T o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = (a0 + ta + 16 * i < R && b < R) ? col[16 * i] : Sc<T>::zero();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (a0 + ta + 16 * i < R && b < R) col[16 * i] = o[i] - acc[i][j];
+    }
+}
+
 // After the factorisation every NB x NB diagonal block holds L11 \ U11.  The triangular solves
 // with those blocks are the sequential heart of the substitution kernels, so they are replaced
 // once, here (fully parallel: one warp per block), by the explicit inverses
@@ -691,7 +759,9 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
                                cudaEvent_t evP = nullptr, cudaEvent_t evU = nullptr) {
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
-    int tiles = (bp.p + 31) / 32;
+    static const int tile_env = [] { const char* e = getenv("CS_LU_TILE"); return e ? atoi(e) : 0; }();
+    const bool big = tile_env == 64 && NB == 16;      // opt-in: measured identical (273 ms vs 273 ms on 109x32x460), see below
+    int tiles = big ? (bp.p + 63) / 64 : (bp.p + 31) / 32;
     int chunks = (bp.p + 63) / 64;
     // (timing experiments only: CS_LU_SKIP=panel|update drops one of the two kernels of every step -- wrong factors)
     static const int skip = [] { const char* e = getenv("CS_LU_SKIP"); return !e ? 0 : (!strcmp(e, "panel") ? 1 : (!strcmp(e, "update") ? 2 : 0)); }();
@@ -703,16 +773,19 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
         if (skip == 2) continue;
         if (!la) {
             dim3 g(tiles, tiles, nsys);
-            k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 0, tiles);
+            if (big) k_lu_update64<T, 16><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 0, tiles);
+            else k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 0, tiles);
             continue;
         }
         if (cudaEventRecord(evP, st) != cudaSuccess) return CS_ERR;
         if (have_u2 && cudaStreamWaitEvent(st, evU, 0) != cudaSuccess) return CS_ERR;       // U1(t) overlaps the region U2(t-1) wrote
         dim3 g1(2 * tiles - 1, 1, nsys);
-        k_lu_update<T, NB><<<g1, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 1, tiles);
+        if (big) k_lu_update64<T, 16><<<g1, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 1, tiles);
+        else k_lu_update<T, NB><<<g1, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 1, tiles);
         if (cudaStreamWaitEvent(stB, evP, 0) != cudaSuccess) return CS_ERR;
         dim3 g2(tiles - 1, tiles - 1, nsys);
-        k_lu_update<T, NB><<<g2, 256, 0, stB>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 2, tiles);
+        if (big) k_lu_update64<T, 16><<<g2, 256, 0, stB>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 2, tiles);
+        else k_lu_update<T, NB><<<g2, 256, 0, stB>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 2, tiles);
         if (cudaEventRecord(evU, stB) != cudaSuccess) return CS_ERR;
         have_u2 = true;
     }
@@ -733,6 +806,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     int groups_key = 0;
     { const char* e = getenv("CS_BAND_GROUPS"); if (e) groups_key = atoi(e); }
     { const char* e = getenv("CS_LU_LOOKAHEAD"); if (e && atoi(e) == 1) groups_key += 100; }
+    { const char* e = getenv("CS_LU_TILE"); if (e) groups_key += 10000 * atoi(e); }
     FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
