@@ -85,6 +85,7 @@ struct DistState {
 };
 
 struct cs_op {
+    bool valid = true;               // false once cs_model_* / cs_mesh_set dropped it: the handle stays addressable, its calls fail
     cs_ctx* ctx = nullptr;
     int kind = 0, family = 0;        // family: 0 cell, 1 edge, 2 face
     long long n = 0;                 // vector length
@@ -119,6 +120,7 @@ struct cs_ctx {
     double* zn_d = nullptr;
     double *sigma = nullptr, *mu = nullptr;
     std::map<int, cs_op*> ops;
+    std::vector<cs_op*> stale_ops;
     DevBuf work, scal, modes, tmp1, tmp2, ework, ddwork;
     Pool pool;
     std::vector<std::pair<std::vector<unsigned long long>, cudaGraphExec_t>> probe_graphs;
@@ -134,20 +136,29 @@ struct cs_ctx {
 
 static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc);
 
-static void op_free(cs_op* op) {
-    if (!op) return;
+static void op_release_buffers(cs_op* op) {
     op->bw1.release(); op->bw2.release(); op->bmass.release();
     cudaFree(op->csr_indptr); cudaFree(op->csr_indices); cudaFree(op->csr_vals);
+    op->csr_indptr = nullptr; op->csr_indices = nullptr; op->csr_vals = nullptr;
     op->bmap.release(); op->bjstr.release(); op->bmdiag.release(); op->bhs.release();
     op->kband.release(); op->bp.Kband = nullptr;
     op->LU.release(); op->wts.release();
     op->gmap.release(); op->gjstr.release(); op->gmdiag.release(); op->gfmap.release(); op->gstage.release(); op->gmodes.release();
+    op->w1 = op->w2 = op->mass = nullptr;
+}
+static void op_free(cs_op* op) {
+    if (!op) return;
+    op_release_buffers(op);
     delete op;
 }
+// cs_model_* / cs_mesh_set invalidate the cached operators.  Callers (the Python Op objects, C clients) may still hold
+// their handles: the device buffers go back to the pool, the small structs stay alive as tombstones until the context is
+// destroyed, and every cs_op_* call on one fails with a message instead of touching freed memory.
 static void ctx_drop_ops(cs_ctx* c) {
-    for (auto& kv : c->ops) op_free(kv.second);
+    for (auto& kv : c->ops) { op_release_buffers(kv.second); kv.second->valid = false; c->stale_ops.push_back(kv.second); }
     c->ops.clear();
 }
+#define CS_OP_LIVE(op) CS_CHECK((op) && (op)->valid, "stale operator handle: the model or mesh changed after it was obtained (call cs_op_get again)")
 
 // ------------------------------------------------------------- small kernels --
 __global__ void k_gather_diag(const long long* __restrict__ map3d, const int* __restrict__ jstr, int jprobe,
@@ -497,10 +508,10 @@ extern "C" int cs_op_from_csr(cs_ctx* c, int family, long long n, long long nnz,
     return CS_OK;
 }
 
-extern "C" long long cs_op_size(cs_op* op) { return op ? op->n : -1; }
+extern "C" long long cs_op_size(cs_op* op) { return (op && op->valid) ? op->n : -1; }
 
 extern "C" int cs_op_apply(cs_op* op, const double* shifts_h, const void* x_d, void* y_d, int nvec, int is_complex) {
-    CS_CHECK(op, "null op");
+    CS_OP_LIVE(op);
     cs_ctx* c = op->ctx;
     CS_CUDA(cudaSetDevice(c->device));
     CS_TRY(c->scal.ensure(std::max<size_t>(4096, 2 * nvec * sizeof(double))));
@@ -512,7 +523,8 @@ extern "C" int cs_op_apply(cs_op* op, const double* shifts_h, const void* x_d, v
 // reps back-to-back launches bracketed by CUDA events on the context's stream
 extern "C" int cs_op_apply_timed(cs_op* op, const double* shifts_h, const void* x_d, void* y_d, int nvec, int is_complex,
                                  int reps, double* ms_per_launch) {
-    CS_CHECK(op && reps >= 1, "bad arguments");
+    CS_OP_LIVE(op);
+    CS_CHECK(reps >= 1, "bad arguments");
     cs_ctx* c = op->ctx;
     CS_TRY(cs_op_apply(op, shifts_h, x_d, y_d, nvec, is_complex));   // uploads the shifts, warms up
     CS_CUDA(cudaStreamSynchronize(c->st));
@@ -526,14 +538,15 @@ extern "C" int cs_op_apply_timed(cs_op* op, const double* shifts_h, const void* 
 }
 
 extern "C" int cs_op_clean(cs_op* op) {
-    CS_CHECK(op, "null op");
+    CS_OP_LIVE(op);
     op->LU.release();
     op->shifts.clear();
     return CS_OK;
 }
 
 extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int complex_shift) {
-    CS_CHECK(op && nshift >= 1, "bad arguments");
+    CS_OP_LIVE(op);
+    CS_CHECK(nshift >= 1, "bad arguments");
     CS_CHECK(op->bp.Kband, "operator was created without a band plan (cs_op_get_noplan)");
     cs_ctx* c = op->ctx;
     CS_CUDA(cudaSetDevice(c->device));
@@ -1200,7 +1213,7 @@ static int krylov_solve(cs_op* op, const void* rhs, void* x, int nvec, const int
 
 extern "C" int cs_op_solve(cs_op* op, const void* rhs_d, void* x_d, int nvec, const int* shift_of_vec_h,
                            int is_complex, double rtol, int maxit, double* info_h) {
-    CS_CHECK(op, "null op");
+    CS_OP_LIVE(op);
     cs_ctx* c = op->ctx;
     CS_CUDA(cudaSetDevice(c->device));
     long long l0 = g_launches;
@@ -1281,6 +1294,8 @@ extern "C" int cs_ctx_destroy(cs_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     ctx_drop_ops(c);
+    for (cs_op* z : c->stale_ops) delete z;
+    c->stale_ops.clear();
     cudaFree(c->tables); cudaFree(c->sigma); cudaFree(c->mu);
     c->work.release(); c->scal.release(); c->modes.release(); c->tmp1.release(); c->tmp2.release(); c->ework.release(); c->ddwork.release();
     c->halo_s.release(); c->halo_r.release();

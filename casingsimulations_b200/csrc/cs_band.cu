@@ -618,6 +618,157 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     if (m1 && n1) c01[16] = old11 - acc11;
 }
 
+// ---- fused step: trailing update of step t + panel of step t+1 in ONE launch ("last block done") ----
+// The two-kernel schedule pays a fixed ~12.5 us per block step for two dependent launches, most of it the latency-bound
+// panel (102 CTAs).  Here the update kernel's CTAs count themselves off per system as they finish the first tile row /
+// column of the trailing block -- everything the next panel reads -- and the CTA that completes the count runs that
+// panel (pivot-block LU by one warp, then the row / column triangular solves in sweeps of 128 + 128) while the rest
+// of the grid is still updating: no second launch, no waiting (nobody spins, so nothing can deadlock).  Grid =
+// (systems, tiles^2): the system index is the FASTEST block index and the first-row/column tiles come first, so the panels
+// of all systems overlap the bulk of the update.  Loads of the tail bypass L1 (__ldcg): the data were written by other SMs.
+template <typename T> __device__ __forceinline__ T ldcg_t(const T* p);
+template <> __device__ __forceinline__ double ldcg_t<double>(const double* p) { return __ldcg(p); }
+template <> __device__ __forceinline__ cplx ldcg_t<cplx>(const cplx* p) { return __ldcg(p); }
+
+template <typename T, int NB>
+__device__ __noinline__ void lu_panel_tail(T* __restrict__ A, long long n2, int p, int ld, long long t, T* __restrict__ S, T (*D)[NB + 1]) {
+    const int tid = threadIdx.x;
+    const int nbe = (int)min((long long)NB, n2 - t);
+    const int R = (int)min((long long)p, n2 - (t + nbe));
+    for (int e = tid; e < NB * NB; e += 256) {
+        int r = e % NB, c = e / NB;
+        T val = (r == c) ? Sc<T>::one() : Sc<T>::zero();
+        if (r < nbe && c < nbe) val = ldcg_t<T>(A + (t + r) + (t + c) * (long long)ld);
+        D[r][c] = val;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int r = tid & (NB - 1);
+        T v[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) v[c] = D[r][c];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            T piv = Sc<T>::inv(shfl_row(v[c], c));
+            T l = v[c] * piv;
+            if (r > c) v[c] = l;
+#pragma unroll
+            for (int cc = c + 1; cc < NB; ++cc) {
+                T u = shfl_row(v[cc], c);
+                if (r > c) v[cc] -= l * u;
+            }
+        }
+        if (tid < NB) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) D[r][c] = v[c];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) S[e] = D[e % NB][e / NB];
+    for (int base = 0; base < R; base += 128) {
+        const int idx = base + (tid & 127);
+        const bool isrow = tid < 128;
+        if (idx >= R) continue;
+        T v[NB];
+        if (isrow) {
+            const long long row = t + nbe + idx;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) v[c] = (c < nbe) ? ldcg_t<T>(A + row + (t + c) * (long long)ld) : Sc<T>::zero();
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                T acc0 = v[c], acc1 = Sc<T>::zero();
+#pragma unroll
+                for (int c2 = 0; c2 < c; ++c2) { if (c2 & 1) acc1 -= v[c2] * D[c2][c]; else acc0 -= v[c2] * D[c2][c]; }
+                v[c] = (acc0 + acc1) * Sc<T>::inv(D[c][c]);
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (c < nbe) A[row + (t + c) * (long long)ld] = v[c];
+        } else {
+            T* cp = A + (t + nbe + idx) * (long long)ld + t;
+#pragma unroll
+            for (int r = 0; r < NB; ++r) v[r] = (r < nbe) ? ldcg_t<T>(cp + r) : Sc<T>::zero();
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                T acc0 = v[r], acc1 = Sc<T>::zero();
+#pragma unroll
+                for (int r2 = 0; r2 < r; ++r2) { if (r2 & 1) acc1 -= D[r][r2] * v[r2]; else acc0 -= D[r][r2] * v[r2]; }
+                v[r] = acc0 + acc1;
+            }
+#pragma unroll
+            for (int r = 0; r < NB; ++r) if (r < nbe) cp[r] = v[r];
+        }
+    }
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(256, 2)
+k_lu_update_fused(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, T* __restrict__ scratch,
+                  int tiles, int* __restrict__ cnt, int target) {
+    __shared__ T Ls[NB][32];
+    __shared__ T Us[NB][33];
+    __shared__ int s_last;
+    const int sys = blockIdx.x;
+    T* A = LU + (size_t)sys * nel + pw;
+    const int nbe = (int)min((long long)NB, n2 - t);
+    const int R = (int)min((long long)p, n2 - (t + nbe));
+    // tile order: the 2 tiles - 1 tiles of the first tile row / column first, then the rest
+    const int nu1 = 2 * tiles - 1;
+    int bx, by;
+    const int L = blockIdx.y;
+    if (L < nu1) { if (L < tiles) { bx = L; by = 0; } else { bx = 0; by = L - tiles + 1; } }
+    else { int l2 = L - nu1; bx = 1 + l2 % (tiles - 1); by = 1 + l2 / (tiles - 1); }
+    const int a0 = bx * 32, b0 = by * 32;
+    const int tid = threadIdx.x;
+    if (bx == 0 && by == 0) {
+        // put the factored diagonal block (parked by the panel of this step) in place
+        const T* S = scratch + (size_t)sys * NB * NB;
+        for (int e = tid; e < nbe * nbe; e += 256) {
+            int r = e % nbe, c = e / nbe;
+            A[(t + r) + (t + c) * (long long)ld] = S[r + c * NB];
+        }
+    }
+    if (a0 < R && b0 < R) {
+        const long long r0 = t + nbe + a0, c0 = t + nbe + b0;
+        const int ta = tid % 16, tb = tid / 16;
+        const bool m0 = (a0 + ta < R), m1 = (a0 + ta + 16 < R), n0 = (b0 + tb < R), n1 = (b0 + tb + 16 < R);
+        T* c00 = A + (r0 + ta) + (c0 + tb) * (long long)ld;
+        T* c01 = A + (r0 + ta) + (c0 + tb + 16) * (long long)ld;
+        T old00 = (m0 && n0) ? c00[0] : Sc<T>::zero(), old10 = (m1 && n0) ? c00[16] : Sc<T>::zero();
+        T old01 = (m0 && n1) ? c01[0] : Sc<T>::zero(), old11 = (m1 && n1) ? c01[16] : Sc<T>::zero();
+        for (int e = tid; e < NB * 32; e += 256) {
+            int a = e % 32, c = e / 32;
+            Ls[c][a] = (a0 + a < R && c < nbe) ? A[(r0 + a) + (t + c) * (long long)ld] : Sc<T>::zero();
+        }
+        for (int e = tid; e < NB * 32; e += 256) {
+            int c = e % NB, b = e / NB;
+            Us[c][b] = (b0 + b < R && c < nbe) ? A[(t + c) + (c0 + b) * (long long)ld] : Sc<T>::zero();
+        }
+        __syncthreads();
+        T acc00 = Sc<T>::zero(), acc01 = Sc<T>::zero(), acc10 = Sc<T>::zero(), acc11 = Sc<T>::zero();
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            T l0 = Ls[c][ta], l1 = Ls[c][ta + 16];
+            T u0 = Us[c][tb], u1 = Us[c][tb + 16];
+            fmacc(acc00, l0, u0); fmacc(acc01, l0, u1); fmacc(acc10, l1, u0); fmacc(acc11, l1, u1);
+        }
+        if (m0 && n0) c00[0] = old00 - acc00;
+        if (m1 && n0) c00[16] = old10 - acc10;
+        if (m0 && n1) c01[0] = old01 - acc01;
+        if (m1 && n1) c01[16] = old11 - acc11;
+    }
+    if (L >= nu1) return;
+    // ---- tail: count this first-row/column tile off; the last one of the system factors the next panel ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(cnt + sys, 1) == target - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long tn = t + nbe;
+    if (tn >= n2) return;
+    lu_panel_tail<T, NB>(A, n2, p, ld, tn, scratch + (size_t)sys * NB * NB, reinterpret_cast<T (*)[NB + 1]>(&Ls[0][0]));
+}
+
 // Wide bands (p >= 128: the 3-D edge / face forms): 64 x 64 tiles with a 4 x 4 register block per thread.  A CTA of the 32 x 32
 // kernel lives for 16 k-steps of 4 complex FMAs per thread -- its time is the load latency of its prologue; four times
 // the work per CTA and per staged L / U element amortises it.  MEASURED: no gain (update chain 168 ms with either tile shape
@@ -756,7 +907,7 @@ static unsigned long long g_stamp = 0;
 // latency-bound panel of step t+1 runs concurrently with the throughput-bound bulk update of step t.
 template <typename T, int NB>
 static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, cudaStream_t st, cudaStream_t stB = nullptr,
-                               cudaEvent_t evP = nullptr, cudaEvent_t evU = nullptr) {
+                               cudaEvent_t evP = nullptr, cudaEvent_t evU = nullptr, int* cnt = nullptr) {
     size_t nel = bp.band_elems();
     int ld = bp.ldab - 1;
     static const int tile_env = [] { const char* e = getenv("CS_LU_TILE"); return e ? atoi(e) : 0; }();
@@ -766,6 +917,21 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     // (timing experiments only: CS_LU_SKIP=panel|update drops one of the two kernels of every step -- wrong factors)
     static const int skip = [] { const char* e = getenv("CS_LU_SKIP"); return !e ? 0 : (!strcmp(e, "panel") ? 1 : (!strcmp(e, "update") ? 2 : 0)); }();
     const bool la = stB != nullptr && tiles >= 2;
+    static const bool fused_on = [] { const char* e = getenv("CS_LU_FUSED"); return !(e && atoi(e) == 0); }();
+    if (fused_on && !la && !big && NB == 16 && tiles >= 2 && skip == 0 && cnt) {
+        // one launch per block step: update of step t + panel of step t+1 (k_lu_update_fused); the first panel stands alone
+        if (cudaMemsetAsync(cnt, 0, (size_t)nsys * sizeof(int), st) != cudaSuccess) return CS_ERR;
+        dim3 gp(chunks, nsys);
+        k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, 0, scratch);
+        int step = 0;
+        for (long long t = 0; t < bp.n2; t += NB, ++step) {
+            dim3 g(nsys, tiles * tiles, 1);
+            k_lu_update_fused<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, tiles, cnt, (step + 1) * (2 * tiles - 1));
+        }
+        dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
+        k_invert_diag<T, NB><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
+        return CS_OK;
+    }
     bool have_u2 = false;
     for (long long t = 0; t < bp.n2; t += NB) {
         dim3 gp(chunks, nsys);
@@ -801,12 +967,16 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_band_mu);
     void* scratch = nullptr;
     CS_TRY(band_scratch(0, st, (size_t)nsys * NB * NB * sizeof(T), false, &scratch));
+    void* cntv = nullptr;
+    CS_TRY(band_scratch(2, st, (size_t)nsys * sizeof(int), true, &cntv));
+    int* cnt = (int*)cntv;
     int dev_key = 0;
     CS_CUDA(cudaGetDevice(&dev_key));
     int groups_key = 0;
     { const char* e = getenv("CS_BAND_GROUPS"); if (e) groups_key = atoi(e); }
     { const char* e = getenv("CS_LU_LOOKAHEAD"); if (e && atoi(e) == 1) groups_key += 100; }
     { const char* e = getenv("CS_LU_TILE"); if (e) groups_key += 10000 * atoi(e); }
+    { const char* e = getenv("CS_LU_FUSED"); if (e && atoi(e) == 0) groups_key += 1000000; }
     FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
@@ -852,7 +1022,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
             int s0 = (int)((long long)nsys * g / groups), s1 = (int)((long long)nsys * (g + 1) / groups);
             cudaStream_t sg = (g == 0) ? st : aux[g - 1];
             okq = okq && band_factor_enqueue<T, NB>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NB * NB, sg,
-                                                    lookahead ? as.auxB[g] : nullptr, as.evP[g], as.evU[g]) == CS_OK;
+                                                    lookahead ? as.auxB[g] : nullptr, as.evP[g], as.evU[g], cnt + s0) == CS_OK;
         }
         for (int g = 1; g < groups; ++g) {
             okq = okq && cudaEventRecord(ev_join[g - 1], aux[g - 1]) == cudaSuccess;
@@ -864,7 +1034,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     }
     if (!captured) {
         cudaGetLastError();                 // capture unavailable: plain launches (same kernels)
-        CS_TRY((band_factor_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st)));
+        CS_TRY((band_factor_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st, nullptr, nullptr, nullptr, cnt)));
         CS_CUDA(cudaGetLastError());
         return CS_OK;
     }

@@ -455,3 +455,20 @@ def test_fdem_eb_formulations(gpu_ctx, form):
         assert rel(j, P.j_from_eb(freq, u[f], se)) < 1e-5
     with pytest.raises(Exception, match="edges"):
         gpu_ctx.solve_fdem(form, freqs, gpu_ctx.to_device(np.zeros(om.nF)))          # a face vector is refused up front
+
+
+def test_stale_operator_handle_fails_cleanly(gpu_ctx):
+    """cs_model_paint / cs_model_set / cs_mesh_set drop the cached operators; a handle obtained before keeps failing with
+    a message instead of touching freed memory"""
+    from casingsimulations_b200 import _lib
+    setup(gpu_ctx, 1)
+    op = gpu_ctx.op(_lib.KIND_DC)
+    x = gpu_ctx.to_device(rnd(op.n, False))
+    op.apply(x)
+    gpu_ctx.paint(paint_params(CASING))                       # drops the operator
+    with pytest.raises(_lib.CasingB200Error, match="stale operator"):
+        op.apply(x)
+    with pytest.raises(_lib.CasingB200Error, match="stale operator"):
+        op.factor([0.0])
+    op2 = gpu_ctx.op(_lib.KIND_DC)                            # a fresh handle works
+    assert op2.apply(x).shape == x.shape
