@@ -917,7 +917,9 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     // (timing experiments only: CS_LU_SKIP=panel|update drops one of the two kernels of every step -- wrong factors)
     static const int skip = [] { const char* e = getenv("CS_LU_SKIP"); return !e ? 0 : (!strcmp(e, "panel") ? 1 : (!strcmp(e, "update") ? 2 : 0)); }();
     const bool la = stB != nullptr && tiles >= 2;
-    static const bool fused_on = [] { const char* e = getenv("CS_LU_FUSED"); return !(e && atoi(e) == 0); }();
+    // MEASURED (109x32x460, 17 systems): 356 ms (443 ms at 3 CTAs/SM) vs 273 ms for the two-kernel schedule -- the one-CTA
+    // panel tail of the last system is exposed and the lower occupancy slows the tiles; opt-in only (CS_LU_FUSED=1)
+    static const bool fused_on = [] { const char* e = getenv("CS_LU_FUSED"); return e && atoi(e) == 1; }();
     if (fused_on && !la && !big && NB == 16 && tiles >= 2 && skip == 0 && cnt) {
         // one launch per block step: update of step t + panel of step t+1 (k_lu_update_fused); the first panel stands alone
         if (cudaMemsetAsync(cnt, 0, (size_t)nsys * sizeof(int), st) != cudaSuccess) return CS_ERR;
@@ -976,7 +978,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     { const char* e = getenv("CS_BAND_GROUPS"); if (e) groups_key = atoi(e); }
     { const char* e = getenv("CS_LU_LOOKAHEAD"); if (e && atoi(e) == 1) groups_key += 100; }
     { const char* e = getenv("CS_LU_TILE"); if (e) groups_key += 10000 * atoi(e); }
-    { const char* e = getenv("CS_LU_FUSED"); if (e && atoi(e) == 0) groups_key += 1000000; }
+    { const char* e = getenv("CS_LU_FUSED"); if (e && atoi(e) == 1) groups_key += 1000000; }
     FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
