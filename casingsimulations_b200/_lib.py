@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcasing_b200.so")
 
-KIND_DC, KIND_DC_GROUNDED, KIND_EDGE_H, KIND_EDGE_E, KIND_FACE_J, KIND_FACE_B = range(6)
+KIND_DC, KIND_DC_GROUNDED, KIND_EDGE_H, KIND_EDGE_E, KIND_FACE_J, KIND_FACE_B, KIND_NODAL_E = range(7)
 INFO_LEN = 16
 INFO_NAMES = ["iters", "relres", "ms_assemble", "ms_factor", "ms_solve", "n_apply", "n_launch", "bytes", "converged", "backward_err",
               "dd_steps", "dd_corr"]
@@ -70,6 +70,8 @@ def load_library():
         "cs_curlT": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_div": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_divT": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_grad": (c.c_int, [vp, vp, vp, c.c_int]),
+        "cs_gradT": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_ave_f2ccv": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_ave_e2ccv": (c.c_int, [vp, vp, vp, c.c_int]),
         "cs_op_get": (c.c_int, [vp, c.c_int, c.POINTER(vp)]),
@@ -102,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "cs_last_error", "cs_launch_count", "cs_ctx_create", "cs_ctx_destroy", "cs_ctx_sync", "cs_fp64_peak", "cs_ctx_set_refine",
     "cs_comm_unique_id", "cs_comm_init", "cs_comm_local_range", "cs_comm_halo", "cs_mesh_set",
     "cs_mesh_counts", "cs_model_paint", "cs_model_set", "cs_face_inner_product", "cs_edge_inner_product",
-    "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_ave_f2ccv", "cs_ave_e2ccv", "cs_op_get", "cs_op_get_noplan", "cs_op_apply_timed", "cs_op_from_csr", "cs_op_size", "cs_op_apply", "cs_op_factor",
+    "cs_curl", "cs_curlT", "cs_div", "cs_divT", "cs_grad", "cs_gradT", "cs_ave_f2ccv", "cs_ave_e2ccv", "cs_op_get", "cs_op_get_noplan", "cs_op_apply_timed", "cs_op_from_csr", "cs_op_size", "cs_op_apply", "cs_op_factor",
     "cs_op_solve", "cs_op_clean", "cs_solve_dc", "cs_solve_fdem", "cs_tdem_run", "cs_tdem_run_multi", "cs_fields_fdem",
     "cs_fields_dc", "cs_casing_currents", "cs_casing_charges",
 ]
@@ -381,6 +383,19 @@ class Context(object):
     def divT(self, xC):
         return self._unary(self.lib.cs_divT, xC, self.nC, self.nF)
 
+    @property
+    def nN(self):
+        """nodes of a 3-D mesh: per z-node level the axis node, then nx*nth nodes"""
+        return (self.nz + 1) * (self.nx * self.nth + 1)
+
+    def grad(self, xN):
+        """mesh.nodalGrad * xN (3-D meshes)"""
+        return self._unary(self.lib.cs_grad, xN, self.nN, self.nE)
+
+    def gradT(self, xE):
+        """mesh.nodalGrad.T * xE (3-D meshes)"""
+        return self._unary(self.lib.cs_gradT, xE, self.nE, self.nN)
+
     def ave_f2ccv(self, xF):
         """mesh.aveF2CCV * xF: cell-centred vector, blocks [x | y | z] ([x | z] on a symmetric mesh)"""
         return self._unary(self.lib.cs_ave_f2ccv, xF, self.nF, self.nC * (2 if self.nth == 1 else 3))
@@ -454,10 +469,14 @@ class Context(object):
         """s_e: (nF,) -> (nsteps+1, nF), or (nsrc, nF) -> (nsteps+1, nsrc, nF): all sources share the factorisations"""
         dts = np.ascontiguousarray(dts, dtype=np.float64)
         multi = s_e.dim() == 2
-        se2 = s_e.reshape(-1, self.nF).contiguous()
+        n = self.nE if form == "e" else self.nF                  # e: EDGE source vectors and fields (SURVEY A.7)
+        if s_e.shape[-1] != n:
+            raise CasingB200Error("the {} formulation takes source vectors on {} ({} entries), got {}".format(
+                form, "edges" if form == "e" else "faces", n, s_e.shape[-1]))
+        se2 = s_e.reshape(-1, n).contiguous()
         nsrc = se2.shape[0]
         torch = _torch()
-        out = torch.empty((len(dts) + 1, nsrc, self.nF), dtype=torch.float64, device=self.device)
+        out = torch.empty((len(dts) + 1, nsrc, n), dtype=torch.float64, device=self.device)
         info = np.zeros(INFO_LEN)
         self._enter()
         rc = self.lib.cs_tdem_run_multi(self.h, ord(form), _dptr(dts), len(dts), _tptr(se2), nsrc, _tptr(out),

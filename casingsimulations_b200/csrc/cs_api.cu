@@ -248,6 +248,7 @@ static int op_apply_dev(cs_op* op, const double* s_d, const void* x, void* y, in
     g_launches += 1;
     if (op->is_csr) return launch_csr_spmv(op->n, op->csr_indptr, op->csr_indices, op->csr_vals, op->csr_cplx, x, y, nvec, cplx_vec, c->st);
     if (op->family == 0) return launch_dc_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st);
+    if (op->family == 3) { g_launches += 2 * nvec - 1; return launch_node_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st); }
     if (op->family == 1) return launch_edge_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st);
     // 3-D: two-pass face operator through an edge workspace (220 vs 385 us on the 4.86 M-cell mesh;
     // CS_FACE_OP=fused forces the single-pass kernel).  2-D: single pass (6.5 vs 9.2 us at 152 k cells).
@@ -265,6 +266,7 @@ static double op_bytes_per_apply(cs_op* op, bool cplx_vec) {
     double v = cplx_vec ? 16.0 : 8.0;
     if (op->is_csr) return (double)op->csr_nnz * ((op->csr_cplx ? 16.0 : 8.0) + 4.0) + (double)op->n * (2 * v + 8.0);
     if (op->family == 0) return (double)m.nC * (2 * v + (m.sym ? 16.0 : 24.0));
+    if (op->family == 3) return (double)m.nC * (2 * v + 24.0);
     if (m.sym) return (double)m.nC * (op->family == 1 ? (2 * v + 16.0 + 8.0) : (4 * v + 16.0 + 8.0));
     return (double)m.nC * (6 * v + 24.0 + 24.0);
 }
@@ -282,6 +284,14 @@ static int build_plan(cs_op* op) {
         L = nx; bp.n2 = (long long)nx * nz; bp.p = nx;
         map.assign(bp.n2, -1); js.assign(bp.n2, nx);
         for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) map[k * L + i] = i + (long long)nx * nth * k;
+    } else if (op->family == 3) {
+        // nodes: per z-node level nx regular nodes (r_1 .. r_nx at theta column 0) and the shared axis node
+        L = nx + 1; bp.n2 = L * (nz + 1); bp.p = (int)L;
+        map.assign(bp.n2, -1); js.assign(bp.n2, nx);
+        for (int k = 0; k <= nz; ++k) {
+            for (int i = 0; i < nx; ++i) map[k * L + i] = (long long)k * m.ezp + 1 + i;
+            map[k * L + nx] = (long long)k * m.ezp; js[k * L + nx] = 0;
+        }
     } else if (op->family == 1 && m.sym) {
         L = nx; bp.n2 = (long long)nx * (nz + 1); bp.p = nx;
         map.assign(bp.n2, -1); js.assign(bp.n2, nx);
@@ -325,7 +335,7 @@ static int build_plan(cs_op* op) {
         if (bp.n2 & 1) { bp.n2 += 1; map.push_back(-1); js.push_back(nx); }
         bp.tma_real = true;
     }
-    bp.scalar_field = (op->family == 0) || (op->family == 1 && m.sym);
+    bp.scalar_field = (op->family == 0) || (op->family == 3) || (op->family == 1 && m.sym);
     bp.jprobe = 0;
     if (nth > 1) {
         double mean = 2.0 * M_PI / nth, best = 1e300;
@@ -462,6 +472,12 @@ static int op_get(cs_ctx* c, int kind, bool with_plan, cs_op** out) {
         rc = launch_face_scale(m, op->mass, op->w1, 2, c->st); if (rc) return fail(rc);   // alpha / area
         rc = launch_edge_ip(m, pg, 0, 1, t1, c->st); if (rc) return fail(rc);             // 1/Me(prop)
         rc = launch_edge_scale(m, t1, op->w2, 0, c->st); if (rc) return fail(rc);         // len^2 * gamma
+    } else if (kind == CS_KIND_NODAL_E) {
+        if (m.sym) { set_error("the nodal operator needs a 3-D mesh"); return fail(CS_ERR); }
+        op->family = 3; op->n = (long long)(m.nz + 1) * m.ezp; op->shift0 = 1.0;             // grounded at node 0, like SimPEG's getAdc
+        if (!palloc(op->bw1, &op->w1, m.nE)) return fail(CS_ERR);
+        rc = launch_edge_ip(m, c->sigma, 0, 0, t1, c->st); if (rc) return fail(rc);             // MeSigma
+        rc = launch_edge_scale(m, t1, op->w1, 2, c->st); if (rc) return fail(rc);               // MeSigma / len^2
     } else {
         set_error("unknown operator kind");
         return fail(CS_ERR);
@@ -1493,6 +1509,29 @@ extern "C" int cs_curlT(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c 
 extern "C" int cs_div(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_div(c->m, x, y, ic != 0, c->st); }
 extern "C" int cs_divT(cs_ctx* c, const void* x, void* y, int ic) { CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1; return launch_divT(c->m, x, y, ic != 0, c->st); }
 
+extern "C" int cs_grad(cs_ctx* c, const void* xN_d, void* yE_d, int ic) {
+    CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1;
+    return launch_node_grad(c->m, xN_d, yE_d, ic != 0, true, c->st);
+}
+// nodalGrad^T x_E = G_topo^T (x_E ./ len)
+extern "C" int cs_gradT(cs_ctx* c, const void* xE_d, void* yN_d, int ic) {
+    CS_CHECK(c && c->has_mesh && !c->m.sym, "a 3-D mesh is required"); CS_CUDA(cudaSetDevice(c->device));
+    const MeshD& m = c->m;
+    CS_TRY(c->tmp1.ensure((size_t)m.nE * sizeof(double)));
+    CS_TRY(c->tmp2.ensure((size_t)m.nE * sizeof(cplx)));
+    // 1 / len: the edge scaling kernel applied to ones gives 1 / len^2, k_mul_real (mode 2) multiplies by its square root
+    double* one = (double*)c->tmp1.p;
+    {
+        std::vector<double> h((size_t)m.nE, 1.0);
+        CS_CUDA(cudaMemcpyAsync(one, h.data(), (size_t)m.nE * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        CS_CUDA(cudaStreamSynchronize(c->st));
+    }
+    CS_TRY(launch_edge_scale(m, one, one, 2, c->st));                                 // 1 / len^2
+    CS_TRY(launch_mul_real(c->tmp2.p, xE_d, one, m.nE, 1, ic != 0, 2, c->st));        // x .* sqrt(1/len^2)
+    g_launches += 4;
+    return launch_node_apply(m, nullptr, 0.0, c->tmp2.p, yN_d, 1, ic != 0, c->st);
+}
+
 // mesh.aveF2CCV * v / mesh.aveE2CCV * v (view.py:300-308): cell-centred vector blocks [x | y | z] of nC each
 extern "C" int cs_ave_f2ccv(cs_ctx* c, const void* xF_d, void* yCCV_d, int ic) {
     CS_CHECK(c && c->has_mesh, "mesh not set"); CS_CUDA(cudaSetDevice(c->device)); g_launches += 1;
@@ -1620,15 +1659,122 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
     return rc;
 }
 
+// tdem.Problem3D_e (run.py:273-277 with formulation 'e'): backward Euler on the edges,
+//   (C^T MfMui C + MeSigma/dt) e^{n+1} = MeSigma e^n / dt - (s_e^{n+1} - s_e^n)/dt,      step-off: s_e(t > 0) = 0,
+// initial state of a grounded source from the NODAL DC problem (G^T MeSigma G) phi = G^T s_e, e0 = -G phi.
+// s_e_d: [nsrc][nE] EDGE vectors (integrated source); out_d: [nsteps+1][nsrc][nE].  3-D meshes only.
+// The exact solution keeps G^T (MeSigma e^n + s_e^n) = 0; like the j formulation's divergence cleaning every step is followed
+// by the projection e <- e - G (G^T MeSigma G)^-1 G^T MeSigma e that enforces it (see the note in the loop).
+static int tdem_run_e(cs_ctx* c, const double* dts_h, int nsteps, const double* s_e_d, int nsrc,
+                      double* out_d, double rtol, int maxit, double* info) {
+    const MeshD& m = c->m;
+    CS_CHECK(!m.sym, "the e formulation needs a 3-D mesh (a cylindrically symmetric mesh has E_theta edges only)");
+    long long l0 = g_launches;
+    const long long nE = m.nE, nN = (long long)(m.nz + 1) * m.ezp, NE = nE * nsrc, NN = nN * nsrc;
+    cs_op *nd = nullptr, *op = nullptr;
+    CS_TRY(cs_op_get(c, CS_KIND_NODAL_E, &nd));
+    CS_TRY(cs_op_get(c, CS_KIND_EDGE_E, &op));
+    double inf2[CS_INFO_LEN];
+    DevBuf b1, b2, b3, il;
+    b1.pool = b2.pool = b3.pool = il.pool = &c->pool;
+    CS_TRY(b1.ensure((size_t)NN * 8)); CS_TRY(b2.ensure((size_t)NN * 8)); CS_TRY(b3.ensure((size_t)NE * 8)); CS_TRY(il.ensure((size_t)nE * 8));
+    double* invlen = (double*)il.p;
+    {   // 1 / len per edge: 1 / len^2 of ones, then the square root on use (k_mul_real mode 2)
+        std::vector<double> h((size_t)nE, 1.0);
+        CS_CUDA(cudaMemcpyAsync(invlen, h.data(), (size_t)nE * 8, cudaMemcpyHostToDevice, c->st));
+        CS_CUDA(cudaStreamSynchronize(c->st));
+        CS_TRY(launch_edge_scale(m, invlen, invlen, 2, c->st));
+    }
+    const double* sig_e = op->mass;                    // MeSigma
+    double ms_fac = 0, ms_sol = 0, worst = 0;
+    // d_N = G^T (MeSigma .* x_E)  (with_sigma) or G^T x_E, for all sources
+    auto gradT_all = [&](const double* xE, bool with_sigma, double* yN) -> int {
+        double* t = (double*)b3.p;
+        CS_TRY(launch_mul_real(t, xE, invlen, nE, nsrc, false, 2, c->st));                     // ./ len
+        if (with_sigma) CS_TRY(launch_mul_real(t, t, sig_e, nE, nsrc, false, 0, c->st));
+        g_launches += 2;
+        return launch_node_apply(m, nullptr, 0.0, t, yN, nsrc, false, c->st);
+    };
+    auto grad_all = [&](const double* xN, double* yE) -> int {
+        for (int s = 0; s < nsrc; ++s) CS_TRY(launch_node_grad(m, xN + s * nN, yE + s * nE, false, true, c->st));
+        g_launches += nsrc;
+        return CS_OK;
+    };
+    { double z[2] = {0, 0}; CS_TRY(cs_op_factor(nd, z, 1, 0)); ms_fac += nd->ms_factor; }
+    CS_TRY(gradT_all(s_e_d, false, (double*)b1.p));
+    memset(inf2, 0, sizeof inf2);
+    int rc = krylov_solve(nd, b1.p, b2.p, nsrc, nullptr, false, rtol, maxit, inf2);
+    if (rc) return rc;
+    worst = std::max(worst, inf2[CS_INFO_RELRES]);
+    CS_TRY(grad_all((const double*)b2.p, (double*)b3.p));
+    k_scale_add<<<cdiv(NE, 256), 256, 0, c->st>>>(out_d, (const double*)b3.p, NE, -1.0, 0.0);        // e0 = -G phi
+    CS_CUDA(cudaGetLastError());
+    double dt_prev = -1.0;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int t = 0; t < nsteps && rc == CS_OK; ++t) {
+        double dt = dts_h[t];
+        if (dt_prev < 0 || std::fabs(dt - dt_prev) > 1e-8) {
+            double sh[2] = {1.0 / dt, 0.0};
+            rc = cs_op_factor(op, sh, 1, 0);
+            if (rc) break;
+            ms_fac += op->ms_factor;
+            dt_prev = dt;
+        }
+        const double* en = out_d + (size_t)t * NE;
+        double* en1 = out_d + (size_t)(t + 1) * NE;
+        double* rhs = (double*)b3.p;
+        cudaEventRecord(e0, c->st);
+        rc = launch_mul_real(rhs, en, sig_e, nE, nsrc, false, 0, c->st);                           // MeSigma e^n
+        if (rc) break;
+        k_scale_add<<<cdiv(NE, 256), 256, 0, c->st>>>(rhs, rhs, NE, 1.0 / dt_prev, 0.0);
+        if (t == 0) k_scale_add<<<cdiv(NE, 256), 256, 0, c->st>>>(rhs, s_e_d, NE, 1.0 / dt_prev, 1.0);   // -(0 - s_e)/dt
+        g_launches += 3;
+        memset(inf2, 0, sizeof inf2);
+        rc = krylov_solve(op, rhs, en1, nsrc, nullptr, false, rtol, maxit, inf2);
+        cudaEventRecord(e1, c->st); cudaStreamSynchronize(c->st);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms_sol += ms;
+        worst = std::max(worst, inf2[CS_INFO_RELRES]);
+        if (info) { info[CS_INFO_N_APPLY] += inf2[CS_INFO_N_APPLY]; info[CS_INFO_BYTES] += inf2[CS_INFO_BYTES]; info[CS_INFO_ITERS] += inf2[CS_INFO_ITERS]; }
+        if (rc != CS_OK) break;
+        // cleaning of the gradient null space (CS_TDEM_E_CLEAN=0 turns it off).  Backward Euler carries a gradient G psi
+        // unchanged from step to step (A G psi = MeSigma G psi / dt), so whatever the Krylov tolerance leaves in G^T MeSigma e
+        // stays for the rest of the run while the field itself decays by ten orders of magnitude.  The projection pins every
+        // step to G^T MeSigma e = 0 as fp64 evaluates it, independent of rtol and of the number of steps.  Measured on the
+        // test mesh against the exactly assembled systems (energy norm, per step): 5.9e-5 with, 8.7e-5 at rtol 1e-10 without;
+        // the reference's own arithmetic (fp64 assembly + SuperLU) 4.5e-6, the fp64-ASSEMBLED systems solved exactly 2.4e-5 --
+        // the entry roundings of MeSigma decide this digit, not the solver.
+        static const bool clean = [] { const char* e = getenv("CS_TDEM_E_CLEAN"); return !(e && atoi(e) == 0); }();
+        if (clean) {
+            rc = gradT_all(en1, true, (double*)b1.p);
+            if (rc) break;
+            memset(inf2, 0, sizeof inf2);
+            rc = krylov_solve(nd, b1.p, b2.p, nsrc, nullptr, false, rtol, maxit, inf2);
+            if (rc != CS_OK) break;
+            rc = grad_all((const double*)b2.p, (double*)b3.p);
+            if (rc) break;
+            k_scale_add<<<cdiv(NE, 256), 256, 0, c->st>>>(en1, (const double*)b3.p, NE, -1.0, 1.0);
+            g_launches += 1;
+        }
+    }
+    cs_op_clean(nd);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (info) {
+        info[CS_INFO_RELRES] = worst; info[CS_INFO_MS_FACTOR] = ms_fac; info[CS_INFO_MS_SOLVE] = ms_sol;
+        info[CS_INFO_MS_ASSEMBLE] = op->ms_assemble + nd->ms_assemble; info[CS_INFO_N_LAUNCH] = (double)(g_launches - l0); info[CS_INFO_CONVERGED] = rc == CS_OK;
+    }
+    return rc;
+}
+
 // Backward Euler for nsrc sources at once: they share every factorisation (one per distinct dt) and travel as columns
 // of one batched solve, like SimPEG's (n x nSrc) right-hand sides.  s_e_d: [nsrc][nF]; out_d: [nsteps+1][nsrc][nF].
 extern "C" int cs_tdem_run_multi(cs_ctx* c, int form, const double* dts_h, int nsteps, const double* s_e_d, int nsrc,
                                  double* out_d, double rtol, int maxit, double* info) {
     CS_CHECK(c && c->has_model, "model not set");
-    CS_CHECK(form == 'j', "cs_tdem_run implements the (default) j formulation");
+    CS_CHECK(form == 'j' || form == 'e', "cs_tdem_run implements the j (face sources, default) and e (edge sources) formulations");
     CS_CHECK(nsrc >= 1 && nsteps >= 0, "bad arguments");
-    long long l0 = g_launches;
     info_begin(info);
+    if (form == 'e') return tdem_run_e(c, dts_h, nsteps, s_e_d, nsrc, out_d, rtol, maxit, info);
+    long long l0 = g_launches;
     const MeshD& m = c->m;
     const long long nF = m.nF, nC = m.nC;
     const long long NF = nF * nsrc, NC = nC * nsrc;

@@ -13,7 +13,7 @@ int launch_face_ip(const MeshD& m, const double* prop, int invProp, int invMat, 
 int launch_edge_ip(const MeshD& m, const double* prop, int invProp, int invMat, double* out, cudaStream_t st);
 // elementwise geometric rescalings: mode 0: area^2/in, 1: in/area^2, 2: in/area, 3: in*area
 int launch_face_scale(const MeshD& m, const double* in, double* out, int mode, cudaStream_t st);
-// mode 0: len^2*in, 1: len^2/in
+// mode 0: len^2*in, 1: len^2/in, 2: in/len^2
 int launch_edge_scale(const MeshD& m, const double* in, double* out, int mode, cudaStream_t st);
 
 // K3: y = Dt diag(g) Dt^T x (+ shift0 * x[0] on row 0), Dt = vol*faceDiv; nsys vectors of length nC
@@ -24,6 +24,10 @@ int launch_divT(const MeshD& m, const void* xC, void* yF, bool cplx_vec, cudaStr
 // y_F = edgeCurl x_E ; y_E = edgeCurl^T x_F
 int launch_curl(const MeshD& m, const void* xE, void* yF, bool cplx_vec, cudaStream_t st);
 int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaStream_t st);
+// 3-D nodal operators (discretize mesh.nodalGrad; nodes per z level: the axis node, then nx*nth nodes)
+int launch_node_grad(const MeshD& m, const void* xN, void* yE, bool cplx_vec, bool with_len, cudaStream_t st);
+// w != null: y_N = G_topo^T diag(w) G_topo x_N (+ shift0 x[0]);  w == null: y_N = G_topo^T x_E
+int launch_node_apply(const MeshD& m, const double* w, double shift0, const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
 // mesh.aveF2CCV / aveE2CCV: face / edge vector -> cell-centred vector, blocks [x | y | z] (view.py:300-308)
 int launch_ave_ccv(const MeshD& m, bool from_faces, const void* x, void* y, bool cplx_vec, cudaStream_t st);
 // K4 edge form: y = C^T diag(alpha) C x + s[sys] * beta .* x, wF = alpha/area^2

@@ -149,7 +149,7 @@ __global__ void k_edge_scale(MeshD m, const double* __restrict__ in, double* __r
     Slot s;
     if (!slot_of(m, t, m.nz + 1, s)) return;
     int i = s.i, j = s.j, k = s.k;
-    auto f = [&](double v, double l) -> double { return mode == 0 ? l * l * v : l * l / v; };
+    auto f = [&](double v, double l) -> double { return mode == 0 ? l * l * v : (mode == 1 ? l * l / v : v / (l * l)); };
     long long c = m.cidx(i, j, k);
     out[m.nEx + c] = f(in[m.nEx + c], m.lEy(i, j));
     if (m.sym) return;
@@ -360,6 +360,124 @@ int launch_curlT(const MeshD& m, const void* xF, void* yE, bool cplx_vec, cudaSt
     long long n = m.nxy * (m.nz + 1);
     if (cplx_vec) k_curlT<cplx><<<grid1(n), TPB, 0, st>>>(m, (const cplx*)xF, (cplx*)yE);
     else k_curlT<double><<<grid1(n), TPB, 0, st>>>(m, (const double*)xF, (double*)yE);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// ============================ nodal gradient and nodal Laplacian (3-D) =============
+// discretize mesh.nodalGrad = diag(1/len) G_topo on the deflated node set: per z-node level the single
+// axis node first, then the nx*nth nodes at (r_{i}, theta_j), i = 1..nx.  Needed by the E-B time stepping: the DC initial
+// state of a grounded source, (G^T MeSigma G) phi = G^T s_e, e0 = -G phi, and the per-step cleaning of the
+// gradient null space.  npl = nx*nth + 1 nodes per level.
+__device__ __forceinline__ long long nodeidx(const MeshD& m, int i /*0 = axis, 1..nx*/, int j, int k) {
+    return (long long)k * m.ezp + (i == 0 ? 0 : 1 + (i - 1) + (long long)m.nx * j);
+}
+// y_E = scale_E .* (G_topo x_N)      (scale = 1/len gives nodalGrad; scale may be null = topological gradient)
+template <typename T>
+__global__ void k_node_grad(MeshD m, const T* __restrict__ xN, T* __restrict__ yE, int with_len) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    const int i = s.i, j = s.j, k = s.k;                 // edge radial index i <-> node radial index i + 1
+    const long long c = m.cidx(i, j, k);
+    const T xc = xN[nodeidx(m, i + 1, j, k)];
+    const double sx = with_len ? 1.0 / m.lEx(i) : 1.0, sy = with_len ? 1.0 / m.lEy(i, j) : 1.0;
+    yE[c] = sx * (xc - xN[nodeidx(m, i, j, k)]);                                   // Ex: r_i -> r_{i+1}
+    yE[m.nEx + c] = sy * (xN[nodeidx(m, i + 1, m.jp(j), k)] - xc);                 // Ey: theta_j -> theta_{j+1}
+    if (k < m.nz) {
+        const double sz = with_len ? 1.0 / m.lEz(k) : 1.0;
+        yE[m.nEx + m.nEy + m.ez(i, j, k)] = sz * (xN[nodeidx(m, i + 1, j, k + 1)] - xc);
+        if (i == 0 && j == 0) yE[m.nEx + m.nEy + m.ezaxis(k)] = sz * (xN[nodeidx(m, 0, 0, k + 1)] - xN[nodeidx(m, 0, 0, k)]);
+    }
+}
+// y_N = G_topo^T (w_E .* (G_topo x_N)) + shift0 * x[0] on row 0 ; w == null: y_N = G_topo^T xin_E (plain transpose, xin = x)
+template <typename T, bool LAPLACE>
+__global__ void k_node_apply(MeshD m, const double* __restrict__ w, double shift0, const T* __restrict__ x, T* __restrict__ y) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    Slot s;
+    if (!slot_of(m, t, m.nz + 1, s)) return;
+    const int i = s.i, j = s.j, k = s.k;                 // node (i + 1, j, k)
+    const long long c = m.cidx(i, j, k);
+    const long long oy = m.nEx, oz = m.nEx + m.nEy;
+    const int jm = m.jm(j), jp = m.jp(j);
+    T acc = Sc<T>::zero();
+    if (LAPLACE) {
+        const T xc = x[nodeidx(m, i + 1, j, k)];
+        acc += w[c] * (xc - x[nodeidx(m, i, j, k)]);                                             // Ex(i): towards r_i / the axis
+        if (i + 1 < m.nx) acc += w[c + 1] * (xc - x[nodeidx(m, i + 2, j, k)]);                   // Ex(i+1): towards r_{i+2}
+        acc += w[oy + c] * (xc - x[nodeidx(m, i + 1, jp, k)]);                                   // Ey(i, j)
+        acc += w[oy + m.cidx(i, jm, k)] * (xc - x[nodeidx(m, i + 1, jm, k)]);                    // Ey(i, j-1)
+        if (k < m.nz) acc += w[oz + m.ez(i, j, k)] * (xc - x[nodeidx(m, i + 1, j, k + 1)]);
+        if (k > 0) acc += w[oz + m.ez(i, j, k - 1)] * (xc - x[nodeidx(m, i + 1, j, k - 1)]);
+    } else {
+        // G_topo^T: + for the edge's head node, - for its tail node
+        acc += x[c];                                                                             // Ex(i) ends here
+        if (i + 1 < m.nx) acc -= x[c + 1];                                                       // Ex(i+1) starts here
+        acc -= x[oy + c];                                                                        // Ey(i, j) starts here
+        acc += x[oy + m.cidx(i, jm, k)];                                                         // Ey(i, j-1) ends here
+        if (k < m.nz) acc -= x[oz + m.ez(i, j, k)];
+        if (k > 0) acc += x[oz + m.ez(i, j, k - 1)];
+    }
+    y[nodeidx(m, i + 1, j, k)] = acc;
+}
+// the axis node of every level: Ex(0, j, k) for all j + the axis Ez edges above / below
+template <typename T, bool LAPLACE>
+__global__ void k_node_apply_axis(MeshD m, const double* __restrict__ w, double shift0, const T* __restrict__ x, T* __restrict__ y) {
+    int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (k > m.nz) return;
+    const long long oz = m.nEx + m.nEy;
+    double re = 0.0, im = 0.0;
+    T xa = LAPLACE ? x[nodeidx(m, 0, 0, k)] : Sc<T>::zero();
+    for (int j = lane; j < m.nth; j += 32) {
+        long long c = m.cidx(0, j, k);
+        T v = LAPLACE ? w[c] * (xa - x[nodeidx(m, 1, j, k)]) : Sc<T>::zero() - x[c];            // Ex(0, j, k) starts at the axis
+        re += Sc<T>::re(v); im += Sc<T>::im(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) { re += __shfl_down_sync(0xffffffffu, re, o); im += __shfl_down_sync(0xffffffffu, im, o); }
+    if (lane == 0) {
+        T acc = Sc<T>::from(re, im);
+        if (LAPLACE) {
+            if (k < m.nz) acc += w[oz + m.ezaxis(k)] * (xa - x[nodeidx(m, 0, 0, k + 1)]);
+            if (k > 0) acc += w[oz + m.ezaxis(k - 1)] * (xa - x[nodeidx(m, 0, 0, k - 1)]);
+            if (k == 0) acc += shift0 * xa;                                                      // node 0 = the axis node of level 0
+        } else {
+            if (k < m.nz) acc -= x[oz + m.ezaxis(k)];
+            if (k > 0) acc += x[oz + m.ezaxis(k - 1)];
+        }
+        y[nodeidx(m, 0, 0, k)] = acc;
+    }
+}
+int launch_node_grad(const MeshD& m, const void* xN, void* yE, bool cplx_vec, bool with_len, cudaStream_t st) {
+    CS_CHECK(!m.sym, "nodal operators need a 3-D mesh (a cylindrically symmetric mesh has no nodes)");
+    long long n = m.nxy * (m.nz + 1);
+    if (cplx_vec) k_node_grad<cplx><<<grid1(n), TPB, 0, st>>>(m, (const cplx*)xN, (cplx*)yE, with_len ? 1 : 0);
+    else k_node_grad<double><<<grid1(n), TPB, 0, st>>>(m, (const double*)xN, (double*)yE, with_len ? 1 : 0);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+// w != null: y = G_topo^T diag(w) G_topo x (+ shift0 x[0]), x, y nodal, nsys vectors;  w == null: y_N = G_topo^T x_E (one vector)
+int launch_node_apply(const MeshD& m, const double* w, double shift0, const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st) {
+    CS_CHECK(!m.sym, "nodal operators need a 3-D mesh (a cylindrically symmetric mesh has no nodes)");
+    const long long n = m.nxy * (m.nz + 1), nN = (long long)(m.nz + 1) * m.ezp;
+    const long long nin = w ? nN : m.nE;
+    for (int sidx = 0; sidx < nsys; ++sidx) {
+        const size_t es = cplx_vec ? sizeof(cplx) : sizeof(double);
+        const void* xs = (const char*)x + (size_t)sidx * nin * es;
+        void* ys = (char*)y + (size_t)sidx * nN * es;
+        dim3 ga((m.nz + 1 + 7) / 8);
+        if (w) {
+            if (cplx_vec) { k_node_apply<cplx, true><<<grid1(n), TPB, 0, st>>>(m, w, shift0, (const cplx*)xs, (cplx*)ys);
+                            k_node_apply_axis<cplx, true><<<ga, 256, 0, st>>>(m, w, shift0, (const cplx*)xs, (cplx*)ys); }
+            else { k_node_apply<double, true><<<grid1(n), TPB, 0, st>>>(m, w, shift0, (const double*)xs, (double*)ys);
+                   k_node_apply_axis<double, true><<<ga, 256, 0, st>>>(m, w, shift0, (const double*)xs, (double*)ys); }
+        } else {
+            if (cplx_vec) { k_node_apply<cplx, false><<<grid1(n), TPB, 0, st>>>(m, w, 0.0, (const cplx*)xs, (cplx*)ys);
+                            k_node_apply_axis<cplx, false><<<ga, 256, 0, st>>>(m, w, 0.0, (const cplx*)xs, (cplx*)ys); }
+            else { k_node_apply<double, false><<<grid1(n), TPB, 0, st>>>(m, w, 0.0, (const double*)xs, (double*)ys);
+                   k_node_apply_axis<double, false><<<ga, 256, 0, st>>>(m, w, 0.0, (const double*)xs, (double*)ys); }
+        }
+    }
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

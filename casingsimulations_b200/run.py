@@ -285,7 +285,10 @@ class Problem3D_b(_ProblemFDEM):
 
 class _ProblemTDEM(_Problem):
     form = "j"
-    _solution_name = "jSolution"
+
+    @property
+    def _solution_name(self):
+        return self.form + "Solution"
 
     def __init__(self, mesh, timeSteps=None, **kw):
         super(_ProblemTDEM, self).__init__(mesh, **kw)
@@ -301,10 +304,17 @@ class _ProblemTDEM(_Problem):
         self._set_model(m)
         ctx = self.ctx
         srcs = self.survey.srcList
+        n = self.mesh.nE if self.form == "e" else self.mesh.nF
+        for s in srcs:
+            if np.size(s.s_e) != n:
+                raise NotImplementedError(
+                    "tdem Problem3D_{f}: source vectors must live on {w} ({n} entries, got {g}).  casingSimulations sources are "
+                    "face vectors (sources.py:125, 236), which the j formulation accepts; the e formulation takes an edge "
+                    "vector.".format(f=self.form, w="edges" if self.form == "e" else "faces", n=n, g=np.size(s.s_e)))
         # all sources of the survey at once: (n x nSrc) right-hand sides sharing every factorisation
         se = np.ascontiguousarray(np.stack([np.real(s.s_e) for s in srcs]))
         out = ctx.tdem_run(self.form, self.timeSteps, ctx.to_device(se, complex_=False), rtol=self.rtol, maxit=self.maxit)
-        sol = np.ascontiguousarray(out.cpu().numpy().transpose(2, 1, 0))             # (nF, nSrc, nT+1)
+        sol = np.ascontiguousarray(out.cpu().numpy().transpose(2, 1, 0))             # (n, nSrc, nT+1)
         info = dict(ctx.info)
         self.info = info
         return Fields(self, sol, srcs, times=self.times)
@@ -314,18 +324,31 @@ class _ProblemTDEM(_Problem):
         nT = len(self.timeSteps) + 1
         if sol.ndim == 2:                                         # one source: Fields.__getitem__ dropped the source axis
             sol = sol[:, None, :]
-        assert sol.shape == (self.mesh.nF, len(srcs), nT), "fields file does not match sources / time steps"
+        n = self.mesh.nE if self.form == "e" else self.mesh.nF
+        assert sol.shape == (n, len(srcs), nT), "fields file does not match sources / time steps"
         return Fields(self, np.real(sol), srcs, times=self.times)
 
     def _field(self, f, name, idx):
-        if name in ("jSolution", "j"):
+        if name in (self.form + "Solution", self.form):
             return f._sol[:, idx, :]
+        if self.form == "e":
+            raise KeyError(name)
         if name == "e":      # e = Mf^-1 MfRho j
             ctx = self.ctx
             self._ensure_model()
             w = (ctx.face_inner_product(self._sigma_d, True, False) / ctx.face_inner_product()).cpu().numpy()
             return f._sol[:, idx, :] * w[:, None, None]
         raise KeyError(name)
+
+
+class Problem3D_j_tdem(_ProblemTDEM):
+    """tdem.Problem3D_j (run.py:287-296), face sources"""
+    form = "j"
+
+
+class Problem3D_e_tdem(_ProblemTDEM):
+    """tdem.Problem3D_e: C^T MfMui C + MeSigma/dt on the edges, nodal DC initial state, EDGE source vectors"""
+    form = "e"
 
 
 class BaseSimulation(BaseCasing):
@@ -461,10 +484,17 @@ class SimulationTDEM(BaseSimulation):
     @property
     def prob(self):
         if getattr(self, "_prob", None) is None:
-            if self.formulation != "j":
-                raise NotImplementedError("only the default j formulation takes the grounded face sources (sources.py:125)")
-            prob = _ProblemTDEM(self.meshGenerator.mesh, timeSteps=self.modelParameters.timeSteps, Solver=Solver,
-                                verbose=self.verbose, device=self.device, solver_opts=self.solver_opts)
+            if self.formulation not in ("j", "e"):
+                raise NotImplementedError("the time-domain path implements the j (default; face sources, sources.py:125) and e "
+                                          "(edge sources) formulations")
+            some = self.srcList.srcList
+            if self.formulation == "e" and some and np.size(some[0].s_e) != self.meshGenerator.mesh.nE:
+                raise NotImplementedError(
+                    "casingSimulations sources are face vectors (sources.py:125, 236); only the j formulation accepts them.  "
+                    "The e formulation (Problem3D_e) takes an edge source vector.")
+            klass = Problem3D_e_tdem if self.formulation == "e" else Problem3D_j_tdem
+            prob = klass(self.meshGenerator.mesh, timeSteps=self.modelParameters.timeSteps, Solver=Solver,
+                         verbose=self.verbose, device=self.device, solver_opts=self.solver_opts)
             survey = _Survey(self.srcList.srcList)
             prob.survey = survey
             object.__setattr__(self, "_prob", prob)

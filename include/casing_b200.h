@@ -28,6 +28,7 @@ typedef struct cs_op cs_op;
 #define CS_KIND_EDGE_E 3      /* C^T MfMui C + s MeSigma    Problem3D_e                             */
 #define CS_KIND_FACE_J 4      /* MfRho (C MeMuI C^T MfRho + s)   Problem3D_j, run.py:287-296        */
 #define CS_KIND_FACE_B 5      /* MfMui (C MeSigmaI C^T MfMui + s) Problem3D_b                       */
+#define CS_KIND_NODAL_E 6     /* G^T MeSigma G + 1 at [0,0]      nodal DC initial state of tdem Problem3D_e (3-D meshes) */
 
 /* info_h layout (doubles) returned by the solve calls */
 #define CS_INFO_ITERS 0      /* Krylov iterations (max over systems)          */
@@ -100,6 +101,10 @@ int cs_curl(cs_ctx* ctx, const void* xE_d, void* yF_d, int is_complex);
 int cs_curlT(cs_ctx* ctx, const void* xF_d, void* yE_d, int is_complex);
 int cs_div(cs_ctx* ctx, const void* xF_d, void* yC_d, int is_complex);
 int cs_divT(cs_ctx* ctx, const void* xC_d, void* yF_d, int is_complex);
+
+/* mesh.nodalGrad (3-D meshes; nodes per z level: the axis node, then nx*nth nodes) and its transpose: x_N -> y_E, x_E -> y_N */
+int cs_grad(cs_ctx* ctx, const void* xN_d, void* yE_d, int is_complex);
+int cs_gradT(cs_ctx* ctx, const void* xE_d, void* yN_d, int is_complex);
 
 /* mesh.aveF2CCV / mesh.aveE2CCV applied to a vector: the viewer's re-gridding to cell centres (view.py:300-308).
  * Output blocks [x | y | z] of nC entries (symmetric mesh: [x | z] from faces, [y] from edges). */

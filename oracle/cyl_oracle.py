@@ -679,6 +679,10 @@ class OracleTDEM(object):
         self.Dt = mesh._Dtopo() @ _sdiag(mesh.area)
         self.ground_first_cell = ground_first_cell
         self.dt_threshold = 1e-8
+        if form == "e":                              # E-B formulation on the edges (A.7), 3-D meshes
+            self.MfMui = mesh.getFaceInnerProduct(1.0 / self.mu)
+            self.MeSigma = mesh.getEdgeInnerProduct(self.sigma)
+            self.G = mesh.nodalGrad
 
     def getAdc(self):
         A = (self.Dt @ self.MfRhoI @ self.Dt.T).tolil()
@@ -697,9 +701,42 @@ class OracleTDEM(object):
         n = self.mesh.nF
         return (self.MfRho @ (self.C @ self.MeMuI @ self.C.T @ self.MfRho + sp.identity(n) / dt)).tocsr()
 
+    # ---- e formulation (A.7): s_e is an EDGE vector --------------------------------------------------
+    def getAdc_nodal(self):
+        A = (self.G.T @ self.MeSigma @ self.G).tolil()
+        A[0, 0] = A[0, 0] + 1.0                    # grounded at node 0 (the axis node of the lowest level), like getAdc
+        return A.tocsr()
+
+    def e_initial(self, s_e, refine=False):
+        rhs = self.G.T @ s_e
+        A = self.getAdc_nodal()
+        phi = solve_refined(A, rhs)[0] if refine else SolverLU(A) * np.asarray(rhs, dtype=float)
+        return -(self.G @ phi), phi
+
+    def getAdiag_e(self, dt):
+        return (self.C.T @ self.MfMui @ self.C + self.MeSigma / dt).tocsr()
+
+    def fields_e(self, s_e, refine=False):
+        """eSolution (nE x (nT+1)), step-off: (C^T MfMui C + MeSigma/dt) e^{n+1} = MeSigma e^n/dt - (s^{n+1} - s^n)/dt"""
+        assert self.form == "e"
+        s_e = np.asarray(s_e, dtype=getattr(self.mesh, "dtype", float))
+        nT = len(self.time_steps)
+        F = np.zeros((self.mesh.nE, nT + 1))
+        F[:, 0] = np.asarray(self.e_initial(s_e, refine)[0], dtype=float)
+        A, lu, dt_prev = None, None, None
+        for t, dt in enumerate(self.time_steps):
+            if lu is None or abs(dt - dt_prev) > self.dt_threshold:
+                A = self.getAdiag_e(dt)
+                lu = spla.splu(A.tocsc().astype(float)); dt_prev = dt
+            rhs = self.MeSigma @ F[:, t] / dt + (s_e / dt if t == 0 else 0.0 * s_e)
+            F[:, t + 1] = solve_refined(A, rhs, lu=lu)[0] if refine else lu.solve(np.asarray(rhs, dtype=float))
+        return F
+
     def fields(self, s_e, refine=False):
         """returns jSolution (nF x (nT+1)); step-off waveform: s_e(t=0) = s_e,
         s_e(t>0) = 0."""
+        if self.form == "e":
+            return self.fields_e(s_e, refine)
         assert self.form == "j"
         s_e = np.asarray(s_e, dtype=float)
         nT = len(self.time_steps)
