@@ -373,7 +373,7 @@ static int build_plan(cs_op* op) {
 }
 
 // probe the s-independent part of the operator into the per-mode band matrices
-static int probe_plan(cs_op* op) {
+static int probe_plan_run(cs_op* op) {
     cs_ctx* c = op->ctx;
     BandPlan& bp = op->bp;
     bool cv = bp.cplx_band;
@@ -420,6 +420,19 @@ static int probe_plan(cs_op* op) {
     if (c->probe_graphs.size() >= 6) { cudaGraphExecDestroy(c->probe_graphs.front().second); c->probe_graphs.erase(c->probe_graphs.begin()); }
     c->probe_graphs.push_back({key, exec});
     CS_CUDA(cudaGraphLaunch(exec, c->st));
+    return CS_OK;
+}
+
+static int probe_plan(cs_op* op) {
+    CS_TRY(probe_plan_run(op));
+    // every operator of the path is symmetric (complex symmetric after the shift); an assembled CSR matrix may not be --
+    // measured on the probed band, and only then does the step factorisation use the lower triangle alone
+    double asym = 1.0;
+    CS_TRY(band_check_symmetric(op->bp, &asym, op->ctx->st));
+    op->bp.sym = asym < 1e-11;
+    static const bool log = getenv("CS_FACTOR_LOG") != nullptr;
+    if (log) fprintf(stderr, "[cs] probed band: kind %d  n2 %lld  p %d  modes %d  asymmetry %.2e -> %s\n", op->kind, op->bp.n2, op->bp.p, op->bp.nmodes, asym,
+                     op->bp.sym ? "symmetric step LU" : "general step LU");
     return CS_OK;
 }
 

@@ -134,7 +134,9 @@ k_dft_gather(const long long* __restrict__ map3d, const int* __restrict__ jstr, 
     for (int m = ty; m < nm; m += DFT_MY) {
         cplx acc = mk(0.0, 0.0);
         if (b >= 0) {
-            if (st == 0) { if (m == 0) acc = to_c(x3d[b]); }      // the shared axis unknown lives in mode 0 only
+            // the shared axis unknown lives in mode 0 only.  Its row of the mode-0 system sums nth theta columns and its column
+            // reaches nth of them: scaled by sqrt(nth) here and by 1 / sqrt(nth) in the scatter the system stays SYMMETRIC
+            if (st == 0) { if (m == 0) acc = sqrt((double)nth) * to_c(x3d[b]); }
             else {
                 // entry jj sits at theta position p = jj (thin: jj - 1) + hs/2: twiddle index m (2 p + hs) mod 2 nth
                 int idx = ((m * (h2 - (thin ? 2 : 0))) % n2t + n2t) % n2t;
@@ -192,7 +194,7 @@ k_dft_scatter(const long long* __restrict__ map3d, const int* __restrict__ jstr,
     if (st == 0) {
         if (ty == 0) {
             cplx a = ys[tq];                                       // mode 0, T = 1 (weight 1 above)
-            x3d[b] = from_c<TX>(a);
+            x3d[b] = from_c<TX>((1.0 / sqrt((double)nth)) * a);            // (the symmetric scaling of the axis unknown, see the gather)
         }
         return;
     }
@@ -353,9 +355,12 @@ __global__ void k_probe_store(const long long* __restrict__ map3d, const int* __
     cplx val = ym[(size_t)m * n2 + r];
     if (jstr[q] == 0 && jstr[r] != 0) {
         // column of the shared axis unknown: it couples to EVERY theta column with the same entry B, the
-        // mode-0 entry is the sum over all nth of them (the three-term gather saw only three)
-        val = (double)nth * to_c(y3d[map3d[r] + (long long)jprobe * jstr[r]]);
+        // mode-0 entry is the sum over all nth of them (the three-term gather saw only three); the axis unknown itself
+        // is carried as sqrt(nth) x_axis (see k_dft_gather), which leaves sqrt(nth) B -- the transpose of its row
+        val = sqrt((double)nth) * to_c(y3d[map3d[r] + (long long)jprobe * jstr[r]]);
         if (hs[r] != 0) val = mk(val.y, -val.x);
+    } else if (jstr[q] == 0) {
+        val = (1.0 / sqrt((double)nth)) * val;          // axis row (scaled by the gather) of an axis column: unscaled entry
     }
     const int h2 = hs[q];
     if (h2 != 0) {
@@ -435,6 +440,41 @@ int band_form_shifted_mode(const BandPlan& bp, int mode, const double* s_d, void
 }
 
 // (the diagonal is invariant under the rotation; modes m and nth - m share it)
+// max |K(i,j) - K(j,i)| and max |K(i,j)| over the stored band of all modes (non-negative doubles order like their bit patterns)
+template <typename TB>
+__global__ void k_band_asym(const TB* __restrict__ K, long long n2, int p, int pw, int ldab, size_t nel, unsigned long long* __restrict__ out) {
+    const long long j = blockIdx.x;                  // one column per CTA, threads across the sub-diagonals
+    const TB* A = K + (size_t)blockIdx.y * nel;
+    double da = 0.0, mx = 0.0;
+    if (threadIdx.x == 0) mx = sqrt(Sc<TB>::abs2(A[pw + j * (long long)ldab]));
+    for (int d = 1 + threadIdx.x; d <= p && j + d < n2; d += blockDim.x) {
+        TB lo = A[(pw + d) + j * (long long)ldab], up = A[(pw - d) + (j + d) * (long long)ldab];
+        da = fmax(da, sqrt(Sc<TB>::abs2(lo - up)));
+        mx = fmax(mx, fmax(sqrt(Sc<TB>::abs2(lo)), sqrt(Sc<TB>::abs2(up))));
+    }
+    for (int o = 16; o; o >>= 1) { da = fmax(da, __shfl_xor_sync(0xffffffffu, da, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMax(out, (unsigned long long)__double_as_longlong(da)); atomicMax(out + 1, (unsigned long long)__double_as_longlong(mx)); }
+}
+int band_check_symmetric(const BandPlan& bp, double* asym_rel, cudaStream_t st) {
+    void* buf = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_band_mu);
+        CS_TRY(band_scratch(3, st, 2 * sizeof(unsigned long long), false, &buf));
+    }
+    CS_CUDA(cudaMemsetAsync(buf, 0, 2 * sizeof(unsigned long long), st));
+    dim3 g((unsigned)bp.n2, bp.nmodes);
+    if (bp.cplx_band) k_band_asym<cplx><<<g, 128, 0, st>>>((const cplx*)bp.Kband, bp.n2, bp.p, bp.pw, bp.ldab, bp.band_elems(), (unsigned long long*)buf);
+    else k_band_asym<double><<<g, 128, 0, st>>>((const double*)bp.Kband, bp.n2, bp.p, bp.pw, bp.ldab, bp.band_elems(), (unsigned long long*)buf);
+    CS_CUDA(cudaGetLastError());
+    unsigned long long h[2];
+    CS_CUDA(cudaMemcpyAsync(h, buf, sizeof h, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    double da, mx;
+    memcpy(&da, &h[0], 8); memcpy(&mx, &h[1], 8);
+    *asym_rel = mx > 0 ? da / mx : 0.0;
+    return CS_OK;
+}
+
 template <typename TB>
 __global__ void k_diag_weights(const long long* __restrict__ map3d, const int* __restrict__ jstr, const double* __restrict__ mdiag,
                                long long n2, int pw, int ldab, int nmodes, int nth, const TB* __restrict__ K,
@@ -483,14 +523,15 @@ int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long lo
 // chunk 0 parks the factored block in `scratch`, the update kernel copies it in place.
 template <typename T, int NB>
 __global__ void __launch_bounds__(160)
-k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, T* __restrict__ scratch) {
+k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, T* __restrict__ scratch, int sym, int dahead) {
     __shared__ T D[NB][NB + 1];                      // D[r][c]
     T* A = LU + (size_t)blockIdx.y * nel + pw;       // dense view base
     int nbe = (int)min((long long)NB, n2 - t);
     int R = (int)min((long long)p, n2 - (t + nbe));
     int tid = threadIdx.x;
-    int idx = blockIdx.x * 64 + (tid & 63);          // row / column handled by this thread
-    bool isrow = (tid < 64) && idx < R, iscol = (tid >= 64 && tid < 128) && idx < R;
+    // symmetric matrices: 128 rows of A21 per CTA and no column solves -- U12 = diag(U11) L21^T is written by the row threads
+    int idx = sym ? blockIdx.x * 128 + (tid & 127) : blockIdx.x * 64 + (tid & 63);          // row / column handled by this thread
+    bool isrow = (tid < (sym ? 128 : 64)) && idx < R, iscol = !sym && (tid >= 64 && tid < 128) && idx < R;
     // threads 0..127: 64 rows of A21 + 64 columns of A12; warp 4: the LU of the diagonal block.
     // The panel loads are issued first so that they overlap the A11 factorisation.
     T v[NB];
@@ -503,16 +544,20 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
 #pragma unroll
         for (int r = 0; r < NB; ++r) v[r] = (r < nbe) ? cp[r] : Sc<T>::zero();
     }
+    // dahead: the pivot block was factored (and parked in `scratch`) by the trailing update of the previous step, off the
+    // critical path -- see k_lu_update
+    const T* Sin = scratch + (size_t)blockIdx.y * NB * NB;
     for (int e = tid; e < NB * NB; e += blockDim.x) {
         int r = e % NB, c = e / NB;
         T val = (r == c) ? Sc<T>::one() : Sc<T>::zero();
-        if (r < nbe && c < nbe) val = A[(t + r) + (t + c) * (long long)ld];
+        if (dahead) val = Sin[e];
+        else if (r < nbe && c < nbe) val = A[(t + r) + (t + c) * (long long)ld];
         D[r][c] = val;
     }
     __syncthreads();
     // unblocked LU of the NB x NB diagonal block by one warp (lane r owns row r)
     // (the LU warp reuses v[] for its row: it holds no panel data)
-    if (tid >= 128) {
+    if (tid >= 128 && !dahead) {
         int lane = tid - 128;
         int r = lane & (NB - 1);
 #pragma unroll
@@ -534,7 +579,7 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
         }
     }
     __syncthreads();
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && !dahead) {
         T* S = scratch + (size_t)blockIdx.y * NB * NB;
         for (int e = tid; e < NB * NB; e += blockDim.x) S[e] = D[e % NB][e / NB];
     }
@@ -549,6 +594,11 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) if (c < nbe) A[row + (t + c) * (long long)ld] = v[c];
+        if (sym) {
+            T* cp = A + row * (long long)ld + t;         // column `row` of U12
+#pragma unroll
+            for (int r = 0; r < NB; ++r) if (r < nbe) cp[r] = D[r][r] * v[r];
+        }
     } else if (iscol) {
         // column b of A12:  L11 w = col (unit lower)
 #pragma unroll
@@ -566,9 +616,10 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
 
 template <typename T, int NB>
 __global__ void __launch_bounds__(256)
-k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, const T* __restrict__ scratch, int part, int tiles) {
+k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, T* __restrict__ scratch, int part, int tiles, int dahead) {
     __shared__ T Ls[NB][32];
     __shared__ T Us[NB][33];
+    __shared__ T Dn[NB][NB + 1];
     T* A = LU + (size_t)blockIdx.z * nel + pw;
     int nbe = (int)min((long long)NB, n2 - t);
     int R = (int)min((long long)p, n2 - (t + nbe));
@@ -577,6 +628,14 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     int bx = blockIdx.x, by = blockIdx.y;
     if (part == 1) { if (bx < tiles) by = 0; else { by = bx - tiles + 1; bx = 0; } }
     else if (part == 2) { bx += 1; by += 1; }
+    else if (part == 3) {
+        // symmetric matrices: the tiles on and below the diagonal only (1-D grid of tiles (tiles + 1) / 2, column by column);
+        // the upper triangle of the window is never read again -- the panel mirrors the pivot rows from L21
+        int L = bx, rem = tiles;
+        by = 0;
+        while (L >= rem) { L -= rem; --rem; ++by; }
+        bx = by + L;
+    }
     int a0 = bx * 32, b0 = by * 32;
     int tid = threadIdx.x;
     if (bx == 0 && by == 0) {
@@ -616,6 +675,28 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     if (m1 && n0) c00[16] = old10 - acc10;
     if (m0 && n1) c01[0] = old01 - acc01;
     if (m1 && n1) c01[16] = old11 - acc11;
+    // dahead: the CTA of the first diagonal tile also factors the NEXT pivot block (the leading NB x NB of its tile, still in
+    // registers) and parks it in `scratch`, while the rest of the grid is still updating: the scalar LU of the pivot block
+    // (NB dependent complex reciprocals, ~4 us) leaves the critical path of the panel kernel
+    if constexpr (NB == 16) {
+        if (dahead && bx == 0 && by == 0 && t + nbe < n2) {
+            const int nbe2 = (int)min((long long)NB, n2 - (t + nbe));
+            T val = (ta == tb) ? Sc<T>::one() : Sc<T>::zero();
+            if (ta < nbe2 && tb < nbe2) val = (m0 && n0) ? old00 - acc00 : c00[0];      // (narrow bands: beyond this step's reach)
+            Dn[ta][tb] = val;
+            __syncthreads();
+            // right-looking scalar LU out of shared memory, one element per thread (no per-thread row in registers: the
+            // tile update's register budget, and with it the occupancy of the whole grid, stays what it was)
+            for (int c = 0; c < NB - 1; ++c) {
+                if (tb == c && ta > c) Dn[ta][c] = Dn[ta][c] * Sc<T>::inv(Dn[c][c]);
+                __syncthreads();
+                if (ta > c && tb > c) Dn[ta][tb] -= Dn[ta][c] * Dn[c][tb];
+                __syncthreads();
+            }
+            T* S = scratch + (size_t)blockIdx.z * NB * NB;
+            S[tid] = Dn[tid % NB][tid / NB];
+        }
+    }
 }
 
 // ---- fused step: trailing update of step t + panel of step t+1 in ONE launch ("last block done") ----
@@ -917,14 +998,20 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     // (timing experiments only: CS_LU_SKIP=panel|update drops one of the two kernels of every step -- wrong factors)
     static const int skip = [] { const char* e = getenv("CS_LU_SKIP"); return !e ? 0 : (!strcmp(e, "panel") ? 1 : (!strcmp(e, "update") ? 2 : 0)); }();
     const bool la = stB != nullptr && tiles >= 2;
+    static const bool sym_env = [] { const char* e = getenv("CS_LU_SYM"); return !(e && atoi(e) == 0); }();
+    const bool sym = bp.sym && sym_env && !la && !big;
+    if (sym) chunks = (bp.p + 127) / 128;
+    // pivot block of step t+1 factored by the update of step t (CS_LU_DAHEAD=0: by the panel kernel itself, as before)
+    static const bool dahead_env = [] { const char* e = getenv("CS_LU_DAHEAD"); return !(e && atoi(e) == 0); }();
+    const int dahead = (dahead_env && NB == 16 && !la && !big && skip == 0) ? 1 : 0;
     // MEASURED (109x32x460, 17 systems): 356 ms (443 ms at 3 CTAs/SM) vs 273 ms for the two-kernel schedule -- the one-CTA
     // panel tail of the last system is exposed and the lower occupancy slows the tiles; opt-in only (CS_LU_FUSED=1)
     static const bool fused_on = [] { const char* e = getenv("CS_LU_FUSED"); return e && atoi(e) == 1; }();
-    if (fused_on && !la && !big && NB == 16 && tiles >= 2 && skip == 0 && cnt) {
+    if (fused_on && !la && !big && !sym && NB == 16 && tiles >= 2 && skip == 0 && cnt) {
         // one launch per block step: update of step t + panel of step t+1 (k_lu_update_fused); the first panel stands alone
         if (cudaMemsetAsync(cnt, 0, (size_t)nsys * sizeof(int), st) != cudaSuccess) return CS_ERR;
         dim3 gp(chunks, nsys);
-        k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, 0, scratch);
+        k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, 0, scratch, 0, 0);
         int step = 0;
         for (long long t = 0; t < bp.n2; t += NB, ++step) {
             dim3 g(nsys, tiles * tiles, 1);
@@ -937,23 +1024,28 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     bool have_u2 = false;
     for (long long t = 0; t < bp.n2; t += NB) {
         dim3 gp(chunks, nsys);
-        if (skip != 1) k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch);
+        if (skip != 1) k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, sym ? 1 : 0, (dahead && t > 0) ? 1 : 0);
         if (skip == 2) continue;
+        if (sym) {
+            dim3 g(tiles * (tiles + 1) / 2, 1, nsys);
+            k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, 3, tiles, dahead);
+            continue;
+        }
         if (!la) {
             dim3 g(tiles, tiles, nsys);
             if (big) k_lu_update64<T, 16><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 0, tiles);
-            else k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 0, tiles);
+            else k_lu_update<T, NB><<<g, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, 0, tiles, dahead);
             continue;
         }
         if (cudaEventRecord(evP, st) != cudaSuccess) return CS_ERR;
         if (have_u2 && cudaStreamWaitEvent(st, evU, 0) != cudaSuccess) return CS_ERR;       // U1(t) overlaps the region U2(t-1) wrote
         dim3 g1(2 * tiles - 1, 1, nsys);
         if (big) k_lu_update64<T, 16><<<g1, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 1, tiles);
-        else k_lu_update<T, NB><<<g1, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 1, tiles);
+        else k_lu_update<T, NB><<<g1, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, 1, tiles, 0);
         if (cudaStreamWaitEvent(stB, evP, 0) != cudaSuccess) return CS_ERR;
         dim3 g2(tiles - 1, tiles - 1, nsys);
         if (big) k_lu_update64<T, 16><<<g2, 256, 0, stB>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 2, tiles);
-        else k_lu_update<T, NB><<<g2, 256, 0, stB>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, 2, tiles);
+        else k_lu_update<T, NB><<<g2, 256, 0, stB>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, 2, tiles, 0);
         if (cudaEventRecord(evU, stB) != cudaSuccess) return CS_ERR;
         have_u2 = true;
     }
@@ -979,6 +1071,8 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     { const char* e = getenv("CS_LU_LOOKAHEAD"); if (e && atoi(e) == 1) groups_key += 100; }
     { const char* e = getenv("CS_LU_TILE"); if (e) groups_key += 10000 * atoi(e); }
     { const char* e = getenv("CS_LU_FUSED"); if (e && atoi(e) == 1) groups_key += 1000000; }
+    { const char* e = getenv("CS_LU_SYM"); if (bp.sym && !(e && atoi(e) == 0)) groups_key += 50; }
+    { const char* e = getenv("CS_LU_DAHEAD"); if (e && atoi(e) == 0) groups_key += 25; }
     FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {

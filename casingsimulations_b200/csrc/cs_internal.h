@@ -94,6 +94,9 @@ struct BandPlan {
     // the probing response is confined to theta columns jprobe-1 .. jprobe+1 (three-term DFT).  Not for face unknowns:
     // the Fy faces of the innermost cells share the single axis Ez edge, so C C^T couples them across ALL theta columns
     bool thin_probe = true;
+    // the probed band matrices are symmetric (measured after probing, band_check_symmetric): the step LU then works on the
+    // lower triangle of the trailing window only and mirrors the pivot rows, U12 = diag(U11) L21^T
+    bool sym = false;
     size_t band_elems() const { return (size_t)n2 * ldab; }
     // mode vectors per 3-D vector: complex factors take all nth modes (mode m uses factor min(m, nth - m));
     // real factors (real shift) take Re / Im of modes 0 .. nth/2 of a REAL 3-D vector as 2 * nmodes real vectors
@@ -118,6 +121,7 @@ int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]
 int band_probe_gather(const BandPlan& bp, const void* y3d, bool y_cplx, void* ym, long long n3d, int nb, cudaStream_t st);
 int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st);
 // w[f][3-D index] = 1 / |diag(A(s_f))| recovered from the mode matrices (mean over modes of K_m[q,q]) + s_f * mass
+int band_check_symmetric(const BandPlan& bp, double* asym_rel /*host*/, cudaStream_t st);
 int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long long n3d, double* w, cudaStream_t st);
 // LU[f][mode] = Kband[mode] + s[f] * diag(mdiag)   (f = 0..nshift-1)
 int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shift*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
