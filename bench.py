@@ -384,13 +384,19 @@ def run_ours(args, rank, world, local_rank):
         # band LU of the theta-mode systems: nth/2+1 complex band matrices of order n2, half bandwidth p, per frequency
         nx, nth, nz = (int(v) for v in m.vnC)
         n2, p, nsys = (3 * nx + 1) * (nz + 1), 3 * nx + 3, nth // 2 + 1
-        flops = 8.0 * n2 * float(p) ** 2 * nsys * len(freqs)              # complex LU without pivoting, 8 flop per complex FMA
+        # EXECUTED flops of the symmetric step LU (8 per complex FMA): per 16-column block step the row solves of the panel
+        # (p rows x 16^2/2) and the 32x32 tiles on and below the diagonal of the trailing window (T (T+1)/2 tiles x 32x32x16,
+        # T = ceil(p / 32)); a general LU of the same band would execute 8 n2 p^2 (reported beside it)
+        tl = (p + 31) // 32
+        flops = 8.0 * (n2 / 16.0) * (p * 128.0 + tl * (tl + 1) / 2 * 32 * 32 * 16) * nsys * len(freqs)
+        flops_lu = 8.0 * n2 * float(p) ** 2 * nsys * len(freqs)
         ach = flops / (ms_factor * 1e-3) / 1e12
-        roof = {"bound": "fp64", "kernel": "band LU of the {} theta-mode systems per frequency (k_lu_panel + k_lu_update, {} dependent "
+        roof = {"bound": "fp64", "kernel": "symmetric band LU of the {} theta-mode systems per frequency (k_lu_panel + k_lu_update on the lower triangle, {} dependent "
                                             "16-column block steps replayed as one CUDA graph): {:.0f} % of the step's device time"
                                             .format(nsys, (n2 + 15) // 16, 100.0 * ms_factor / (t_dev / args.steps * 1e3)),
                 "achieved": ach, "peak": fp64_peak, "peak_source": "live DFMA microbenchmark (cs_fp64_peak), 148 SMs",
                 "unit": "TFLOP/s", "frac": ach / fp64_peak, "flops_per_step": flops,
+                "general_lu_equivalent": {"flops_per_step": flops_lu, "tflops": flops_lu / (ms_factor * 1e-3) / 1e12},
                 "ms_factor_per_step": ms_factor, "traffic": None,
                 "traffic_note": "per-launch DRAM bytes of k_lu_panel / k_lu_update (the window is L2 resident) in profiles/r02_ncu_lu_step.md",
                 "launch_shares": "profiles/r02_launch_list_3d.md"}

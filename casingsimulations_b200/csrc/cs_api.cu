@@ -345,7 +345,8 @@ static int build_plan(cs_op* op) {
         }
     }
     bp.nb = band_choose_nb(bp.p);
-    bp.pw = bp.p + bp.nb;
+    bp.nbf = band_choose_nbf(bp.p, bp.nb);
+    bp.pw = bp.p + std::max(bp.nb, bp.nbf);
     bp.ldab = 2 * bp.pw + 1;
     bp.nth = nth;
     bp.thin_probe = (op->family != 2);
@@ -428,7 +429,7 @@ static int probe_plan(cs_op* op) {
     // every operator of the path is symmetric (complex symmetric after the shift); an assembled CSR matrix may not be --
     // measured on the probed band, and only then does the step factorisation use the lower triangle alone
     double asym = 1.0;
-    CS_TRY(band_check_symmetric(op->bp, &asym, op->ctx->st));
+    CS_TRY(band_check_symmetric(op->bp, op->csr_vals ? 1 : 29, &asym, op->ctx->st));
     op->bp.sym = asym < 1e-11;
     static const bool log = getenv("CS_FACTOR_LOG") != nullptr;
     if (log) fprintf(stderr, "[cs] probed band: kind %d  n2 %lld  p %d  modes %d  asymmetry %.2e -> %s\n", op->kind, op->bp.n2, op->bp.p, op->bp.nmodes, asym,

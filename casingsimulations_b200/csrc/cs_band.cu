@@ -442,8 +442,8 @@ int band_form_shifted_mode(const BandPlan& bp, int mode, const double* s_d, void
 // (the diagonal is invariant under the rotation; modes m and nth - m share it)
 // max |K(i,j) - K(j,i)| and max |K(i,j)| over the stored band of all modes (non-negative doubles order like their bit patterns)
 template <typename TB>
-__global__ void k_band_asym(const TB* __restrict__ K, long long n2, int p, int pw, int ldab, size_t nel, unsigned long long* __restrict__ out) {
-    const long long j = blockIdx.x;                  // one column per CTA, threads across the sub-diagonals
+__global__ void k_band_asym(const TB* __restrict__ K, long long n2, int p, int pw, int ldab, size_t nel, int stride, unsigned long long* __restrict__ out) {
+    const long long j = blockIdx.x * (long long)stride;      // one column per CTA, threads across the sub-diagonals
     const TB* A = K + (size_t)blockIdx.y * nel;
     double da = 0.0, mx = 0.0;
     if (threadIdx.x == 0) mx = sqrt(Sc<TB>::abs2(A[pw + j * (long long)ldab]));
@@ -455,16 +455,20 @@ __global__ void k_band_asym(const TB* __restrict__ K, long long n2, int p, int p
     for (int o = 16; o; o >>= 1) { da = fmax(da, __shfl_xor_sync(0xffffffffu, da, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
     if ((threadIdx.x & 31) == 0) { atomicMax(out, (unsigned long long)__double_as_longlong(da)); atomicMax(out + 1, (unsigned long long)__double_as_longlong(mx)); }
 }
-int band_check_symmetric(const BandPlan& bp, double* asym_rel, cudaStream_t st) {
+// stride > 1: every stride-th column only (the transposed reads are uncoalesced: 60 ms for all columns of the 109x32x1394
+// edge systems).  The operators of the path are symmetric by construction, for them the sampled check is a guard; an
+// assembled CSR matrix is checked in full.
+int band_check_symmetric(const BandPlan& bp, int stride, double* asym_rel, cudaStream_t st) {
     void* buf = nullptr;
     {
         std::lock_guard<std::mutex> lock(g_band_mu);
         CS_TRY(band_scratch(3, st, 2 * sizeof(unsigned long long), false, &buf));
     }
     CS_CUDA(cudaMemsetAsync(buf, 0, 2 * sizeof(unsigned long long), st));
-    dim3 g((unsigned)bp.n2, bp.nmodes);
-    if (bp.cplx_band) k_band_asym<cplx><<<g, 128, 0, st>>>((const cplx*)bp.Kband, bp.n2, bp.p, bp.pw, bp.ldab, bp.band_elems(), (unsigned long long*)buf);
-    else k_band_asym<double><<<g, 128, 0, st>>>((const double*)bp.Kband, bp.n2, bp.p, bp.pw, bp.ldab, bp.band_elems(), (unsigned long long*)buf);
+    if (stride < 1) stride = 1;
+    dim3 g((unsigned)((bp.n2 + stride - 1) / stride), bp.nmodes);
+    if (bp.cplx_band) k_band_asym<cplx><<<g, 128, 0, st>>>((const cplx*)bp.Kband, bp.n2, bp.p, bp.pw, bp.ldab, bp.band_elems(), stride, (unsigned long long*)buf);
+    else k_band_asym<double><<<g, 128, 0, st>>>((const double*)bp.Kband, bp.n2, bp.p, bp.pw, bp.ldab, bp.band_elems(), stride, (unsigned long long*)buf);
     CS_CUDA(cudaGetLastError());
     unsigned long long h[2];
     CS_CUDA(cudaMemcpyAsync(h, buf, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -614,12 +618,83 @@ k_lu_panel(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, 
     }
 }
 
+// Panel of a step whose pivot block is already factored (parked in `scratch` by the previous update, see k_lu_update):
+// four threads per row of A21.  One thread per row runs 136 dependent-ish complex FMAs -- ~1 500 instructions issued one
+// per ~10 cycles by a lone warp per scheduler, ~8 us of the step.  Here the row solve  v U11 = a  is right-looking over a
+// quad: the owner of column c2 finishes v[c2] = a[c2] / U[c2][c2], one shuffle hands it to the quad, every thread updates
+// the (at most four) later columns it owns -- a chain of 16 x (shuffle + complex FMA + complex multiply).  Symmetric
+// matrices get U12 = diag(U11) L21^T from the same registers (16 contiguous elements per quad); general ones solve the
+// columns of A12 (L11 w = a, unit lower) in the second half of the grid.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_lu_panel4(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, const T* __restrict__ scratch, int sym, int chunks) {
+    constexpr int NB = 16;
+    __shared__ T D[NB][NB + 1];
+    __shared__ T invd[NB];
+    T* A = LU + (size_t)blockIdx.y * nel + pw;
+    const int nbe = (int)min((long long)NB, n2 - t);
+    const int R = (int)min((long long)p, n2 - (t + nbe));
+    const int tid = threadIdx.x, q = tid & 3, lane = tid & 31, qbase = lane & ~3;
+    const bool colmode = (int)blockIdx.x >= chunks;
+    const int idx = (colmode ? (int)blockIdx.x - chunks : (int)blockIdx.x) * 64 + (tid >> 2);
+    const bool act = idx < R;
+    const long long rc = t + nbe + idx;                 // the row of A21 (column of A12) of this quad
+    const T zero = Sc<T>::zero();
+    T a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = q + 4 * i;
+        a[i] = zero;
+        if (act && c < nbe) a[i] = colmode ? A[rc * (long long)ld + t + c] : A[rc + (t + c) * (long long)ld];
+    }
+    D[tid % NB][tid / NB] = scratch[(size_t)blockIdx.y * NB * NB + tid];
+    __syncthreads();
+    if (tid < NB) invd[tid] = Sc<T>::inv(D[tid][tid]);
+    __syncthreads();
+    if (!colmode) {
+#pragma unroll
+        for (int c2 = 0; c2 < NB; ++c2) {
+            const int io = c2 >> 2, qo = c2 & 3;
+            const T v = shfl_t<T>(a[io] * invd[c2], qbase | qo);
+            if (q == qo) a[io] = v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < io) continue;
+                if (i > io || q > qo) a[i] -= v * D[c2][q + 4 * i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = q + 4 * i;
+            if (act && c < nbe) {
+                A[rc + (t + c) * (long long)ld] = a[i];
+                if (sym) A[(t + c) + rc * (long long)ld] = D[c][c] * a[i];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r2 = 0; r2 < NB; ++r2) {
+            const int io = r2 >> 2, qo = r2 & 3;
+            const T w = shfl_t<T>(a[io], qbase | qo);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < io) continue;
+                if (i > io || q > qo) a[i] -= D[q + 4 * i][r2] * w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = q + 4 * i;
+            if (act && r < nbe) A[rc * (long long)ld + t + r] = a[i];
+        }
+    }
+}
+
 template <typename T, int NB>
 __global__ void __launch_bounds__(256)
 k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld, long long t, T* __restrict__ scratch, int part, int tiles, int dahead) {
     __shared__ T Ls[NB][32];
     __shared__ T Us[NB][33];
-    __shared__ T Dn[NB][NB + 1];
     T* A = LU + (size_t)blockIdx.z * nel + pw;
     int nbe = (int)min((long long)NB, n2 - t);
     int R = (int)min((long long)p, n2 - (t + nbe));
@@ -678,24 +753,36 @@ k_lu_update(T* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
     // dahead: the CTA of the first diagonal tile also factors the NEXT pivot block (the leading NB x NB of its tile, still in
     // registers) and parks it in `scratch`, while the rest of the grid is still updating: the scalar LU of the pivot block
     // (NB dependent complex reciprocals, ~4 us) leaves the critical path of the panel kernel
-    if constexpr (NB == 16) {
-        if (dahead && bx == 0 && by == 0 && t + nbe < n2) {
-            const int nbe2 = (int)min((long long)NB, n2 - (t + nbe));
-            T val = (ta == tb) ? Sc<T>::one() : Sc<T>::zero();
-            if (ta < nbe2 && tb < nbe2) val = (m0 && n0) ? old00 - acc00 : c00[0];      // (narrow bands: beyond this step's reach)
-            Dn[ta][tb] = val;
+    if (dahead && bx == 0 && by == 0 && t + nbe < n2) {
+        // (the staged pivot rows are dead after the k loop of every thread: the block lives in the memory of Us)
+        __syncthreads();
+        T (*Dn)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(&Us[0][0]);
+        const int nbe2 = (int)min((long long)NB, n2 - (t + nbe));
+        auto put = [&](int r, int c, bool inwin, T fresh, const T* gp) {
+            if (r >= NB || c >= NB) return;
+            T val = (r == c) ? Sc<T>::one() : Sc<T>::zero();
+            if (r < nbe2 && c < nbe2) val = inwin ? fresh : *gp;      // (narrow bands: beyond this step's reach, unchanged)
+            Dn[r][c] = val;
+        };
+        put(ta, tb, m0 && n0, old00 - acc00, c00);
+        put(ta + 16, tb, m1 && n0, old10 - acc10, c00 + 16);
+        put(ta, tb + 16, m0 && n1, old01 - acc01, c01);
+        put(ta + 16, tb + 16, m1 && n1, old11 - acc11, c01 + 16);
+        __syncthreads();
+        // right-looking scalar LU out of shared memory (no per-thread row in registers: the tile update's register
+        // budget, and with it the occupancy of the whole grid, stays what it was)
+        for (int c = 0; c < NB - 1; ++c) {
+            if (tid > c && tid < NB) Dn[tid][c] = Dn[tid][c] * Sc<T>::inv(Dn[c][c]);
             __syncthreads();
-            // right-looking scalar LU out of shared memory, one element per thread (no per-thread row in registers: the
-            // tile update's register budget, and with it the occupancy of the whole grid, stays what it was)
-            for (int c = 0; c < NB - 1; ++c) {
-                if (tb == c && ta > c) Dn[ta][c] = Dn[ta][c] * Sc<T>::inv(Dn[c][c]);
-                __syncthreads();
-                if (ta > c && tb > c) Dn[ta][tb] -= Dn[ta][c] * Dn[c][tb];
-                __syncthreads();
+#pragma unroll
+            for (int q = 0; q < (NB * NB) / 256; ++q) {
+                const int r = ta + 16 * (q & 1), cc = tb + 16 * (q >> 1);
+                if (r > c && cc > c) Dn[r][cc] -= Dn[r][c] * Dn[c][cc];
             }
-            T* S = scratch + (size_t)blockIdx.z * NB * NB;
-            S[tid] = Dn[tid % NB][tid / NB];
+            __syncthreads();
         }
+        T* S = scratch + (size_t)blockIdx.z * NB * NB;
+        for (int e = tid; e < NB * NB; e += 256) S[e] = Dn[e % NB][e / NB];
     }
 }
 
@@ -1003,7 +1090,8 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     if (sym) chunks = (bp.p + 127) / 128;
     // pivot block of step t+1 factored by the update of step t (CS_LU_DAHEAD=0: by the panel kernel itself, as before)
     static const bool dahead_env = [] { const char* e = getenv("CS_LU_DAHEAD"); return !(e && atoi(e) == 0); }();
-    const int dahead = (dahead_env && NB == 16 && !la && !big && skip == 0) ? 1 : 0;
+    const int dahead = (dahead_env && !la && !big && skip == 0) ? 1 : 0;
+    static const bool panel4 = [] { const char* e = getenv("CS_LU_PANEL4"); return !(e && atoi(e) == 0); }();
     // MEASURED (109x32x460, 17 systems): 356 ms (443 ms at 3 CTAs/SM) vs 273 ms for the two-kernel schedule -- the one-CTA
     // panel tail of the last system is exposed and the lower occupancy slows the tiles; opt-in only (CS_LU_FUSED=1)
     static const bool fused_on = [] { const char* e = getenv("CS_LU_FUSED"); return e && atoi(e) == 1; }();
@@ -1024,7 +1112,13 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     bool have_u2 = false;
     for (long long t = 0; t < bp.n2; t += NB) {
         dim3 gp(chunks, nsys);
-        if (skip != 1) k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, sym ? 1 : 0, (dahead && t > 0) ? 1 : 0);
+        if (skip != 1) {
+            if (NB == 16 && dahead && t > 0 && panel4) {
+                const int ch4 = (bp.p + 63) / 64;
+                dim3 g4(sym ? ch4 : 2 * ch4, nsys);
+                k_lu_panel4<T><<<g4, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, sym ? 1 : 0, ch4);
+            } else k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, sym ? 1 : 0, (dahead && t > 0) ? 1 : 0);
+        }
         if (skip == 2) continue;
         if (sym) {
             dim3 g(tiles * (tiles + 1) / 2, 1, nsys);
@@ -1050,14 +1144,20 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
         have_u2 = true;
     }
     if (la && have_u2 && cudaStreamWaitEvent(st, evU, 0) != cudaSuccess) return CS_ERR;      // join
-    dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
-    k_invert_diag<T, NB><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
+    // diagonal blocks in the format of the substitution kernel (ITS block size, which may be smaller than the steps')
+    if (bp.nb == 16) {
+        dim3 gi((unsigned)((bp.n2 + 15) / 16), nsys);
+        k_invert_diag<T, 16><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
+    } else {
+        dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
+        k_invert_diag<T, NB><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
+    }
     return CS_OK;
 }
 
 template <typename T, int NB>
 static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
-    CS_CHECK(bp.nb == NB, "band plan block size must equal the instantiated NB");
+    CS_CHECK(bp.nbf == NB, "band plan step size must equal the instantiated NB");
     std::lock_guard<std::mutex> lock(g_band_mu);
     void* scratch = nullptr;
     CS_TRY(band_scratch(0, st, (size_t)nsys * NB * NB * sizeof(T), false, &scratch));
@@ -1073,6 +1173,8 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     { const char* e = getenv("CS_LU_FUSED"); if (e && atoi(e) == 1) groups_key += 1000000; }
     { const char* e = getenv("CS_LU_SYM"); if (bp.sym && !(e && atoi(e) == 0)) groups_key += 50; }
     { const char* e = getenv("CS_LU_DAHEAD"); if (e && atoi(e) == 0) groups_key += 25; }
+    { const char* e = getenv("CS_LU_PANEL4"); if (e && atoi(e) == 0) groups_key += 12; }
+    { const char* e = getenv("CS_LU_NBF"); if (e) groups_key += 6; }
     FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
@@ -1620,6 +1722,7 @@ static int band_factor_any(const BandPlan& bp, T* LU, int nsys, cudaStream_t st)
         ClusterLuPlan pl = cluster_lu_plan<T, 16>(bp);
         if (pl.ok) { bp.diag_full = 1; ClusterLuSource none{}; return band_factor_cluster<T, T, 16>(bp, pl, LU, nsys, none, st); }
         bp.diag_full = 0;
+        if (bp.nbf == 32) return band_factor_t<T, 32>(bp, LU, nsys, st);
         return band_factor_t<T, 16>(bp, LU, nsys, st);
     }
     CS_CHECK(bp.nb == 32, "band plan block size must be 16 or 32");
@@ -1654,7 +1757,7 @@ int band_factor_launches(const BandPlan& bp, bool lu_cplx) {
         bool ok = lu_cplx ? cluster_lu_plan<cplx, 16>(bp).ok : cluster_lu_plan<double, 16>(bp).ok;
         if (ok) return 1;
     }
-    return 1 + 2 * (int)((bp.n2 + bp.nb - 1) / bp.nb);
+    return 1 + 2 * (int)((bp.n2 + bp.nbf - 1) / bp.nbf);
 }
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st) {
     if (lu_cplx) return band_factor_any<cplx>(bp, (cplx*)LU, nsys_tot, st);
@@ -2016,6 +2119,17 @@ int band_choose_nb(int p) {
     // factor 137 ms vs 84 ms, solve 25 vs 22 ms), so 16 is the default; CS_BAND_NB=32 opts in.
     size_t stage32 = (size_t)(p + 32) * 32 * sizeof(cplx);
     if (e && atoi(e) == 32 && 2 * stage32 + 16 * 1024 <= 200 * 1024) return 32;
+    return 16;
+}
+
+// Factorisation steps of 32 columns with the substitution's 16-column blocks (CS_LU_NBF=32): half as many dependent launch
+// pairs.  MEASURED on 109x32x460 (17 systems, p = 330, symmetric steps): 215 ms vs 177 ms with 16-column steps -- a 32-column
+// step costs 47.7 us against 2 x 19.6 us: the row solves of the panel (4 x the dependent arithmetic per row) sit on the
+// critical path, not the launches.  Opt-in only.
+int band_choose_nbf(int p, int nb) {
+    const char* e = getenv("CS_LU_NBF");
+    if (nb != 16) return nb;
+    if (e && atoi(e) == 32 && p >= 64) return 32;
     return 16;
 }
 

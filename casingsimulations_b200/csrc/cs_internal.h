@@ -64,7 +64,11 @@ struct BandPlan {
     long long n2 = 0;          // unknowns per mode system (incl. dummies)
     int p = 0;                 // half bandwidth of the true couplings
     int nb = 16;               // block size of the blocked LU
-    int pw = 0;                // stored half bandwidth = p + nb
+    int pw = 0;                // stored half bandwidth = p + max(nb, nbf)
+    // block size of the FACTORISATION steps (step kernels only).  The scalar LU without pivoting does not depend on the
+    // blocking, so wide bands are factored in 32-column steps (half as many dependent launch pairs) while the substitution
+    // keeps its 16-column blocks; k_invert_diag prepares the diagonal blocks for the latter
+    int nbf = 16;
     int ldab = 0;              // 2*pw + 1
     int nth = 1;               // azimuthal cells of the mesh
     // stored mode systems per shift.  With T_m = diag(1 | i exp(+-i pi m / nth)) on the theta-staggered component
@@ -110,6 +114,7 @@ struct BandPlan {
 
 // block size (16 or 32) for a plan with half bandwidth p
 int band_choose_nb(int p);
+int band_choose_nbf(int p, int nb);
 void band_release_stream(cudaStream_t st);   // frees the band scratch buffers keyed by this stream
 int band_factor_launches(const BandPlan& bp, bool lu_cplx);
 // theta-DFT into the rotated mode basis x''_m = T_m^* x_m; xm [nvec][nmv][n2]
@@ -121,7 +126,7 @@ int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]
 int band_probe_gather(const BandPlan& bp, const void* y3d, bool y_cplx, void* ym, long long n3d, int nb, cudaStream_t st);
 int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st);
 // w[f][3-D index] = 1 / |diag(A(s_f))| recovered from the mode matrices (mean over modes of K_m[q,q]) + s_f * mass
-int band_check_symmetric(const BandPlan& bp, double* asym_rel /*host*/, cudaStream_t st);
+int band_check_symmetric(const BandPlan& bp, int stride, double* asym_rel /*host*/, cudaStream_t st);
 int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long long n3d, double* w, cudaStream_t st);
 // LU[f][mode] = Kband[mode] + s[f] * diag(mdiag)   (f = 0..nshift-1)
 int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shift*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);

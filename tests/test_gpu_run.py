@@ -286,6 +286,52 @@ def test_full_size_c3_dc_3d_properties():
     ctx.close()
 
 
+def test_full_size_c4_tdem_200_steps():
+    """BASELINE config 4 at full size: TDEM (default j formulation, backward Euler, run.py:260-315) on the 3-D mesh
+    109 x 32 x 460 (1 604 480 cells), 200 steps over 5 distinct dt (5 factorisations), TopCasingSrc.  The host cannot
+    factor one of these systems, so parity goes through size-independent properties of the scheme (the small-mesh twin
+    against the exactly assembled oracle systems is test_simulation_tdem / test_gpu_parity.py::test_tdem_run): every
+    Krylov solve to 1e-10, the galvanic initial state D (j0 + s_e) = 0, the ohmic energy j^T MfRho j non-increasing,
+    the divergence of j^n staying at rounding level, and the casing carrying the whole source current at t = 0."""
+    import time
+    import torch
+    from casingsimulations_b200 import _lib
+    nper, nth = 40, 32
+    steps = [(1e-6, nper), (1e-5, nper), (1e-4, nper), (1e-3, nper), (1e-2, nper)]
+    mp = cs.model.CasingInHalfspace(src_a=np.r_[0.0, 0.0, 0.0], src_b=np.r_[1000.0, 0.0, 0.0], mur_casing=100.0, timeSteps=steps)
+    mg = cs.CasingMeshGenerator(modelParameters=mp, npadx=10, npadz=25, csz=2.5, hy=np.ones(nth) * 2 * np.pi / nth)
+    m = mg.mesh
+    assert tuple(int(v) for v in m.vnC) == (109, 32, 460) and len(mp.timeSteps) == 200
+    th = m.vectorCCy[nth // 2]
+    mp.src_a, mp.src_b = np.r_[0.0, th, 0.0], np.r_[1000.0, th, 0.0]
+    src = cs.sources.TopCasingSrc(modelParameters=mp, meshGenerator=mg, physics="tdem")
+    src.validate()
+    ctx = _lib.Context(0)
+    ctx.set_mesh(m.hx, m.hy, m.hz, m.x0[2])
+    sig = ctx.paint(mp.paint_params())[0]
+    se_d = ctx.to_device(src.s_e)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = ctx.tdem_run("j", mp.timeSteps, se_d, rtol=1e-10)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    info = dict(ctx.info)
+    print("C4 TDEM: wall %.2f s" % wall, {k: round(float(v), 3) for k, v in info.items()})
+    assert info["converged"] == 1.0 and info["relres"] <= 5e-10      # worst TRUE residual of the 400 solves (recurrence stopped at 1e-10)
+    nds = float(torch.linalg.norm(ctx.div(se_d)))
+    assert float(torch.linalg.norm(ctx.div(out[0] + se_d))) <= 1e-6 * nds       # (1.5e-7 measured: unweighted norm of a 1e-10 weighted residual)
+    alpha = ctx.face_inner_product(sig, True, False)
+    en = np.array([float((out[t] * alpha * out[t]).sum()) for t in range(1, out.shape[0])])
+    assert np.all(en[1:] <= en[:-1] * (1 + 1e-9)), "ohmic energy must not increase"
+    assert en[-1] < 1e-3 * en[0]
+    for t in range(1, out.shape[0], 20):
+        assert float(torch.linalg.norm(ctx.div(out[t]))) <= 1e-6 * nds, t
+    iz = ctx.casing_currents(out[0], mp.casing_a, mp.casing_b, mp.casing_z)[1]
+    k = int(np.argmin(np.abs(m.vectorNz + 5.0)))
+    assert 0.9 < abs(float(iz[k])) <= 1.0 + 1e-6            # 5 m below the top nearly all of the 1 A is still in the casing
+    ctx.close()
+
+
 def test_theta_varying_flawed_casing_krylov(tmp_path):
     """A flawed casing (theta-limited flaw, model.py:583-668) breaks the block-circulant structure:
     the theta-mode factorisation (built from the theta = 0 column) is then only a preconditioner
