@@ -1090,7 +1090,7 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     if (sym) chunks = (bp.p + 127) / 128;
     // pivot block of step t+1 factored by the update of step t (CS_LU_DAHEAD=0: by the panel kernel itself, as before)
     static const bool dahead_env = [] { const char* e = getenv("CS_LU_DAHEAD"); return !(e && atoi(e) == 0); }();
-    const int dahead = (dahead_env && !la && !big && skip == 0) ? 1 : 0;
+    const int dahead = (dahead_env && !la && !big) ? 1 : 0;      // (also under CS_LU_SKIP: timing experiments on garbage)
     static const bool panel4 = [] { const char* e = getenv("CS_LU_PANEL4"); return !(e && atoi(e) == 0); }();
     // MEASURED (109x32x460, 17 systems): 356 ms (443 ms at 3 CTAs/SM) vs 273 ms for the two-kernel schedule -- the one-CTA
     // panel tail of the last system is exposed and the lower occupancy slows the tiles; opt-in only (CS_LU_FUSED=1)
