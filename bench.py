@@ -221,7 +221,7 @@ def stencil_roofline(torch, dev, reps=20):
         return {"kernel": name, "bytes_per_cell": bpc, "us_per_launch": t * 1e6, "achieved": bpc * ctx.nC / t / 1e9,
                 "frac": bpc * ctx.nC / t / 1e9 / peak}
     out["k4_edge_c128"] = one(_lib.KIND_EDGE_H, ctx.nE, True, 144.0, "k_edge_op<cplx> (K4: C^T MfRho C + i w MeMu)")
-    out["k4_face_f64"] = one(_lib.KIND_FACE_J, ctx.nF, False, 96.0, "k_face_op_* <double> (K4': MfRho (C MeMuI C^T MfRho + 1/dt))")
+    out["k4_face_f64"] = one(_lib.KIND_FACE_J, ctx.nF, False, 96.0, "k_face_axis + k_face_op_ring<double> (K4': MfRho (C MeMuI C^T MfRho + 1/dt))")
     out["k3_dc_f64"] = one(_lib.KIND_DC, ctx.nC, False, 40.0, "k_dc_apply<double> (K3: D~ MfRhoI D~^T)")
     ctx.close()
     return out

@@ -250,8 +250,9 @@ static int op_apply_dev(cs_op* op, const double* s_d, const void* x, void* y, in
     if (op->family == 0) return launch_dc_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st);
     if (op->family == 3) { g_launches += 2 * nvec - 1; return launch_node_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st); }
     if (op->family == 1) return launch_edge_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st);
-    // 3-D: two-pass face operator through an edge workspace (220 vs 385 us on the 4.86 M-cell mesh;
-    // CS_FACE_OP=fused forces the single-pass kernel).  2-D: single pass (6.5 vs 9.2 us at 152 k cells).
+    // 3-D: the single-pass ring kernel (118 us on the 4.86 M-cell mesh; its axis sums use the workspace) or, for theta
+    // rings wider than 32 cells, the two-pass operator through an edge workspace (220 us; the naive single pass
+    // CS_FACE_OP=fused: 385 us).  2-D: single pass (6.5 vs 9.2 us at 152 k cells).
     static const bool fused = [] { const char* e = getenv("CS_FACE_OP"); return e && !strcmp(e, "fused"); }();
     void* ew = nullptr;
     if (!fused && !c->m.sym) {

@@ -927,10 +927,158 @@ k_face_op_faces(MeshD m, const double* __restrict__ uF, const double* __restrict
     face_op_slot<T, EdgeRead<T>>(m, d, uF, s, x, y, sl.i, sl.j, sl.k);
 }
 
+// ---- single pass, full theta ring per CTA, z march ("ring" kernel; 3-D meshes with nth * 16 <= 512) ----
+// The two-pass variant moves 192 B/cell (real) for 96 algorithmic ones.  Here a CTA owns TW - 2 = 14 radial cells x ALL nth azimuthal
+// cells (so theta needs no halo: the neighbours j +- 1 wrap inside the tile; the first and last lane are the radial halo) and marches
+// ZC node levels.  Per level every thread loads its own three faces / weights once (register-prefetched one level
+// ahead), publishes u = uF x in shared memory, the edge values gE * (signed sum of the four u around the edge) are
+// computed once per edge and published, and the faces are gathered from them; the values of the level below that the
+// Fx / Fy faces need (u, the node-level edges, the Ez edges of the cell level) stay in registers.  Two barriers per level,
+// no workspace in HBM.  The shared axis edge (sum over all theta of the innermost Fy faces) comes from a one-warp-per-level
+// pre-kernel.
+template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int o);
+template <> __device__ __forceinline__ double shfl_down_t<double>(double v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ cplx shfl_down_t<cplx>(cplx v, int o) {
+    return mk(__shfl_down_sync(0xffffffffu, v.x, o), __shfl_down_sync(0xffffffffu, v.y, o));
+}
+template <typename T>
+__global__ void k_face_axis(MeshD m, const double* __restrict__ uF, const double* __restrict__ gE, const T* __restrict__ x, T* __restrict__ axis) {
+    const int k = blockIdx.x, sys = blockIdx.y;
+    x += (size_t)sys * m.nF;
+    const double* uy = uF + m.nFx;
+    T r = Sc<T>::zero();
+    for (int j = threadIdx.x; j < m.nth; j += 32) {
+        long long c = m.cidx(0, j, k);
+        r += uy[c] * x[m.nFx + c];
+    }
+    for (int o = 16; o; o >>= 1) r += shfl_down_t<T>(r, o);
+    if (threadIdx.x == 0) axis[(size_t)sys * m.nz + k] = gE[m.nEx + m.nEy + m.ezaxis(k)] * r;
+}
+
+template <typename T, int ZC, int TW>
+__global__ void __launch_bounds__(512)
+k_face_op_ring(MeshD m, const double* __restrict__ uF, const double* __restrict__ gE, const double* __restrict__ s_d,
+               const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ axis) {
+    extern __shared__ __align__(16) unsigned char face_sm[];
+    const int nth = blockDim.y;
+    const int tsz = nth * TW;
+    T* U = reinterpret_cast<T*>(face_sm);          // [3][nth][TW]  u of Fx, Fy (cell level n), Fz (node level n)
+    T* E = U + 3 * tsz;                            // [3][nth][TW]  gE * d of Ex, Ey (node level n), Ez (cell level n)
+    const int l = threadIdx.x, j = threadIdx.y;
+    const int i = (int)blockIdx.x * (TW - 2) - 1 + l;
+    const bool in = (i >= 0 && i < m.nx);
+    const bool edge_ok = in && l <= TW - 2;
+    const bool out_ok = in && l >= 1 && l <= TW - 2;
+    const bool has_ip = (i + 1 < m.nx);
+    const int sys = blockIdx.z;
+    x += (size_t)sys * m.nF;
+    y += (size_t)sys * m.nF;
+    axis += (size_t)sys * m.nz;
+    const T s = Sc<T>::from(s_d[2 * sys], s_d[2 * sys + 1]);
+    const T zero = Sc<T>::zero();
+    const int k0 = (int)blockIdx.y * ZC, k1 = min(m.nz, k0 + ZC);
+    const T* X = x; const T* Yf = x + m.nFx; const T* Z = x + m.nFx + m.nFy;
+    T* OX = y; T* OY = y + m.nFx; T* OZ = y + m.nFx + m.nFy;
+    const double* wxp_ = uF; const double* wyp_ = uF + m.nFx; const double* wzp_ = uF + m.nFx + m.nFy;
+    const double* gx = gE; const double* gy = gE + m.nEx; const double* gz = gE + m.nEx + m.nEy;
+    const long long col = (long long)(in ? i : 0) + (long long)m.nx * j;
+    const int me = j * TW + l, mjm = ((j == 0) ? nth - 1 : j - 1) * TW + l, mjp = ((j + 1 == nth) ? 0 : j + 1) * TW + l;
+    const double afz = in ? m.aFz(i, j) : 0.0;
+
+    // values of the level below (cell level n-1 / node level n-1)
+    T uxp = zero, uyp = zero, xxp = zero, xyp = zero, exq = zero, eyq = zero, ezq = zero, ezjp_q = zero, ezim_q = zero;
+    double wxq = 0.0, wyq = 0.0;
+    if (in && k0 > 0) {
+        const long long c = col + m.nxy * (long long)(k0 - 1);
+        uxp = wxp_[c] * X[c];
+        uyp = wyp_[c] * Yf[c];
+    }
+    // register prefetch of level n
+    T cxx = zero, cxy = zero, cxz = zero;
+    double cwx = 0.0, cwy = 0.0, cwz = 0.0, cgx = 0.0, cgy = 0.0, cgz = 0.0;
+    auto fetch = [&](int n, T& fx_, T& fy_, T& fz_, double& wx_, double& wy_, double& wz_, double& gx_, double& gy_, double& gz_) {
+        fx_ = zero; fy_ = zero; fz_ = zero; wx_ = wy_ = wz_ = gx_ = gy_ = gz_ = 0.0;
+        if (!in || n > k1) return;
+        const long long c = col + m.nxy * (long long)n;
+        fz_ = Z[c]; wz_ = wzp_[c]; gx_ = gx[c]; gy_ = gy[c];
+        if (n < m.nz) { fx_ = X[c]; fy_ = Yf[c]; wx_ = wxp_[c]; wy_ = wyp_[c]; gz_ = gz[(long long)n * m.ezp + 1 + col]; }
+    };
+    fetch(k0, cxx, cxy, cxz, cwx, cwy, cwz, cgx, cgy, cgz);
+    for (int n = k0; n <= k1; ++n) {
+        const bool cell = n < m.nz;
+        T nxx, nxy_, nxz; double nwx, nwy, nwz, ngx, ngy, ngz;
+        fetch(n + 1, nxx, nxy_, nxz, nwx, nwy, nwz, ngx, ngy, ngz);
+        const T ux = cwx * cxx, uy = cwy * cxy, uz = cwz * cxz;        // (zero above the top cell level / outside the mesh)
+        U[me] = ux; U[tsz + me] = uy; U[2 * tsz + me] = uz;
+        __syncthreads();
+        T ex = zero, ey = zero, ez = zero;
+        if (edge_ok) {
+            const T uz_ip = has_ip ? U[2 * tsz + me + 1] : zero;
+            ex = cgx * (uz - U[2 * tsz + mjm] - uy + uyp);
+            ey = cgy * (uz - uz_ip + ux - uxp);
+            if (cell) {
+                const T uy_ip = has_ip ? U[tsz + me + 1] : zero;
+                ez = cgz * (U[mjm] - ux - uy + uy_ip);
+            }
+        }
+        E[me] = ex; E[tsz + me] = ey; E[2 * tsz + me] = ez;
+        __syncthreads();
+        if (out_ok) {
+            const long long c = col + m.nxy * (long long)n;
+            if (n < k1 || n == m.nz) {
+                // Fz of node level n
+                T r3 = ey - E[mjp] + ex;
+                if (i > 0) r3 -= E[tsz + me - 1];
+                OZ[c] = cwz * r3 + s * ((cwz * afz) * cxz);
+            }
+            if (n > k0) {
+                // Fx, Fy of cell level n - 1
+                const long long cb = c - m.nxy;
+                const T r = eyq - ey + ezjp_q - ezq;
+                OX[cb] = wxq * r + s * ((wxq * m.aFx(i, j, n - 1)) * xxp);
+                const T r2 = ex - exq - ezq + ezim_q;
+                OY[cb] = wyq * r2 + s * ((wyq * m.aFy(i, n - 1)) * xyp);
+            }
+            if (cell) {
+                ezjp_q = E[2 * tsz + mjp];
+                ezim_q = (i > 0) ? E[2 * tsz + me - 1] : axis[n];
+            }
+        }
+        uxp = ux; uyp = uy; xxp = cxx; xyp = cxy; wxq = cwx; wyq = cwy; exq = ex; eyq = ey; ezq = ez;
+        cxx = nxx; cxy = nxy_; cxz = nxz; cwx = nwx; cwy = nwy; cwz = nwz; cgx = ngx; cgy = ngy; cgz = ngz;
+    }
+}
+
 // ework: nsys * nE elements of workspace, or nullptr for the single-pass kernel
 int launch_face_op(const MeshD& m, const double* uF, const double* gE, const double* s_d,
                    const void* x, void* y, int nsys, bool cplx_vec, void* ework, cudaStream_t st) {
     long long n = m.nxy * (m.nz + 1);
+    // large 3-D meshes whose theta ring fits one CTA: the single-pass ring kernel (CS_FACE_OP=twopass: the two-pass one)
+    static const bool twopass = [] { const char* e = getenv("CS_FACE_OP"); return e && !strcmp(e, "twopass"); }();
+    if (ework && !twopass && !m.sym && m.nth >= 4 && m.nth * 16 <= 512 && m.nz >= 32) {
+        constexpr int TW = 16;
+        static const int zc = [] { const char* e = getenv("CS_FACE_ZC"); int v = e ? atoi(e) : 16; return (v == 8 || v == 32) ? v : 16; }();
+        const size_t es = cplx_vec ? sizeof(cplx) : sizeof(double);
+        const size_t sm = (size_t)6 * m.nth * TW * es;
+        dim3 blk(TW, m.nth), grd((unsigned)((m.nx + TW - 3) / (TW - 2)), (unsigned)((m.nz + zc - 1) / zc), (unsigned)nsys), ga((unsigned)m.nz, (unsigned)nsys);
+        auto run = [&](auto kern_c, auto kern_d) -> int {
+            if (cplx_vec) {
+                CS_CUDA(cudaFuncSetAttribute(kern_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                k_face_axis<cplx><<<ga, 32, 0, st>>>(m, uF, gE, (const cplx*)x, (cplx*)ework);
+                kern_c<<<grd, blk, sm, st>>>(m, uF, gE, s_d, (const cplx*)x, (cplx*)y, (const cplx*)ework);
+            } else {
+                CS_CUDA(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                k_face_axis<double><<<ga, 32, 0, st>>>(m, uF, gE, (const double*)x, (double*)ework);
+                kern_d<<<grd, blk, sm, st>>>(m, uF, gE, s_d, (const double*)x, (double*)y, (const double*)ework);
+            }
+            return CS_OK;
+        };
+        if (zc == 8) CS_TRY(run(k_face_op_ring<cplx, 8, TW>, k_face_op_ring<double, 8, TW>));
+        else if (zc == 32) CS_TRY(run(k_face_op_ring<cplx, 32, TW>, k_face_op_ring<double, 32, TW>));
+        else CS_TRY(run(k_face_op_ring<cplx, 16, TW>, k_face_op_ring<double, 16, TW>));
+        CS_CUDA(cudaGetLastError());
+        return CS_OK;
+    }
     if (ework) {
         if (cplx_vec) {
             k_face_op_edges<cplx><<<grid1(n, nsys), TPB, 0, st>>>(m, uF, gE, (const cplx*)x, (cplx*)ework);
