@@ -122,6 +122,9 @@ struct cs_ctx {
     std::map<int, cs_op*> ops;
     std::vector<cs_op*> stale_ops;
     DevBuf work, scal, modes, tmp1, tmp2, ework, ddwork;
+    // probing only: the stencil apply is wanted for these theta columns alone (the response of a probe at column jprobe
+    // lives in jprobe - 1 .. jprobe + 1); 0 = all columns
+    int apply_jc0 = 0, apply_jcn = 0;
     Pool pool;
     std::vector<std::pair<std::vector<unsigned long long>, cudaGraphExec_t>> probe_graphs;
     double* pin = nullptr;         // pinned host scratch
@@ -249,7 +252,7 @@ static int op_apply_dev(cs_op* op, const double* s_d, const void* x, void* y, in
     if (op->is_csr) return launch_csr_spmv(op->n, op->csr_indptr, op->csr_indices, op->csr_vals, op->csr_cplx, x, y, nvec, cplx_vec, c->st);
     if (op->family == 0) return launch_dc_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st);
     if (op->family == 3) { g_launches += 2 * nvec - 1; return launch_node_apply(c->m, op->w1, op->shift0, x, y, nvec, cplx_vec, c->st); }
-    if (op->family == 1) return launch_edge_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st);
+    if (op->family == 1) return launch_edge_op(c->m, op->w1, op->w2, s_d, x, y, nvec, cplx_vec, c->st, c->apply_jc0, c->apply_jcn);
     // 3-D: the single-pass ring kernel (118 us on the 4.86 M-cell mesh; its axis sums use the workspace) or, for theta
     // rings wider than 32 cells, the two-pass operator through an edge workspace (220 us; the naive single pass
     // CS_FACE_OP=fused: 385 us).  2-D: single pass (6.5 vs 9.2 us at 152 k cells).
@@ -395,17 +398,20 @@ static int probe_plan_run(cs_op* op) {
         (unsigned long long)c->scal.p, (unsigned long long)bp.Kband, (unsigned long long)bp.map3d, (unsigned long long)bp.jstr,
         (unsigned long long)op->w1, (unsigned long long)op->w2, (unsigned long long)op->csr_vals, (unsigned long long)op->kind,
         (unsigned long long)bp.n2, (unsigned long long)bp.p, (unsigned long long)bp.nmodes, (unsigned long long)op->n,
-        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables, (unsigned long long)pb, (unsigned long long)bp.jprobe, (unsigned long long)bp.hs, c->mesh_gen};
+        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables, (unsigned long long)pb, (unsigned long long)bp.jprobe, (unsigned long long)bp.hs, c->mesh_gen, (unsigned long long)c->apply_jcn};
     g_launches += 4LL * ((ncol + pb - 1) / pb);
     for (auto& g : c->probe_graphs)
         if (g.first == key) { CS_CUDA(cudaGraphLaunch(g.second, c->st)); return CS_OK; }
     auto enqueue = [&]() -> int {
+        // the probing vectors are zeroed once; every batch sets its ones and takes them out again
+        CS_CUDA(cudaMemsetAsync(c->tmp1.p, 0, (size_t)pb * op->n * esz(cv), c->st));
         for (int col = 0; col < ncol; col += pb) {
             int nb = std::min(pb, ncol - col);
-            CS_TRY(band_probe_fill(bp, col, nb, c->tmp1.p, op->n, cv, c->st));
+            CS_TRY(band_probe_fill(bp, col, nb, c->tmp1.p, op->n, cv, c->st, 1));
             CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, nb, cv));
             CS_TRY(band_probe_gather(bp, c->tmp2.p, cv, c->modes.p, op->n, nb, c->st));
             CS_TRY(band_probe_store(bp, col, nb, c->modes.p, c->tmp2.p, cv, op->n, c->st));
+            CS_TRY(band_probe_fill(bp, col, nb, c->tmp1.p, op->n, cv, c->st, 2));
         }
         return CS_OK;
     };
@@ -426,7 +432,14 @@ static int probe_plan_run(cs_op* op) {
 }
 
 static int probe_plan(cs_op* op) {
-    CS_TRY(probe_plan_run(op));
+    {
+        cs_ctx* c = op->ctx;
+        static const bool thin_apply = [] { const char* e = getenv("CS_PROBE_THIN_APPLY"); return !(e && atoi(e) == 0); }();
+        if (thin_apply && op->bp.thin_probe && op->bp.nth >= 8) { c->apply_jc0 = op->bp.jprobe - 1; c->apply_jcn = 3; }
+        int rc = probe_plan_run(op);
+        c->apply_jc0 = 0; c->apply_jcn = 0;
+        CS_TRY(rc);
+    }
     // every operator of the path is symmetric (complex symmetric after the shift); an assembled CSR matrix may not be --
     // measured on the probed band, and only then does the step factorisation use the lower triangle alone
     double asym = 1.0;

@@ -290,21 +290,24 @@ int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d
 // three-term DFT holds column q of every mode matrix at once (cost independent of nth).
 template <typename TX>
 __global__ void k_probe_fill(const long long* __restrict__ map3d, const int* __restrict__ jstr, long long n2, int ncol, int color0,
-                             long long n3d, int jprobe, TX* __restrict__ x3d) {
-    // probing vector blockIdx.y carries colour color0 + blockIdx.y; the ones sit in theta column jprobe
+                             long long n3d, int jprobe, TX* __restrict__ x3d, int set) {
+    // probing vector blockIdx.y carries colour color0 + blockIdx.y; the ones sit in theta column jprobe (set = 0: take them out again)
     long long q = color0 + blockIdx.y + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * ncol;
     if (q >= n2) return;
     long long b = map3d[q];
-    if (b >= 0) x3d[(size_t)blockIdx.y * n3d + b + (long long)jprobe * jstr[q]] = Sc<TX>::one();
+    if (b >= 0) x3d[(size_t)blockIdx.y * n3d + b + (long long)jprobe * jstr[q]] = set ? Sc<TX>::one() : Sc<TX>::zero();
 }
 // nb probing vectors (colours color .. color + nb - 1) at once
-int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d, long long n3d, bool x_cplx, cudaStream_t st) {
+// mode 0: zero the vectors and set the ones (self-contained); 1: set the ones of these colours in vectors that are all zero;
+// 2: take them out again (a full-vector memset per colour is 117 MB at 4.86 M cells)
+int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d, long long n3d, bool x_cplx, cudaStream_t st, int mode) {
     int ncol = 2 * bp.p + 1;
-    CS_CUDA(cudaMemsetAsync(x3d, 0, (size_t)nb * n3d * (x_cplx ? sizeof(cplx) : sizeof(double)), st));
+    if (mode == 0) CS_CUDA(cudaMemsetAsync(x3d, 0, (size_t)nb * n3d * (x_cplx ? sizeof(cplx) : sizeof(double)), st));
     long long cnt = (bp.n2 + ncol - 1) / ncol;
     dim3 g((unsigned)cdiv(cnt, TPB), nb);
-    if (x_cplx) k_probe_fill<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, ncol, color, n3d, bp.jprobe, (cplx*)x3d);
-    else k_probe_fill<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, ncol, color, n3d, bp.jprobe, (double*)x3d);
+    const int set = mode == 2 ? 0 : 1;
+    if (x_cplx) k_probe_fill<cplx><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, ncol, color, n3d, bp.jprobe, (cplx*)x3d, set);
+    else k_probe_fill<double><<<g, TPB, 0, st>>>(bp.map3d, bp.jstr, bp.n2, ncol, color, n3d, bp.jprobe, (double*)x3d, set);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

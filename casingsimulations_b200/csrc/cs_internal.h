@@ -32,7 +32,7 @@ int launch_node_apply(const MeshD& m, const double* w, double shift0, const void
 int launch_ave_ccv(const MeshD& m, bool from_faces, const void* x, void* y, bool cplx_vec, cudaStream_t st);
 // K4 edge form: y = C^T diag(alpha) C x + s[sys] * beta .* x, wF = alpha/area^2
 int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const double* s_d /*2 doubles per sys*/,
-                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st);
+                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st, int jc0 = 0, int jcn = 0 /*theta columns wanted; 0 = all*/);
 // K4 face form: y = alpha .* (C diag(gamma) C^T (alpha .* x) + s[sys] x), uF = alpha/area, gE = len^2 gamma
 int launch_face_op(const MeshD& m, const double* uF, const double* gE, const double* s_d,
                    const void* x, void* y, int nsys, bool cplx_vec, void* ework /*nsys*nE workspace or nullptr*/, cudaStream_t st);
@@ -120,7 +120,7 @@ int band_factor_launches(const BandPlan& bp, bool lu_cplx);
 // theta-DFT into the rotated mode basis x''_m = T_m^* x_m; xm [nvec][nmv][n2]
 int band_dft_gather(const BandPlan& bp, const void* x3d, bool x_cplx, void* xm, bool xm_cplx, long long n3d, int nvec, cudaStream_t st);
 int band_dft_scatter(const BandPlan& bp, const void* xm, bool xm_cplx, void* x3d, bool x_cplx, long long n3d, int nvec, cudaStream_t st);
-int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]*/, long long n3d, bool x_cplx, cudaStream_t st);
+int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]*/, long long n3d, bool x_cplx, cudaStream_t st, int mode = 0);
 // modes 0 .. nmodes-1 of the probing responses y3d [nb][n3d] (nonzero in theta columns jprobe-1 .. jprobe+1 only)
 // -> ym complex [nb][nmodes][n2], then column `color + b` of every mode matrix
 int band_probe_gather(const BandPlan& bp, const void* y3d, bool y_cplx, void* ym, long long n3d, int nb, cudaStream_t st);

@@ -549,7 +549,8 @@ static const int EDGE_NS = 4;             // ring slots
 template <typename T, bool SYM, int TI>
 __global__ void __launch_bounds__(TI * 5, (TI <= 64 ? 2 : 1))
 k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ beta,
-          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y, int tj, int nchunk, int kz, int istride) {
+          const double* __restrict__ s_d, const T* __restrict__ x, T* __restrict__ y, int tj, int nchunk, int kz, int istride,
+          int jtile0, int jtiles) {
     constexpr int TW = TI + 1;                         // staged tile width: lanes i0-1 .. i0+TI-1
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int rows = blockDim.y;                       // face rows: (halo j0-1) + tj   [SYM: 1]
@@ -563,7 +564,7 @@ k_edge_op(MeshD m, const double* __restrict__ wF, const double* __restrict__ bet
     const int i0 = blockIdx.x * istride;
     const int i = i0 + li;
     const int sys = blockIdx.z / nchunk, chunk = blockIdx.z % nchunk;
-    const int j0 = blockIdx.y * tj;
+    const int j0 = (((int)blockIdx.y + jtile0) % jtiles) * tj;      // (probing: only the theta tiles that carry the response)
     const int jraw = SYM ? 0 : j0 + row - 1;
     const bool valid = (i < m.nx) && (SYM || jraw < m.nth);
     const int j = SYM ? 0 : (jraw < 0 ? m.nth - 1 : (jraw >= m.nth ? 0 : jraw));
@@ -746,7 +747,7 @@ __global__ void k_edge_op_axis(MeshD m, const double* __restrict__ wF, const dou
 
 template <typename T, bool SYM, int TI>
 static int launch_edge_op_cfg(const MeshD& m, const double* wF, const double* beta, const double* s_d,
-                              const T* x, T* y, int nsys, cudaStream_t st) {
+                              const T* x, T* y, int nsys, cudaStream_t st, int jc0 = 0, int jcn = 0) {
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
     int nlev = m.nz + 1;
@@ -754,10 +755,17 @@ static int launch_edge_op_cfg(const MeshD& m, const double* wF, const double* be
     int istride = (itiles == 1) ? TI : TI - 1;
     int tj = SYM ? 1 : (m.nth < 4 ? m.nth : 4);
     int jtiles = SYM ? 1 : (m.nth + tj - 1) / tj;
+    // outputs wanted for the theta columns jc0 .. jc0 + jcn - 1 only (jcn <= 0: all): launch the tiles that hold them
+    int jt0 = 0, jtn = jtiles;
+    if (!SYM && jcn > 0 && jcn < m.nth) {
+        int a = ((jc0 % m.nth) + m.nth) % m.nth;
+        jt0 = a / tj;
+        jtn = std::min(jtiles, (a + jcn - 1) / tj - jt0 + 1);
+    }
     // z chunks: ~2 waves of resident CTAs when the mesh is large enough, at least ~16 levels
     // per chunk so the extra priming level stays cheap
     int resident = (TI <= 64) ? 2 : 1;
-    long long plane_ctas = (long long)itiles * jtiles * nsys;
+    long long plane_ctas = (long long)itiles * jtn * nsys;
     int nchunk = (int)((2LL * nsm * resident + plane_ctas - 1) / plane_ctas);
     int maxchunk = (nlev + 15) / 16;
     if (nchunk > maxchunk) nchunk = maxchunk;
@@ -768,7 +776,7 @@ static int launch_edge_op_cfg(const MeshD& m, const double* wF, const double* be
     int trows = SYM ? 1 : rows + 1, ncomp = SYM ? 1 : 3;
     size_t smb = ((size_t)EDGE_NS * ncomp * trows * (TI + 1) + 2 * 3 * (size_t)rows * TI) * sizeof(T);
     CS_CHECK(trows * (TI + 1) <= 2 * TI * rows, "staging descriptor count too small");
-    dim3 blk(TI, rows), grd(itiles, jtiles, nchunk * nsys);
+    dim3 blk(TI, rows), grd(itiles, jtn, nchunk * nsys);
     // the attribute is per device and not capturable into a CUDA graph: set it once per (instantiation, device)
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -778,17 +786,17 @@ static int launch_edge_op_cfg(const MeshD& m, const double* wF, const double* be
         CS_CUDA(cudaFuncSetAttribute(k_edge_op<T, SYM, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
         if (dev < 64) attr_set[dev] = true;
     }
-    k_edge_op<T, SYM, TI><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, tj, nchunk, kz, istride);
+    k_edge_op<T, SYM, TI><<<grd, blk, smb, st>>>(m, wF, beta, s_d, x, y, tj, nchunk, kz, istride, jt0, jtiles);
     return CS_OK;
 }
 
 template <typename T>
 static int launch_edge_op_t(const MeshD& m, const double* wF, const double* beta, const double* s_d,
-                            const T* x, T* y, int nsys, cudaStream_t st) {
+                            const T* x, T* y, int nsys, cudaStream_t st, int jc0, int jcn) {
     if (m.sym) {
         CS_TRY((launch_edge_op_cfg<T, true, 128>(m, wF, beta, s_d, x, y, nsys, st)));
     } else {
-        CS_TRY((launch_edge_op_cfg<T, false, 64>(m, wF, beta, s_d, x, y, nsys, st)));
+        CS_TRY((launch_edge_op_cfg<T, false, 64>(m, wF, beta, s_d, x, y, nsys, st, jc0, jcn)));
         dim3 ga((m.nz + 7) / 8, nsys);
         k_edge_op_axis<T><<<ga, 256, 0, st>>>(m, wF, beta, s_d, x, y);
     }
@@ -797,9 +805,9 @@ static int launch_edge_op_t(const MeshD& m, const double* wF, const double* beta
 }
 
 int launch_edge_op(const MeshD& m, const double* wF, const double* beta, const double* s_d,
-                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st) {
-    if (cplx_vec) return launch_edge_op_t<cplx>(m, wF, beta, s_d, (const cplx*)x, (cplx*)y, nsys, st);
-    return launch_edge_op_t<double>(m, wF, beta, s_d, (const double*)x, (double*)y, nsys, st);
+                   const void* x, void* y, int nsys, bool cplx_vec, cudaStream_t st, int jc0, int jcn) {
+    if (cplx_vec) return launch_edge_op_t<cplx>(m, wF, beta, s_d, (const cplx*)x, (cplx*)y, nsys, st, jc0, jcn);
+    return launch_edge_op_t<double>(m, wF, beta, s_d, (const double*)x, (double*)y, nsys, st, jc0, jcn);
 }
 
 // ============================ K4': fused face-form operator ======================
