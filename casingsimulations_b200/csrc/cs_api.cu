@@ -343,7 +343,8 @@ static int build_plan(cs_op* op) {
     bp.jprobe = 0;
     if (nth > 1) {
         double mean = 2.0 * M_PI / nth, best = 1e300;
-        for (int j = 0; j < nth; ++j) {
+        for (int jj = 0; jj < nth; ++jj) {
+            const int j = (jj + 1) % nth;      // ties (uniform widths) go to column 1: columns 0 .. 2 then sit in ONE theta tile of the stencil kernel
             double dev = std::fabs(c->hth[j] - mean) + 0.5 * std::fabs(c->hth[(j + nth - 1) % nth] - mean);   // own width + the neighbour it couples to
             if (dev < best - 1e-14 * mean) { best = dev; bp.jprobe = j; }
         }
@@ -391,6 +392,9 @@ static int probe_plan_run(cs_op* op) {
     CS_TRY(c->modes.ensure((size_t)pb * bp.nmodes * bp.n2 * sizeof(cplx)));
     CS_TRY(c->scal.ensure(4096));
     CS_CUDA(cudaMemsetAsync(c->scal.p, 0, 4096, c->st));     // shift 0 for every probing vector
+    // thin probing: gather + store fused into one kernel, no mode vectors (CS_PROBE_FUSED=0: the two-kernel path)
+    static const bool fused_env = [] { const char* e = getenv("CS_PROBE_FUSED"); return !(e && atoi(e) == 0); }();
+    const bool fused_thin = fused_env && bp.thin_probe && bp.nth >= 3;
     // ~4 * (2p+1) tiny launches: replay them as one cached CUDA graph (keyed by every pointer
     // and size baked into the launches) so that host jitter cannot stretch the assembly
     CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, pb, cv));     // warm-up, sizes c->ework
@@ -398,7 +402,7 @@ static int probe_plan_run(cs_op* op) {
         (unsigned long long)c->scal.p, (unsigned long long)bp.Kband, (unsigned long long)bp.map3d, (unsigned long long)bp.jstr,
         (unsigned long long)op->w1, (unsigned long long)op->w2, (unsigned long long)op->csr_vals, (unsigned long long)op->kind,
         (unsigned long long)bp.n2, (unsigned long long)bp.p, (unsigned long long)bp.nmodes, (unsigned long long)op->n,
-        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables, (unsigned long long)pb, (unsigned long long)bp.jprobe, (unsigned long long)bp.hs, c->mesh_gen, (unsigned long long)c->apply_jcn};
+        (unsigned long long)c->m.nx, (unsigned long long)c->m.nth, (unsigned long long)c->m.nz, (unsigned long long)c->tables, (unsigned long long)pb, (unsigned long long)bp.jprobe, (unsigned long long)bp.hs, c->mesh_gen, (unsigned long long)c->apply_jcn, (unsigned long long)fused_thin};
     g_launches += 4LL * ((ncol + pb - 1) / pb);
     for (auto& g : c->probe_graphs)
         if (g.first == key) { CS_CUDA(cudaGraphLaunch(g.second, c->st)); return CS_OK; }
@@ -409,8 +413,11 @@ static int probe_plan_run(cs_op* op) {
             int nb = std::min(pb, ncol - col);
             CS_TRY(band_probe_fill(bp, col, nb, c->tmp1.p, op->n, cv, c->st, 1));
             CS_TRY(op_apply_dev(op, (const double*)c->scal.p, c->tmp1.p, c->tmp2.p, nb, cv));
-            CS_TRY(band_probe_gather(bp, c->tmp2.p, cv, c->modes.p, op->n, nb, c->st));
-            CS_TRY(band_probe_store(bp, col, nb, c->modes.p, c->tmp2.p, cv, op->n, c->st));
+            if (fused_thin) CS_TRY(band_probe_store_thin(bp, col, nb, c->tmp2.p, cv, op->n, c->st));
+            else {
+                CS_TRY(band_probe_gather(bp, c->tmp2.p, cv, c->modes.p, op->n, nb, c->st));
+                CS_TRY(band_probe_store(bp, col, nb, c->modes.p, c->tmp2.p, cv, op->n, c->st));
+            }
             CS_TRY(band_probe_fill(bp, col, nb, c->tmp1.p, op->n, cv, c->st, 2));
         }
         return CS_OK;

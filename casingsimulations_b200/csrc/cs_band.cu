@@ -373,6 +373,87 @@ __global__ void k_probe_store(const long long* __restrict__ map3d, const int* __
     }
     K[(size_t)m * n2 * ldab + (size_t)(pw + r - q) + (size_t)q * ldab] = from_c<TB>(val);
 }
+// Thin probing, gather and store in one kernel: the response to a probe in theta column jprobe lives in the columns
+// jprobe - 1 .. jprobe + 1, so entry [r, q] of every mode matrix is a 3-term sum that is formed right here from the 3-D
+// response -- the mode vectors (17 x n2 complex numbers per probing vector: 124 MB written and read back at 4.86 M cells)
+// never exist.  One thread per band row r, all stored modes; writes run down column q of the band (coalesced).
+template <typename TB, typename TX>
+__global__ void __launch_bounds__(128)
+k_probe_store_thin(const long long* __restrict__ map3d, const int* __restrict__ jstr, const signed char* __restrict__ hs,
+                   long long n2, int p, int pw, int ldab, int color0, int nmodes, int nth, int jprobe,
+                   const TX* __restrict__ y3d, long long n3d, TB* __restrict__ K) {
+    extern __shared__ __align__(16) unsigned char pst_sm[];
+    cplx* tw = reinterpret_cast<cplx*>(pst_sm);        // [2 nth]: exp(-i pi t / nth)
+    const int n2t = 2 * nth;
+    for (int t = threadIdx.x; t < n2t; t += blockDim.x) {
+        double sn, cs_;
+        sincospi(-(double)t / (double)nth, &sn, &cs_);
+        tw[t] = mk(cs_, sn);
+    }
+    __syncthreads();
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int color = color0 + blockIdx.y;
+    y3d += (size_t)blockIdx.y * n3d;
+    if (r >= n2) return;
+    const long long b = map3d[r];
+    if (b < 0) return;
+    const int ncol = 2 * p + 1;
+    const long long lo = r - p;
+    const long long off = ((color - lo) % ncol + ncol) % ncol;
+    const long long q = lo + off;
+    if (q < 0 || q >= n2) return;
+    if (map3d[q] < 0) return;
+    const int st = jstr[r], stq = jstr[q], h2 = hs[r], hq = hs[q];
+    const double rt = sqrt((double)nth);
+    TB* Kc = K + (size_t)(pw + r - q) + (size_t)q * ldab;
+    const size_t nel = (size_t)n2 * ldab;
+    if (st == 0) {
+        // axis row (mode 0 only), carried as sqrt(nth) x: scaled row; an axis column gives the unscaled entry back
+        cplx val = rt * to_c(y3d[b]);
+        if (stq == 0) val = (1.0 / rt) * val;
+        if (hq != 0) val = mk(-val.y, val.x);          // T_0[q] = i for a staggered column
+        Kc[0] = from_c<TB>(val);
+        return;
+    }
+    cplx x0, x1, x2;
+    {
+        int c0 = (jprobe - 1 + nth) % nth, c2 = (jprobe + 1) % nth;
+        x0 = to_c(y3d[b + (long long)c0 * st]); x1 = to_c(y3d[b + (long long)jprobe * st]); x2 = to_c(y3d[b + (long long)c2 * st]);
+    }
+    if (stq == 0) {
+        // column of the shared axis unknown (mode 0 only): sqrt(nth) times the single-column response
+        cplx val = rt * x1;
+        if (h2 != 0) val = mk(val.y, -val.x);
+        Kc[0] = from_c<TB>(val);
+        return;
+    }
+    for (int m = 0; m < nmodes; ++m) {
+        // sum_p x_p exp(-i pi m (2 p + hs_r) / nth), p = -1, 0, 1;  times conj(T_m[r]) = -i for a staggered row
+        int idx = ((m * (h2 - 2)) % n2t + n2t) % n2t;
+        const int stp = (2 * m) % n2t;
+        cplx acc = mk(0.0, 0.0);
+        fmacc(acc, x0, tw[idx]); idx += stp; if (idx >= n2t) idx -= n2t;
+        fmacc(acc, x1, tw[idx]); idx += stp; if (idx >= n2t) idx -= n2t;
+        fmacc(acc, x2, tw[idx]);
+        if (h2 != 0) acc = mk(acc.y, -acc.x);
+        if (hq != 0) {
+            // T_m[q] = i exp(i hq pi m / nth) = i conj(tw[hq m])
+            const cplx e = tw[((hq * m) % n2t + n2t) % n2t];
+            acc = acc * mk(e.y, e.x);                  // i * conj(e) = i (e.x - i e.y) = e.y + i e.x
+        }
+        Kc[(size_t)m * nel] = from_c<TB>(acc);
+    }
+}
+int band_probe_store_thin(const BandPlan& bp, int color, int nb, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st) {
+    CS_CHECK(bp.cplx_band == y_cplx, "probing vectors must have the scalar type of the band storage");
+    CS_CHECK(bp.nth >= 3 && bp.thin_probe, "thin probing needs a three-column response");
+    dim3 g((unsigned)cdiv(bp.n2, 128), nb);
+    const size_t sm = (size_t)2 * bp.nth * sizeof(cplx);
+    if (bp.cplx_band) k_probe_store_thin<cplx, cplx><<<g, 128, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, bp.nth, bp.jprobe, (const cplx*)y3d, n3d, (cplx*)bp.Kband);
+    else k_probe_store_thin<double, double><<<g, 128, sm, st>>>(bp.map3d, bp.jstr, bp.hs, bp.n2, bp.p, bp.pw, bp.ldab, color, bp.nmodes, bp.nth, bp.jprobe, (const double*)y3d, n3d, (double*)bp.Kband);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
 int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st) {
     dim3 g((unsigned)cdiv(bp.n2, TPB), bp.nmodes, nb);
     CS_CHECK(bp.cplx_band == y_cplx, "probing vectors must have the scalar type of the band storage");

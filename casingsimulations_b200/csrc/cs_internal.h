@@ -124,6 +124,7 @@ int band_probe_fill(const BandPlan& bp, int color, int nb, void* x3d /*[nb][n3d]
 // modes 0 .. nmodes-1 of the probing responses y3d [nb][n3d] (nonzero in theta columns jprobe-1 .. jprobe+1 only)
 // -> ym complex [nb][nmodes][n2], then column `color + b` of every mode matrix
 int band_probe_gather(const BandPlan& bp, const void* y3d, bool y_cplx, void* ym, long long n3d, int nb, cudaStream_t st);
+int band_probe_store_thin(const BandPlan& bp, int color, int nb, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st);
 int band_probe_store(const BandPlan& bp, int color, int nb, const void* ym, const void* y3d, bool y_cplx, long long n3d, cudaStream_t st);
 // w[f][3-D index] = 1 / |diag(A(s_f))| recovered from the mode matrices (mean over modes of K_m[q,q]) + s_f * mass
 int band_check_symmetric(const BandPlan& bp, int stride, double* asym_rel /*host*/, cudaStream_t st);
