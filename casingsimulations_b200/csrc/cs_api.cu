@@ -355,6 +355,7 @@ static int build_plan(cs_op* op) {
     bp.ldab = 2 * bp.pw + 1;
     bp.nth = nth;
     bp.thin_probe = (op->family != 2);
+    band_plan_twist(bp);
     bp.nmodes = (nth > 1) ? nth / 2 + 1 : 1;          // modes m and nth - m share one (rotated, real) matrix
     bp.cplx_band = op->csr_cplx;                      // the rotated mode matrices of a real operator are real
     hsv.resize(bp.n2, 0);
@@ -607,7 +608,7 @@ extern "C" int cs_op_factor(cs_op* op, const double* shifts_h, int nshift, int c
     // but the substitution kernel stages complex factors with a TMA producer warp) -- A/B switch, see DESIGN.md
     static const bool real_lu = [] { const char* e = getenv("CS_REAL_LU"); return !(e && atoi(e) == 0); }();
     if (!real_lu && bp.nth > 1) lc = true;
-    size_t need = (size_t)nshift * bp.nmodes * bp.band_elems() * esz(lc);
+    size_t need = (size_t)nshift * bp.nmodes * bp.lu_elems_per_system() * esz(lc);
     if (!c->dist.on) CS_TRY(op->LU.ensure(need));
     op->lu_cplx = lc;
     op->shifts.resize(nshift);
@@ -724,6 +725,7 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     const long long L = bl.Lrow;
     op->Lrow = L;
     bg = bl;
+    bg.twist = false;                             // (the mode-sharded global factors keep the one-front elimination)
     bg.n2 = L * (d.g.gnz + 1);
     const long long n2g_true = bg.n2;             // without the padding dummy
     if (bl.tma_real && (bg.n2 & 1)) bg.n2 += 1;
@@ -1615,7 +1617,7 @@ extern "C" int cs_solve_fdem(cs_ctx* c, int form, const double* freqs_h, int nfr
     long long n = op->n;
     // how many frequencies fit at once (driver queries only when the cached buffers are too small:
     // cudaMemGetInfo / cudaMalloc / cudaFree serialise against concurrent nvidia-smi polling)
-    size_t per = (size_t)op->bp.nmodes * op->bp.band_elems() * sizeof(cplx);
+    size_t per = (size_t)op->bp.nmodes * op->bp.lu_elems_per_system() * sizeof(cplx);
     size_t vecs = (size_t)(8 + 2) * n * sizeof(cplx) + (size_t)op->bp.nth * op->bp.n2 * sizeof(cplx);
     long long chunk = std::min(nfreq, 256);
     if (c->dist.on) chunk = 1;                 // slab mode: one frequency at a time (the factors of a rank's modes fill its memory)

@@ -1159,8 +1159,13 @@ static unsigned long long g_stamp = 0;
 // latency-bound panel of step t+1 runs concurrently with the throughput-bound bulk update of step t.
 template <typename T, int NB>
 static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, cudaStream_t st, cudaStream_t stB = nullptr,
-                               cudaEvent_t evP = nullptr, cudaEvent_t evU = nullptr, int* cnt = nullptr) {
-    size_t nel = bp.band_elems();
+                               cudaEvent_t evP = nullptr, cudaEvent_t evU = nullptr, int* cnt = nullptr,
+                               long long t_begin = 0, long long t_end = -1, size_t stride = 0, long long invert_n2 = -1) {
+    // t_begin / t_end: block steps [t_begin, t_end) only (both multiples of NB or the end); stride: elements between
+    // consecutive systems (0: band_elems()); invert_n2: k_invert_diag on the diagonal blocks below this row (-1: all, 0: none)
+    if (t_end < 0) t_end = bp.n2;
+    if (invert_n2 < 0) invert_n2 = bp.n2;
+    size_t nel = stride ? stride : bp.band_elems();
     int ld = bp.ldab - 1;
     static const int tile_env = [] { const char* e = getenv("CS_LU_TILE"); return e ? atoi(e) : 0; }();
     const bool big = tile_env == 64 && NB == 16;      // opt-in: measured identical (273 ms vs 273 ms on 109x32x460), see below
@@ -1179,7 +1184,7 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     // MEASURED (109x32x460, 17 systems): 356 ms (443 ms at 3 CTAs/SM) vs 273 ms for the two-kernel schedule -- the one-CTA
     // panel tail of the last system is exposed and the lower occupancy slows the tiles; opt-in only (CS_LU_FUSED=1)
     static const bool fused_on = [] { const char* e = getenv("CS_LU_FUSED"); return e && atoi(e) == 1; }();
-    if (fused_on && !la && !big && !sym && NB == 16 && tiles >= 2 && skip == 0 && cnt) {
+    if (fused_on && !la && !big && !sym && NB == 16 && tiles >= 2 && skip == 0 && cnt && t_begin == 0 && t_end == bp.n2 && invert_n2 == bp.n2) {
         // one launch per block step: update of step t + panel of step t+1 (k_lu_update_fused); the first panel stands alone
         if (cudaMemsetAsync(cnt, 0, (size_t)nsys * sizeof(int), st) != cudaSuccess) return CS_ERR;
         dim3 gp(chunks, nsys);
@@ -1194,14 +1199,14 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
         return CS_OK;
     }
     bool have_u2 = false;
-    for (long long t = 0; t < bp.n2; t += NB) {
+    for (long long t = t_begin; t < t_end; t += NB) {
         dim3 gp(chunks, nsys);
         if (skip != 1) {
-            if (NB == 16 && dahead && t > 0 && panel4) {
+            if (NB == 16 && dahead && t > t_begin && panel4) {
                 const int ch4 = (bp.p + 63) / 64;
                 dim3 g4(sym ? ch4 : 2 * ch4, nsys);
                 k_lu_panel4<T><<<g4, 256, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, (const T*)scratch, sym ? 1 : 0, ch4);
-            } else k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, sym ? 1 : 0, (dahead && t > 0) ? 1 : 0);
+            } else k_lu_panel<T, NB><<<gp, 160, 0, st>>>(LU, nel, bp.n2, bp.p, bp.pw, ld, t, scratch, sym ? 1 : 0, (dahead && t > t_begin) ? 1 : 0);
         }
         if (skip == 2) continue;
         if (sym) {
@@ -1229,13 +1234,99 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
     }
     if (la && have_u2 && cudaStreamWaitEvent(st, evU, 0) != cudaSuccess) return CS_ERR;      // join
     // diagonal blocks in the format of the substitution kernel (ITS block size, which may be smaller than the steps')
-    if (bp.nb == 16) {
-        dim3 gi((unsigned)((bp.n2 + 15) / 16), nsys);
-        k_invert_diag<T, 16><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
-    } else {
-        dim3 gi((unsigned)((bp.n2 + NB - 1) / NB), nsys);
-        k_invert_diag<T, NB><<<gi, 32, 0, st>>>(LU, nel, bp.n2, bp.pw, ld);
+    if (invert_n2 > 0) {
+        if (bp.nb == 16) {
+            dim3 gi((unsigned)((invert_n2 + 15) / 16), nsys);
+            k_invert_diag<T, 16><<<gi, 32, 0, st>>>(LU, nel, invert_n2, bp.pw, ld);
+        } else {
+            dim3 gi((unsigned)((invert_n2 + NB - 1) / NB), nsys);
+            k_invert_diag<T, NB><<<gi, 32, 0, st>>>(LU, nel, invert_n2, bp.pw, ld);
+        }
     }
+    return CS_OK;
+}
+
+// ---- two-front ("twisted") elimination (BandPlan::twist) ----
+// original index of entry i of half system `half` (-1: identity dummy)
+__device__ __forceinline__ long long tw_orig(int half, long long i, long long n2, long long padT, long long padB) {
+    if (half == 0) return i < padT ? -1 : i - padT;
+    return i < padB ? -1 : n2 - 1 - (i - padB);
+}
+// LU2[f][m][half] = twisted halves of K[m] + s[f] diag(mdiag)  (see BandPlan::twist; the separator block goes to T, B's is zero)
+template <typename TB, typename TL>
+__global__ void k_form_twisted(const long long* __restrict__ map3d, const int* __restrict__ jstr, const double* __restrict__ mdiag,
+                               long long n2, int pw, int ldab, int nmodes, long long n2h, long long nt, long long w, long long padT, long long padB,
+                               const TB* __restrict__ K, const double* __restrict__ s_d, TL* __restrict__ LU) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nelh = n2h * (long long)ldab;
+    if (e >= nelh) return;
+    const int m = blockIdx.y >> 1, half = blockIdx.y & 1, f = blockIdx.z;
+    const long long q = e / ldab;
+    const int d = (int)(e - q * ldab);
+    const long long i = q + d - pw;
+    TL v = Sc<TL>::zero();
+    const long long oq = tw_orig(half, q, n2, padT, padB);
+    if (oq < 0) { if (d == pw) v = Sc<TL>::one(); }
+    else if (i >= 0 && i < n2h) {
+        const long long oi = tw_orig(half, i, n2, padT, padB);
+        const bool sq = oq >= nt && oq < nt + w, si = oi >= nt && oi < nt + w;
+        if (oi >= 0 && !(half == 1 && sq && si)) {
+            const TB kv = K[(size_t)m * ((size_t)n2 * ldab) + (size_t)(pw + oi - oq) + (size_t)oq * ldab];
+            v = Sc<TL>::from(Sc<TB>::re(kv), Sc<TB>::im(kv));
+            if (oi == oq) {
+                const bool dummy = (map3d[oq] < 0) || (jstr[oq] == 0 && m > 0);
+                if (dummy) v = Sc<TL>::one();
+                else v = v + Sc<TL>::from(s_d[2 * f], s_d[2 * f + 1]) * Sc<TL>::from(mdiag[oq], 0.0);
+            }
+        }
+    }
+    LU[(((size_t)f * nmodes + m) * 2 + half) * (size_t)nelh + e] = v;
+}
+int band_form_twisted(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st) {
+    const long long nelh = (long long)bp.band_elems_h();
+    dim3 g((unsigned)cdiv(nelh, 256), 2 * bp.nmodes, nshift);
+#define CS_FORM_TW(TB, TL) k_form_twisted<TB, TL><<<g, 256, 0, st>>>(bp.map3d, bp.jstr, bp.mdiag, bp.n2, bp.pw, bp.ldab, bp.nmodes, bp.tw_n2h, bp.tw_nt, bp.tw_w, \
+                                                                    bp.tw_padT, bp.tw_padB, (const TB*)bp.Kband, s_d, (TL*)LU)
+    if (bp.cplx_band) { CS_CHECK(lu_cplx, "complex band needs complex LU"); CS_FORM_TW(cplx, cplx); }
+    else if (lu_cplx) CS_FORM_TW(double, cplx);
+    else CS_FORM_TW(double, double);
+#undef CS_FORM_TW
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+// separator block of T += the Schur complement the bottom front left in B's separator block (reversed ordering).  Symmetric
+// step LU: only the lower triangles (and the diagonal tiles) of the trailing blocks are up to date -- read B through its
+// lower triangle and write both triangles of T.
+template <typename T>
+__global__ void k_twist_combine(T* __restrict__ LU, size_t nelh, long long M, long long w, int pw, int ld, int sym) {
+    T* AT = LU + (size_t)blockIdx.y * 2 * nelh + pw;
+    const T* AB = AT + nelh;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= w * w) return;
+    const long long i = e % w, j = e / w;
+    if (sym && i < j) return;
+    // B(M + w-1-i, M + w-1-j); symmetric: for i > j that is an upper entry of B -- take its mirror image
+    long long bi = M + w - 1 - i, bj = M + w - 1 - j;
+    if (sym && bi < bj) { long long t = bi; bi = bj; bj = t; }
+    const T val = AT[(M + i) + (M + j) * (long long)ld] + AB[bi + bj * (long long)ld];
+    AT[(M + i) + (M + j) * (long long)ld] = val;
+    if (sym && i != j) AT[(M + j) + (M + i) * (long long)ld] = val;
+}
+template <typename T, int NB>
+static int band_factor_twisted_enqueue(const BandPlan& bp, T* LU2, int nsys, T* scratch, cudaStream_t st) {
+    BandPlan bh = bp;
+    bh.n2 = bp.tw_n2h;
+    const size_t nelh = bp.band_elems_h();
+    const int ld = bp.ldab - 1;
+    static const bool sym_env = [] { const char* e = getenv("CS_LU_SYM"); return !(e && atoi(e) == 0); }();
+    // both fronts of every system: 2 nsys half systems, block steps [0, M)
+    CS_TRY((band_factor_enqueue<T, NB>(bh, LU2, 2 * nsys, scratch, st, nullptr, nullptr, nullptr, nullptr, 0, bp.tw_M, 0, 0)));
+    dim3 gc((unsigned)cdiv(bp.tw_w * bp.tw_w, 256), nsys);
+    k_twist_combine<T><<<gc, 256, 0, st>>>(LU2, nelh, bp.tw_M, bp.tw_w, bp.pw, ld, (bp.sym && sym_env) ? 1 : 0);
+    // the separator: the remaining steps of the T halves alone (stride of two half systems), then the diagonal blocks of T
+    CS_TRY((band_factor_enqueue<T, NB>(bh, LU2, nsys, scratch, st, nullptr, nullptr, nullptr, nullptr, bp.tw_M, bp.tw_n2h, 2 * nelh, bp.tw_n2h)));
+    // diagonal blocks of the eliminated part of the B halves (their separator block is never factored)
+    CS_TRY((band_factor_enqueue<T, NB>(bh, LU2 + nelh, nsys, scratch, st, nullptr, nullptr, nullptr, nullptr, 0, 0, 2 * nelh, bp.tw_M)));
     return CS_OK;
 }
 
@@ -1244,7 +1335,8 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_CHECK(bp.nbf == NB, "band plan step size must equal the instantiated NB");
     std::lock_guard<std::mutex> lock(g_band_mu);
     void* scratch = nullptr;
-    CS_TRY(band_scratch(0, st, (size_t)nsys * NB * NB * sizeof(T), false, &scratch));
+    const int tw = bp.twist ? 2 : 1;                  // twisted: two half systems per system
+    CS_TRY(band_scratch(0, st, (size_t)tw * nsys * NB * NB * sizeof(T), false, &scratch));
     void* cntv = nullptr;
     CS_TRY(band_scratch(2, st, (size_t)nsys * sizeof(int), true, &cntv));
     int* cnt = (int*)cntv;
@@ -1259,7 +1351,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     { const char* e = getenv("CS_LU_DAHEAD"); if (e && atoi(e) == 0) groups_key += 25; }
     { const char* e = getenv("CS_LU_PANEL4"); if (e && atoi(e) == 0) groups_key += 12; }
     { const char* e = getenv("CS_LU_NBF"); if (e) groups_key += 6; }
-    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 1000 * groups_key, dev_key};
+    FactorGraphKey key{(void*)LU, scratch, bp.n2, bp.p, nsys, (int)(sizeof(T) == sizeof(cplx)) + 2 * NB + 128 * (tw - 1) + 1000 * groups_key, dev_key};
     for (auto& g : g_graphs)
         if (g.key == key) {
             g.stamp = ++g_stamp;
@@ -1303,6 +1395,8 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
         for (int g = 0; g < groups && okq; ++g) {
             int s0 = (int)((long long)nsys * g / groups), s1 = (int)((long long)nsys * (g + 1) / groups);
             cudaStream_t sg = (g == 0) ? st : aux[g - 1];
+            if (bp.twist) okq = okq && band_factor_twisted_enqueue<T, NB>(bp, LU + (size_t)s0 * 2 * bp.band_elems_h(), s1 - s0, (T*)scratch + (size_t)s0 * 2 * NB * NB, sg) == CS_OK;
+            else
             okq = okq && band_factor_enqueue<T, NB>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NB * NB, sg,
                                                     lookahead ? as.auxB[g] : nullptr, as.evP[g], as.evU[g], cnt + s0) == CS_OK;
         }
@@ -1316,6 +1410,8 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     }
     if (!captured) {
         cudaGetLastError();                 // capture unavailable: plain launches (same kernels)
+        if (bp.twist) CS_TRY((band_factor_twisted_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st)));
+        else
         CS_TRY((band_factor_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st, nullptr, nullptr, nullptr, cnt)));
         CS_CUDA(cudaGetLastError());
         return CS_OK;
@@ -1816,6 +1912,12 @@ static int band_factor_any(const BandPlan& bp, T* LU, int nsys, cudaStream_t st)
 // A(s_f) = K + s_f diag(mdiag) formed and factored for nshift shifts.  Scalar fields: fused into the cluster
 // kernel's chunk loads (no shifted copies in HBM); otherwise k_form_shifted + the step kernels.
 int band_form_and_factor(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st) {
+    if (bp.twist) {
+        CS_TRY(band_form_twisted(bp, s_d, nshift, LU, lu_cplx, st));
+        bp.diag_full = 0;
+        if (lu_cplx) return band_factor_t<cplx, 16>(bp, (cplx*)LU, nshift * bp.nmodes, st);
+        return band_factor_t<double, 16>(bp, (double*)LU, nshift * bp.nmodes, st);
+    }
     const char* e = getenv("CS_BAND_FUSE");
     bool fuse = !(e && atoi(e) == 0) && bp.nb == 16;
     if (fuse) {
@@ -1948,7 +2050,13 @@ __device__ __forceinline__ void bar_sync0() { asm volatile("bar.sync 0;" ::: "me
 template <typename TL, typename TV, int TPR, int NB, bool HP>
 __global__ void __launch_bounds__(TPR == 1 ? 1024 : (TPR == 2 ? 768 : 640))
 k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw, int ld,
-                             int nmodes, int nmv, int fold, int nth, const int* __restrict__ fmap, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0, int use_tma) {
+                             int nmodes, int nmv, int fold, int nth, const int* __restrict__ fmap, const int* __restrict__ shift_of_vec, TV* __restrict__ xm, int wsz, int nst, int diag_full, int prod0, int use_tma,
+                             int tw, int half0, int fs0, int fs1, int bs1, int given, int flush) {
+    // tw: twisted storage -- two half systems per (shift, mode) and per mode vector, this CTA works on half0 + blockIdx.z.
+    // Forward block steps [fs0, fs1), then the first bs1 backward steps (counted from the end).  `given`: in the first
+    // `given` backward steps the block solution is taken from the vector as it is (the separator solution computed by the
+    // other half) and only carried to the rows above.  `flush`: after the forward sweep the partial sums of the p rows
+    // below its last block go back to the vector (the separator rows of a twisted half).  One-front call: 0, 0, 0, ns, ns, 0, 0.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // TMA bulk copies need 16-byte aligned column segments: always true for complex factors, for real ones when the plan
     // has an even half bandwidth and an even system size (BandPlan::tma_real); otherwise cp.async
@@ -1968,8 +2076,9 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     const int v = blockIdx.y, mm = blockIdx.x;
     const int m = fold == 0 ? mm : (fold == 1 ? min(mm, nth - mm) : (fold == 2 ? (mm >> 1) : fmap[mm]));
     const int f = shift_of_vec ? shift_of_vec[v] : 0;
-    const TL* A = LU + ((size_t)f * nmodes + m) * nel + pw;
-    TV* b = xm + ((size_t)v * nmv + mm) * n2;
+    const int hf = half0 + (int)blockIdx.z;
+    const TL* A = tw ? LU + (((size_t)f * nmodes + m) * 2 + hf) * nel + pw : LU + ((size_t)f * nmodes + m) * nel + pw;
+    TV* b = tw ? xm + (((size_t)v * nmv + mm) * 2 + hf) * n2 : xm + ((size_t)v * nmv + mm) * n2;
     // rows per staged block column, padded so that the TPR column groups of a quarter warp fall into
     // distinct shared-memory banks (TPR = 4: ldd = 2 mod 8, TPR = 2: ldd = 4 mod 8)
     int ldd = NB + p;
@@ -1994,7 +2103,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     if (HP && tid >= prod0) {
         // ------------------------------ producer warp ------------------------------
         auto issue = [&](bool fwd, int s) {
-            if (s >= ns) return;
+            if (s >= (fwd ? fs1 : bs1)) return;
             long long row0, col0; int nrows, ncols;
             stage_geom(fwd, s, row0, nrows, col0, ncols);
             TL* dst = ring + (size_t)(s % nst) * ssz;
@@ -2004,11 +2113,12 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
                 cp_async_mbar_arrive(&full_bar[s % nst]);
             }
         };
-        for (int q = 0; q < nst - 1; ++q) issue(true, q);
-        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(true, s + nst - 1); if (!diag_full) bar_sync0(); }
+        for (int q = 0; q < nst - 1; ++q) issue(true, fs0 + q);
+        for (int s = fs0; s < fs1; ++s) { bar_sync0(); issue(true, s + nst - 1); if (!diag_full) bar_sync0(); }
         bar_sync0();                                          // forward done: every ring slot is free again
+        if (flush) bar_sync0();
         for (int q = 0; q < nst - 1; ++q) issue(false, q);
-        for (int s = 0; s < ns; ++s) { bar_sync0(); issue(false, s + nst - 1); bar_sync0(); }   // (two barriers per backward step)
+        for (int s = 0; s < bs1; ++s) { bar_sync0(); issue(false, s + nst - 1); bar_sync0(); }   // (two barriers per backward step)
         return;
     }
 
@@ -2027,7 +2137,7 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
         }
     };
     auto prefetch = [&](bool fwd, int s) {
-        if (!HP && s < ns) {
+        if (!HP && s < (fwd ? fs1 : bs1)) {
             long long row0, col0; int nrows, ncols;
             stage_geom(fwd, s, row0, nrows, col0, ncols);
             prefetch_cols<TL, TPR, NB>(ring + (size_t)(s % nst) * ssz, ldd, A, ld, row0, nrows, col0, ncols);
@@ -2040,11 +2150,14 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     };
 
     // ================= forward: L y = b (unit lower; diagonal blocks hold inv(L11), or nothing to apply) ==========
-    for (int e = tid; e < 3 * NB + p && e < n2; e += (HP ? prod0 : blockDim.x)) win[e & wm] = b[e];
-    for (int q = 0; q < nst - 1; ++q) prefetch(true, q);
+    if (fs1 > fs0) {
+        const long long t0 = (long long)fs0 * NB;
+        for (long long e = t0 + tid; e < t0 + 3 * NB + p && e < n2; e += (HP ? prod0 : blockDim.x)) win[e & wm] = b[e];
+    }
+    for (int q = 0; q < nst - 1; ++q) prefetch(true, fs0 + q);
     {
-        int slot = 0;
-        for (int s = 0; s < ns; ++s) {
+        int slot = fs0 % nst;
+        for (int s = fs0; s < fs1; ++s) {
             const long long t = (long long)s * NB;
             const int nbe = (int)min((long long)NB, n2 - t);
             const int R = (int)min((long long)p, n2 - (t + nbe));
@@ -2099,14 +2212,21 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     }
     __pipeline_wait_prior(0);
     bar_sync0();
+    if (flush) {
+        // twisted half: the rows below the last forward block (the separator) hold partial sums -- back to the vector
+        const long long t1 = (long long)fs1 * NB;
+        for (long long e = t1 + tid; e < t1 + p && e < n2; e += (HP ? prod0 : blockDim.x)) b[e] = win[e & wm];
+        bar_sync0();
+    }
 
     // ================= backward: U x = y (diagonal blocks hold inv(U11), or the full pivot-block inverse) =========
     // window now slides downwards; (re)load the last p + 4 NB rows of y
-    for (long long e = max(0LL, n2 - (4 * NB + p)) + tid; e < n2; e += (HP ? prod0 : blockDim.x)) win[e & wm] = b[e];
+    if (bs1 > 0)
+        for (long long e = max(0LL, n2 - (4 * NB + p)) + tid; e < n2; e += (HP ? prod0 : blockDim.x)) win[e & wm] = b[e];
     for (int q = 0; q < nst - 1; ++q) prefetch(false, q);
     {
         int slot = 0;
-        for (int s = 0; s < ns; ++s) {
+        for (int s = 0; s < bs1; ++s) {
             const long long t = tlast - (long long)s * NB;
             const int nbe = (int)min((long long)NB, n2 - t);
             const int Ra = (int)min((long long)p, t);
@@ -2132,8 +2252,9 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
                     if ((diag_full || c >= r16) && c < nbe && r16 < nbe) fmacc(xr, cur[(Ra + r16) + c * ldd], win[(t + c) & wm]);
                 }
                 if (HALVES == 2) xr += shfl_xor_t<TV>(xr, 16);
+                if (s < given) xr = (lane < nbe) ? b[t + lane] : zero;       // the separator solution, as given
                 if (lane < NB) yw[0][lane] = xr;
-                if (lane < nbe) b[t + lane] = xr;
+                if (lane < nbe && s >= given) b[t + lane] = xr;
             }
             bar_sync0();
             TV acc = zero;
@@ -2150,8 +2271,11 @@ k_band_solve(const TL* __restrict__ LU, size_t nel, long long n2, int p, int pw,
     __pipeline_wait_prior(0);
 }
 
+struct SolveRange { int tw = 0, half0 = 0, nhz = 1, fs0 = 0, fs1 = -1, bs1 = -1, given = 0, flush = 0; };
+
 template <typename T, int TPR, int NB>
-static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, int th, size_t sm, int wsz, int nst, cudaStream_t st) {
+static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, const int* sov, int th, size_t sm, int wsz, int nst, cudaStream_t st,
+                             SolveRange rg = SolveRange()) {
     // one extra warp that only stages the factors, if the launch bounds leave room (CS_SOLVE_PROD=0: never).
     // Complex systems only: the producer of a real system has to use cp.async (no 16-byte alignment for TMA),
     // and one warp issuing all of a stage's cp.async is much slower than all warps sharing them
@@ -2164,11 +2288,51 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
     else CS_CUDA(cudaFuncSetAttribute(k_band_solve<T, T, TPR, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     const bool xc = sizeof(T) == sizeof(cplx);
     const int nmv = bp.nmv(xc), fold = bp.fold(xc);
-    dim3 g(nmv, nvec);
-    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, th, tma ? 1 : 0);
-    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, bp.band_elems(), bp.n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, 0, 0);
+    const long long n2 = rg.tw ? bp.tw_n2h : bp.n2;
+    const size_t nel = rg.tw ? bp.band_elems_h() : bp.band_elems();
+    const int ns = (int)((n2 + NB - 1) / NB);
+    if (rg.fs1 < 0) rg.fs1 = ns;
+    if (rg.bs1 < 0) rg.bs1 = ns;
+    dim3 g(nmv, nvec, rg.nhz);
+    if (hp) k_band_solve<T, T, TPR, NB, true><<<g, th + 32, sm, st>>>(LU, nel, n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, th, tma ? 1 : 0,
+                                                                    rg.tw, rg.half0, rg.fs0, rg.fs1, rg.bs1, rg.given, rg.flush);
+    else k_band_solve<T, T, TPR, NB, false><<<g, th, sm, st>>>(LU, nel, n2, bp.p, bp.pw, bp.ldab - 1, bp.nmodes, nmv, fold, bp.nth, bp.fmap, sov, xm, wsz, nst, bp.diag_full, 0, 0,
+                                                             rg.tw, rg.half0, rg.fs0, rg.fs1, rg.bs1, rg.given, rg.flush);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
+}
+
+// ---- twisted substitution: vectors between the one-front ordering xm [vec][mv][n2] and the halves xh [vec][mv][2][n2h] ----
+template <typename T>
+__global__ void k_twist_gather(const T* __restrict__ xm, T* __restrict__ xh, long long n2, long long n2h, long long M, long long padT, long long padB) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n2h) return;
+    const size_t vm = blockIdx.y;                       // (vector, mode vector) pair
+    const int half = blockIdx.z;
+    const long long o = tw_orig(half, i, n2, padT, padB);
+    T v = Sc<T>::zero();
+    if (o >= 0 && !(half == 1 && i >= M)) v = xm[vm * n2 + o];        // (the separator right-hand side travels with T)
+    xh[(vm * 2 + half) * n2h + i] = v;
+}
+template <typename T>
+__global__ void k_twist_scatter(T* __restrict__ xm, const T* __restrict__ xh, long long n2, long long n2h, long long M, long long padT, long long padB) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n2h) return;
+    const size_t vm = blockIdx.y;
+    const int half = blockIdx.z;
+    if (half == 1 && i >= M) return;                    // the separator is written from T
+    const long long o = tw_orig(half, i, n2, padT, padB);
+    if (o >= 0) xm[vm * n2 + o] = xh[(vm * 2 + half) * n2h + i];
+}
+// separator rows: dir 0: T += reversed B (partial sums of the two forward sweeps); dir 1: B = reversed T (the separator solution)
+template <typename T>
+__global__ void k_twist_sep(T* __restrict__ xh, long long n2h, long long M, long long w, int dir) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= w) return;
+    T* t = xh + ((size_t)blockIdx.y * 2) * n2h + M;
+    T* b = t + n2h;
+    if (dir == 0) t[i] = t[i] + b[w - 1 - i];
+    else b[w - 1 - i] = t[i];
 }
 
 template <typename T, int NB>
@@ -2190,9 +2354,36 @@ static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const 
     if (nst > 6) nst = 6;
     CS_CHECK(nst >= 2, "half bandwidth too large for the shared-memory staged solve");
     size_t sm = (size_t)nst * stage_b + (size_t)wsz * sizeof(T);
-    if (tpr == 4) return band_solve_launch<T, 4, NB>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
-    if (tpr == 2) return band_solve_launch<T, 2, NB>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
-    return band_solve_launch<T, 1, NB>(bp, LU, xm, nvec, sov, th, sm, wsz, nst, st);
+    auto launch = [&](T* x, SolveRange rg) -> int {
+        if (tpr == 4) return band_solve_launch<T, 4, NB>(bp, LU, x, nvec, sov, th, sm, wsz, nst, st, rg);
+        if (tpr == 2) return band_solve_launch<T, 2, NB>(bp, LU, x, nvec, sov, th, sm, wsz, nst, st, rg);
+        return band_solve_launch<T, 1, NB>(bp, LU, x, nvec, sov, th, sm, wsz, nst, st, rg);
+    };
+    if (!bp.twist) return launch(xm, SolveRange());
+    // two fronts: both halves sweep forward at once, the separator is solved on T, both halves sweep backward at once
+    const bool xc = sizeof(T) == sizeof(cplx);
+    const size_t nvm = (size_t)nvec * bp.nmv(xc);
+    void* xhv = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_band_mu);
+        CS_TRY(band_scratch(4, st, nvm * 2 * bp.tw_n2h * sizeof(T), false, &xhv));
+    }
+    T* xh = (T*)xhv;
+    const long long n2h = bp.tw_n2h, M = bp.tw_M, w = bp.tw_w;
+    const int ns = (int)((n2h + NB - 1) / NB), S1 = (int)(M / NB);
+    dim3 gg((unsigned)cdiv(n2h, 256), (unsigned)nvm, 2), gs((unsigned)cdiv(w, 256), (unsigned)nvm);
+    k_twist_gather<T><<<gg, 256, 0, st>>>(xm, xh, bp.n2, n2h, M, bp.tw_padT, bp.tw_padB);
+    SolveRange r1; r1.tw = 1; r1.nhz = 2; r1.fs0 = 0; r1.fs1 = S1; r1.bs1 = 0; r1.flush = 1;
+    CS_TRY(launch(xh, r1));
+    k_twist_sep<T><<<gs, 256, 0, st>>>(xh, n2h, M, w, 0);
+    SolveRange r2; r2.tw = 1; r2.nhz = 1; r2.fs0 = S1; r2.fs1 = ns; r2.bs1 = ns - S1;
+    CS_TRY(launch(xh, r2));
+    k_twist_sep<T><<<gs, 256, 0, st>>>(xh, n2h, M, w, 1);
+    SolveRange r3; r3.tw = 1; r3.nhz = 2; r3.fs0 = 0; r3.fs1 = 0; r3.bs1 = ns; r3.given = ns - S1;
+    CS_TRY(launch(xh, r3));
+    k_twist_scatter<T><<<gg, 256, 0, st>>>(xm, xh, bp.n2, n2h, M, bp.tw_padT, bp.tw_padB);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
 }
 
 // block size of a plan: 32 halves the length of the dependent step chains, but the staged block
@@ -2204,6 +2395,26 @@ int band_choose_nb(int p) {
     size_t stage32 = (size_t)(p + 32) * 32 * sizeof(cplx);
     if (e && atoi(e) == 32 && 2 * stage32 + 16 * 1024 <= 200 * 1024) return 32;
     return 16;
+}
+
+void band_plan_twist(BandPlan& bp) {
+    bp.twist = false;
+    static const int on = [] { const char* e = getenv("CS_TWIST"); return e ? atoi(e) : 0; }();
+    if (!on || bp.Lrow <= 0 || bp.nb != 16 || bp.nbf != 16 || bp.fmap) return;
+    if (cluster_lu_plan<cplx, 16>(bp).ok || cluster_lu_plan<double, 16>(bp).ok) return;      // narrow bands: the cluster-resident LU
+    const long long levels = bp.n2 / bp.Lrow;
+    if (levels < 8 || bp.p > bp.Lrow + 16 || bp.Lrow < 16) return;                           // (the separator must decouple the two sides)
+    const long long ks = levels / 2;
+    bp.tw_nt = bp.Lrow * ks;
+    bp.tw_w = bp.Lrow;
+    const long long nbot = bp.n2 - bp.tw_nt - bp.tw_w;
+    const long long mx = std::max(bp.tw_nt, nbot);
+    bp.tw_M = (mx + 15) / 16 * 16;
+    bp.tw_padT = bp.tw_M - bp.tw_nt;
+    bp.tw_padB = bp.tw_M - nbot;
+    bp.tw_n2h = bp.tw_M + bp.tw_w;
+    if (bp.tma_real && (bp.tw_n2h & 1)) return;                                              // (TMA staging of real factors needs an even order)
+    bp.twist = true;
 }
 
 // Factorisation steps of 32 columns with the substitution's 16-column blocks (CS_LU_NBF=32): half as many dependent launch

@@ -102,6 +102,18 @@ struct BandPlan {
     // lower triangle of the trailing window only and mirrors the pivot rows, U12 = diag(U11) L21^T
     bool sym = false;
     size_t band_elems() const { return (size_t)n2 * ldab; }
+    // ---- two-front ("twisted") elimination: every mode system is split at one z level (the separator, `tw_w` unknowns);
+    // the levels below it are eliminated top-down, the levels above it bottom-up (the same kernels on the REVERSED
+    // ordering), at the same time: half as many dependent block steps in the factorisation and in both substitution
+    // sweeps, no extra flops.  Storage: two band matrices of order tw_n2h = tw_M + tw_w per system,
+    //   T = [tw_padT identity dummies | unknowns 0 .. tw_nt - 1 | separator],      T index i <-> original i - tw_padT
+    //   B = [tw_padB identity dummies | unknowns n2 - 1 .. tw_nt + tw_w, descending | separator descending], i <-> n2 - 1 - (i - tw_padB)
+    // tw_M is a multiple of the block size, so both fronts stop at a block boundary; the separator block of T then
+    // receives B's Schur complement and is factored last.
+    bool twist = false;
+    long long tw_n2h = 0, tw_M = 0, tw_nt = 0, tw_w = 0, tw_padT = 0, tw_padB = 0;
+    size_t band_elems_h() const { return (size_t)tw_n2h * ldab; }
+    size_t lu_elems_per_system() const { return twist ? 2 * band_elems_h() : band_elems(); }
     // mode vectors per 3-D vector: complex factors take all nth modes (mode m uses factor min(m, nth - m));
     // real factors (real shift) take Re / Im of modes 0 .. nth/2 of a REAL 3-D vector as 2 * nmodes real vectors
     int nmv(bool xm_cplx) const { return fmap ? nmv_own : (nth == 1 ? 1 : (xm_cplx ? nth : 2 * nmodes)); }
@@ -115,6 +127,7 @@ struct BandPlan {
 // block size (16 or 32) for a plan with half bandwidth p
 int band_choose_nb(int p);
 int band_choose_nbf(int p, int nb);
+void band_plan_twist(BandPlan& bp);       // decides BandPlan::twist and fills the tw_* geometry (after n2, p, nb, Lrow are final)
 void band_release_stream(cudaStream_t st);   // frees the band scratch buffers keyed by this stream
 int band_factor_launches(const BandPlan& bp, bool lu_cplx);
 // theta-DFT into the rotated mode basis x''_m = T_m^* x_m; xm [nvec][nmv][n2]
