@@ -1248,9 +1248,11 @@ static int band_factor_enqueue(const BandPlan& bp, T* LU, int nsys, T* scratch, 
 
 // ---- two-front ("twisted") elimination (BandPlan::twist) ----
 // original index of entry i of half system `half` (-1: identity dummy)
-__device__ __forceinline__ long long tw_orig(int half, long long i, long long n2, long long padT, long long padB) {
-    if (half == 0) return i < padT ? -1 : i - padT;
-    return i < padB ? -1 : n2 - 1 - (i - padB);
+// (padT / padB leading dummies; a trailing dummy pads the order to an even number when real factors are TMA-staged)
+__device__ __forceinline__ long long tw_orig(int half, long long i, long long n2, long long padT, long long padB, long long nt, long long w) {
+    if (half == 0) { const long long o = i - padT; return (o < 0 || o >= nt + w) ? -1 : o; }
+    const long long o = n2 - 1 - (i - padB);
+    return (i < padB || o < nt) ? -1 : o;
 }
 // LU2[f][m][half] = twisted halves of K[m] + s[f] diag(mdiag)  (see BandPlan::twist; the separator block goes to T, B's is zero)
 template <typename TB, typename TL>
@@ -1265,10 +1267,10 @@ __global__ void k_form_twisted(const long long* __restrict__ map3d, const int* _
     const int d = (int)(e - q * ldab);
     const long long i = q + d - pw;
     TL v = Sc<TL>::zero();
-    const long long oq = tw_orig(half, q, n2, padT, padB);
+    const long long oq = tw_orig(half, q, n2, padT, padB, nt, w);
     if (oq < 0) { if (d == pw) v = Sc<TL>::one(); }
     else if (i >= 0 && i < n2h) {
-        const long long oi = tw_orig(half, i, n2, padT, padB);
+        const long long oi = tw_orig(half, i, n2, padT, padB, nt, w);
         const bool sq = oq >= nt && oq < nt + w, si = oi >= nt && oi < nt + w;
         if (oi >= 0 && !(half == 1 && sq && si)) {
             const TB kv = K[(size_t)m * ((size_t)n2 * ldab) + (size_t)(pw + oi - oq) + (size_t)oq * ldab];
@@ -1335,7 +1337,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     CS_CHECK(bp.nbf == NB, "band plan step size must equal the instantiated NB");
     std::lock_guard<std::mutex> lock(g_band_mu);
     void* scratch = nullptr;
-    const int tw = bp.twist ? 2 : 1;                  // twisted: two half systems per system
+    const int tw = bp.tw_active ? 2 : 1;              // twisted: two half systems per system
     CS_TRY(band_scratch(0, st, (size_t)tw * nsys * NB * NB * sizeof(T), false, &scratch));
     void* cntv = nullptr;
     CS_TRY(band_scratch(2, st, (size_t)nsys * sizeof(int), true, &cntv));
@@ -1395,7 +1397,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
         for (int g = 0; g < groups && okq; ++g) {
             int s0 = (int)((long long)nsys * g / groups), s1 = (int)((long long)nsys * (g + 1) / groups);
             cudaStream_t sg = (g == 0) ? st : aux[g - 1];
-            if (bp.twist) okq = okq && band_factor_twisted_enqueue<T, NB>(bp, LU + (size_t)s0 * 2 * bp.band_elems_h(), s1 - s0, (T*)scratch + (size_t)s0 * 2 * NB * NB, sg) == CS_OK;
+            if (bp.tw_active) okq = okq && band_factor_twisted_enqueue<T, NB>(bp, LU + (size_t)s0 * 2 * bp.band_elems_h(), s1 - s0, (T*)scratch + (size_t)s0 * 2 * NB * NB, sg) == CS_OK;
             else
             okq = okq && band_factor_enqueue<T, NB>(bp, LU + (size_t)s0 * bp.band_elems(), s1 - s0, (T*)scratch + (size_t)s0 * NB * NB, sg,
                                                     lookahead ? as.auxB[g] : nullptr, as.evP[g], as.evU[g], cnt + s0) == CS_OK;
@@ -1410,7 +1412,7 @@ static int band_factor_t(const BandPlan& bp, T* LU, int nsys, cudaStream_t st) {
     }
     if (!captured) {
         cudaGetLastError();                 // capture unavailable: plain launches (same kernels)
-        if (bp.twist) CS_TRY((band_factor_twisted_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st)));
+        if (bp.tw_active) CS_TRY((band_factor_twisted_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st)));
         else
         CS_TRY((band_factor_enqueue<T, NB>(bp, LU, nsys, (T*)scratch, st, nullptr, nullptr, nullptr, cnt)));
         CS_CUDA(cudaGetLastError());
@@ -1911,8 +1913,37 @@ static int band_factor_any(const BandPlan& bp, T* LU, int nsys, cudaStream_t st)
 }
 // A(s_f) = K + s_f diag(mdiag) formed and factored for nshift shifts.  Scalar fields: fused into the cluster
 // kernel's chunk loads (no shifted copies in HBM); otherwise k_form_shifted + the step kernels.
-int band_form_and_factor(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st) {
-    if (bp.twist) {
+// diagonal of every (half) system: finite?
+template <typename T>
+__global__ void k_diag_finite(const T* __restrict__ LU, size_t nel, long long n2, int pw, int ldab, int* __restrict__ bad) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= n2) return;
+    const T v = LU[(size_t)blockIdx.y * nel + pw + q * (long long)ldab];
+    if (!isfinite(Sc<T>::abs2(v))) *bad = 1;
+}
+int band_factor_finite(const BandPlan& bp, const void* LU, bool lu_cplx, int nshift, bool* ok, cudaStream_t st) {
+    void* buf = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_band_mu);
+        CS_TRY(band_scratch(3, st, 2 * sizeof(unsigned long long), false, &buf));
+    }
+    CS_CUDA(cudaMemsetAsync(buf, 0, sizeof(int), st));
+    const long long n2 = bp.tw_active ? bp.tw_n2h : bp.n2;
+    const size_t nel = bp.tw_active ? bp.band_elems_h() : bp.band_elems();
+    dim3 g((unsigned)cdiv(n2, 256), (unsigned)(nshift * bp.nmodes * (bp.tw_active ? 2 : 1)));
+    if (lu_cplx) k_diag_finite<cplx><<<g, 256, 0, st>>>((const cplx*)LU, nel, n2, bp.pw, bp.ldab, (int*)buf);
+    else k_diag_finite<double><<<g, 256, 0, st>>>((const double*)LU, nel, n2, bp.pw, bp.ldab, (int*)buf);
+    CS_CUDA(cudaGetLastError());
+    int h = 0;
+    CS_CUDA(cudaMemcpyAsync(&h, buf, sizeof h, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    *ok = (h == 0);
+    return CS_OK;
+}
+
+int band_form_and_factor(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st, bool allow_twist) {
+    bp.tw_active = bp.twist && allow_twist;
+    if (bp.tw_active) {
         CS_TRY(band_form_twisted(bp, s_d, nshift, LU, lu_cplx, st));
         bp.diag_full = 0;
         if (lu_cplx) return band_factor_t<cplx, 16>(bp, (cplx*)LU, nshift * bp.nmodes, st);
@@ -2304,24 +2335,24 @@ static int band_solve_launch(const BandPlan& bp, const T* LU, T* xm, int nvec, c
 
 // ---- twisted substitution: vectors between the one-front ordering xm [vec][mv][n2] and the halves xh [vec][mv][2][n2h] ----
 template <typename T>
-__global__ void k_twist_gather(const T* __restrict__ xm, T* __restrict__ xh, long long n2, long long n2h, long long M, long long padT, long long padB) {
+__global__ void k_twist_gather(const T* __restrict__ xm, T* __restrict__ xh, long long n2, long long n2h, long long M, long long padT, long long padB, long long nt, long long w) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n2h) return;
     const size_t vm = blockIdx.y;                       // (vector, mode vector) pair
     const int half = blockIdx.z;
-    const long long o = tw_orig(half, i, n2, padT, padB);
+    const long long o = tw_orig(half, i, n2, padT, padB, nt, w);
     T v = Sc<T>::zero();
     if (o >= 0 && !(half == 1 && i >= M)) v = xm[vm * n2 + o];        // (the separator right-hand side travels with T)
     xh[(vm * 2 + half) * n2h + i] = v;
 }
 template <typename T>
-__global__ void k_twist_scatter(T* __restrict__ xm, const T* __restrict__ xh, long long n2, long long n2h, long long M, long long padT, long long padB) {
+__global__ void k_twist_scatter(T* __restrict__ xm, const T* __restrict__ xh, long long n2, long long n2h, long long M, long long padT, long long padB, long long nt, long long w) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n2h) return;
     const size_t vm = blockIdx.y;
     const int half = blockIdx.z;
     if (half == 1 && i >= M) return;                    // the separator is written from T
-    const long long o = tw_orig(half, i, n2, padT, padB);
+    const long long o = tw_orig(half, i, n2, padT, padB, nt, w);
     if (o >= 0) xm[vm * n2 + o] = xh[(vm * 2 + half) * n2h + i];
 }
 // separator rows: dir 0: T += reversed B (partial sums of the two forward sweeps); dir 1: B = reversed T (the separator solution)
@@ -2359,7 +2390,7 @@ static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const 
         if (tpr == 2) return band_solve_launch<T, 2, NB>(bp, LU, x, nvec, sov, th, sm, wsz, nst, st, rg);
         return band_solve_launch<T, 1, NB>(bp, LU, x, nvec, sov, th, sm, wsz, nst, st, rg);
     };
-    if (!bp.twist) return launch(xm, SolveRange());
+    if (!bp.tw_active) return launch(xm, SolveRange());
     // two fronts: both halves sweep forward at once, the separator is solved on T, both halves sweep backward at once
     const bool xc = sizeof(T) == sizeof(cplx);
     const size_t nvm = (size_t)nvec * bp.nmv(xc);
@@ -2372,7 +2403,7 @@ static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const 
     const long long n2h = bp.tw_n2h, M = bp.tw_M, w = bp.tw_w;
     const int ns = (int)((n2h + NB - 1) / NB), S1 = (int)(M / NB);
     dim3 gg((unsigned)cdiv(n2h, 256), (unsigned)nvm, 2), gs((unsigned)cdiv(w, 256), (unsigned)nvm);
-    k_twist_gather<T><<<gg, 256, 0, st>>>(xm, xh, bp.n2, n2h, M, bp.tw_padT, bp.tw_padB);
+    k_twist_gather<T><<<gg, 256, 0, st>>>(xm, xh, bp.n2, n2h, M, bp.tw_padT, bp.tw_padB, bp.tw_nt, w);
     SolveRange r1; r1.tw = 1; r1.nhz = 2; r1.fs0 = 0; r1.fs1 = S1; r1.bs1 = 0; r1.flush = 1;
     CS_TRY(launch(xh, r1));
     k_twist_sep<T><<<gs, 256, 0, st>>>(xh, n2h, M, w, 0);
@@ -2381,7 +2412,7 @@ static int band_solve_t(const BandPlan& bp, const T* LU, T* xm, int nvec, const 
     k_twist_sep<T><<<gs, 256, 0, st>>>(xh, n2h, M, w, 1);
     SolveRange r3; r3.tw = 1; r3.nhz = 2; r3.fs0 = 0; r3.fs1 = 0; r3.bs1 = ns; r3.given = ns - S1;
     CS_TRY(launch(xh, r3));
-    k_twist_scatter<T><<<gg, 256, 0, st>>>(xm, xh, bp.n2, n2h, M, bp.tw_padT, bp.tw_padB);
+    k_twist_scatter<T><<<gg, 256, 0, st>>>(xm, xh, bp.n2, n2h, M, bp.tw_padT, bp.tw_padB, bp.tw_nt, w);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
@@ -2399,7 +2430,8 @@ int band_choose_nb(int p) {
 
 void band_plan_twist(BandPlan& bp) {
     bp.twist = false;
-    static const int on = [] { const char* e = getenv("CS_TWIST"); return e ? atoi(e) : 0; }();
+    const char* tw_env = getenv("CS_TWIST");          // (read per plan: CS_TWIST=0 keeps the one-front elimination)
+    const int on = tw_env ? atoi(tw_env) : 1;
     if (!on || bp.Lrow <= 0 || bp.nb != 16 || bp.nbf != 16 || bp.fmap) return;
     if (cluster_lu_plan<cplx, 16>(bp).ok || cluster_lu_plan<double, 16>(bp).ok) return;      // narrow bands: the cluster-resident LU
     const long long levels = bp.n2 / bp.Lrow;
@@ -2413,7 +2445,7 @@ void band_plan_twist(BandPlan& bp) {
     bp.tw_padT = bp.tw_M - bp.tw_nt;
     bp.tw_padB = bp.tw_M - nbot;
     bp.tw_n2h = bp.tw_M + bp.tw_w;
-    if (bp.tma_real && (bp.tw_n2h & 1)) return;                                              // (TMA staging of real factors needs an even order)
+    if (bp.tma_real && (bp.tw_n2h & 1)) bp.tw_n2h += 1;                                      // (TMA staging of real factors needs an even order: one trailing dummy)
     bp.twist = true;
 }
 

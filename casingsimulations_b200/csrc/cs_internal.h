@@ -1,5 +1,6 @@
 // Internal host-side interfaces between the translation units of libcasing_b200.
 #pragma once
+#include <algorithm>
 #include "cs_common.cuh"
 #include <vector>
 
@@ -111,9 +112,12 @@ struct BandPlan {
     // tw_M is a multiple of the block size, so both fronts stop at a block boundary; the separator block of T then
     // receives B's Schur complement and is factored last.
     bool twist = false;
+    // set by band_form_and_factor: the factors in the LU buffer ARE twisted (a factorisation that broke down is redone
+    // one-front, see cs_op_factor); read by band_solve
+    mutable bool tw_active = false;
     long long tw_n2h = 0, tw_M = 0, tw_nt = 0, tw_w = 0, tw_padT = 0, tw_padB = 0;
     size_t band_elems_h() const { return (size_t)tw_n2h * ldab; }
-    size_t lu_elems_per_system() const { return twist ? 2 * band_elems_h() : band_elems(); }
+    size_t lu_elems_per_system() const { return twist ? std::max(2 * band_elems_h(), band_elems()) : band_elems(); }   // (room for either format)
     // mode vectors per 3-D vector: complex factors take all nth modes (mode m uses factor min(m, nth - m));
     // real factors (real shift) take Re / Im of modes 0 .. nth/2 of a REAL 3-D vector as 2 * nmodes real vectors
     int nmv(bool xm_cplx) const { return fmap ? nmv_own : (nth == 1 ? 1 : (xm_cplx ? nth : 2 * nmodes)); }
@@ -147,7 +151,9 @@ int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shif
 int band_form_shifted_mode(const BandPlan& bp, int mode, const double* s_d, void* LU, cudaStream_t st);
 // in-place blocked LU without pivoting of nsys_tot = nshift*nmodes band matrices
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st);
-int band_form_and_factor(const BandPlan& bp, const double* s_d /*device*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
+int band_form_and_factor(const BandPlan& bp, const double* s_d /*device*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st, bool allow_twist = true);
+// all pivots of the factors finite? (a twisted factorisation of a nearly singular system can break down where the one-front one does not)
+int band_factor_finite(const BandPlan& bp, const void* LU, bool lu_cplx, int nshift, bool* ok /*host*/, cudaStream_t st);
 // solve: rhs/solution xm [nvec][nmv][n2]; vector v uses the factors of shift shift_of_vec[v]
 int band_solve(const BandPlan& bp, const void* LU, bool lu_cplx, void* xm, bool xm_cplx, int nvec, const int* shift_of_vec_d, cudaStream_t st);
 
