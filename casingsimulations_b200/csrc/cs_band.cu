@@ -1974,6 +1974,7 @@ int band_factor_launches(const BandPlan& bp, bool lu_cplx) {
         bool ok = lu_cplx ? cluster_lu_plan<cplx, 16>(bp).ok : cluster_lu_plan<double, 16>(bp).ok;
         if (ok) return 1;
     }
+    if (bp.tw_active) return 4 + 2 * (int)((bp.tw_n2h + bp.nbf - 1) / bp.nbf);      // both fronts share the launches of a step
     return 1 + 2 * (int)((bp.n2 + bp.nbf - 1) / bp.nbf);
 }
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st) {

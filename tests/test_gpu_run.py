@@ -806,6 +806,44 @@ def test_remaining_painters_gpu(tmp_path, klass_name):
     simf.prob.clean()
 
 
+def test_two_front_elimination_parity_on_wide_band_mesh():
+    """The two-front (twisted) elimination only runs on wide bands (3-D edge / face systems with nx ~ 100: p = 330), which the
+    small test meshes do not have.  Mesh of the bench's reference arm, 109 x 4 x 40 = 17 440 cells (41 levels, split at level
+    20): FDEM-h against the EXACTLY assembled system.  Measured (two-front / one-front / the reference's fp64 SuperLU):
+    10 Hz j energy norm 3.7e-6 / 1.1e-6 / 6.0e-4, casing current 8e-8 / 1e-7 / 3e-6; 10 kHz 3.5e-8 / 7e-9 / 3.9e-7 and
+    3e-10 / 1e-9 / 1e-6.  Fixed tolerances: 2e-5 (10 Hz) and 1e-6 (10 kHz) in the energy norm, 1e-6 for the casing current.
+    (Below ~5 Hz the extended-precision refinement of the truth does not converge on this coarse mesh.)"""
+    import bench
+    from casingsimulations_b200 import _lib
+    from oracle.cyl_oracle import OracleCylMesh, OracleFDEM, paint_casing_in_halfspace, exact_mesh, energy_rel, casing_currents
+    freqs = [10.0, 1e4]
+    mp, mg, src = bench.build_inputs(bench.MESH_REF, freqs)
+    m = mg.mesh
+    assert tuple(int(v) for v in m.vnC) == (109, 4, 40)
+    ctx = _lib.Context(0)
+    ctx.set_mesh(m.hx, m.hy, m.hz, m.x0[2])
+    se = ctx.to_device(np.real(src.s_e))
+    ctx.paint(mp.paint_params())
+    u = ctx.solve_fdem("h", mp.freqs, se)
+    assert ctx.info["converged"] == 1.0 and ctx.info["iters"] <= 2
+    om = OracleCylMesh([m.hx, m.hy, m.hz], m.x0)
+    sig, mu = paint_casing_in_halfspace(om, sigma_back=mp.sigma_back, sigma_air=mp.sigma_air, sigma_casing=mp.sigma_casing,
+                                        sigma_inside=mp.sigma_inside, mur_casing=mp.mur_casing, casing_a=mp.casing_a,
+                                        casing_b=mp.casing_b, casing_z=tuple(mp.casing_z), surface_z=mp.surface_z)
+    PX = OracleFDEM(exact_mesh(om), sig, mu, "h")
+    se_np = np.real(src.s_e)
+    rho = np.asarray(om.getFaceInnerProduct(sig, invProp=True).diagonal())
+    cas = (mp.casing_a, mp.casing_b, tuple(mp.casing_z))
+    for k, (f, tol) in enumerate(zip(freqs, (2e-5, 1e-6))):
+        j_ref = np.asarray(PX.j_from(f, PX.solve(f, se_np, refine=True), se_np), dtype=complex)
+        j = ctx.fields_fdem("h", "j", f, u[k], se).cpu().numpy()
+        iz, iz_ref = casing_currents(j, om, *cas)["z"][1], casing_currents(j_ref, om, *cas)["z"][1]
+        ej, ei = energy_rel(j, j_ref, rho), float(np.linalg.norm(iz - iz_ref) / np.linalg.norm(iz_ref))
+        print("two-front parity at", f, "Hz: j energy", ej, "casing Iz", ei)
+        assert ej < tol and ei < 1e-6
+    ctx.close()
+
+
 def _run_dist_tool(nproc, args, env=None):
     import json
     import subprocess
