@@ -391,14 +391,18 @@ def run_ours(args, rank, world, local_rank):
         flops = 8.0 * (n2 / 16.0) * (p * 128.0 + tl * (tl + 1) / 2 * 32 * 32 * 16) * nsys * len(freqs)
         flops_lu = 8.0 * n2 * float(p) ** 2 * nsys * len(freqs)
         ach = flops / (ms_factor * 1e-3) / 1e12
-        roof = {"bound": "fp64", "kernel": "symmetric band LU of the {} theta-mode systems per frequency (k_lu_panel + k_lu_update on the lower triangle, {} dependent "
-                                            "16-column block steps replayed as one CUDA graph): {:.0f} % of the step's device time"
-                                            .format(nsys, (n2 + 15) // 16, 100.0 * ms_factor / (t_dev / args.steps * 1e3)),
+        # two-front elimination: the fronts meet at the middle z level, both advance in the same launches
+        lrow, levels = 3 * nx + 1, nz + 1
+        nt_ = lrow * (levels // 2)
+        steps2 = ((max(nt_, n2 - nt_ - lrow) + 15) // 16 * 16 + lrow + 15) // 16
+        roof = {"bound": "fp64", "kernel": "symmetric two-front band LU of the {} theta-mode systems per frequency (k_lu_panel4 + k_lu_update on the lower "
+                                            "triangle, {} dependent 16-column block steps of both fronts replayed as one CUDA graph): {:.0f} % of the step's device time"
+                                            .format(nsys, steps2, 100.0 * ms_factor / (t_dev / args.steps * 1e3)),
                 "achieved": ach, "peak": fp64_peak, "peak_source": "live DFMA microbenchmark (cs_fp64_peak), 148 SMs",
                 "unit": "TFLOP/s", "frac": ach / fp64_peak, "flops_per_step": flops,
                 "general_lu_equivalent": {"flops_per_step": flops_lu, "tflops": flops_lu / (ms_factor * 1e-3) / 1e12},
                 "ms_factor_per_step": ms_factor, "traffic": None,
-                "traffic_note": "per-launch DRAM bytes of k_lu_panel / k_lu_update (the window is L2 resident) in profiles/r02_ncu_lu_step.md",
+                "traffic_note": "per-launch DRAM bytes of k_lu_panel4 / k_lu_update (0.7 / 9.6 MB: the windows are L2 resident) in profiles/r02_ncu_lu_final.md",
                 "launch_shares": "profiles/r02_launch_list_3d.md"}
         try:
             roof["stencil_apply"] = stencil_roofline(torch, local_rank)
