@@ -746,7 +746,7 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     const long long L = bl.Lrow;
     op->Lrow = L;
     bg = bl;
-    bg.twist = false;                             // (the mode-sharded global factors keep the one-front elimination)
+    bg.twist = false; bg.tw_active = false;       // (the mode-sharded global factors keep the one-front elimination)
     bg.n2 = L * (d.g.gnz + 1);
     const long long n2g_true = bg.n2;             // without the padding dummy
     if (bl.tma_real && (bg.n2 & 1)) bg.n2 += 1;
