@@ -746,7 +746,7 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     const long long L = bl.Lrow;
     op->Lrow = L;
     bg = bl;
-    bg.twist = false; bg.tw_active = false;       // (the mode-sharded global factors keep the one-front elimination)
+    bg.twist = false; bg.tw_active = false;       // (decided below, once the global geometry is known)
     bg.n2 = L * (d.g.gnz + 1);
     const long long n2g_true = bg.n2;             // without the padding dummy
     if (bl.tma_real && (bg.n2 & 1)) bg.n2 += 1;
@@ -793,9 +793,13 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     CS_CUDA(cudaMemsetAsync(bg.mdiag, 0, bg.n2 * sizeof(double), c->st));
     k_fill_rows<<<cdiv(g1 - g0, 256), 256, 0, c->st>>>(bg.mdiag + g0, bl.mdiag + l0, g1 - g0);
     CS_TRY(dist_allreduce_sum(d.g, d.comm, bg.mdiag, (size_t)bg.n2, c->st));
-    // factors
+    // factors: two-front elimination of every owned global mode system when the plan allows it (every rank decides alike:
+    // the same global geometry and environment)
+    bg.Lrow = L;
+    band_plan_twist(bg);
     const size_t nel_g = bg.band_elems(), nel_l = bl.band_elems();
-    CS_TRY(op->LU.ensure((size_t)nshift * n_own * nel_g * sizeof(cplx)));
+    const size_t per_sys = bg.lu_elems_per_system();
+    CS_TRY(op->LU.ensure((size_t)nshift * n_own * per_sys * sizeof(cplx)));
     CS_TRY(op->gstage.ensure(nel_g * sizeof(double)));
     double* stage = (double*)op->gstage.p;
     CS_CUDA(cudaMemsetAsync(stage, 0, nel_g * sizeof(double), c->st));     // (the padding dummy's column is never received)
@@ -804,6 +808,9 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
     const double* Kl = (const double*)bl.Kband;
     BandPlan one = bg;                     // view of ONE mode system for k_form_shifted
     one.nmodes = 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool tw = bg.twist && attempt == 0;
+    bg.tw_active = tw;
     for (int h = 0; h < H; ++h) {
         const int owner = h % R;
         const double* src = Kl + (size_t)h * nel_l + (size_t)l0 * bl.ldab;
@@ -824,14 +831,30 @@ static int dist_factor(cs_op* op, const double* shifts_h, int nshift, bool lc) {
             // which in the one-mode view is always 0 -> pass the true mode through the Kband offset trick below
             one.Kband = stage;
             for (int f = 0; f < nshift; ++f) {
-                cplx* dst = (cplx*)op->LU.p + ((size_t)f * n_own + h / R) * nel_g;
-                CS_TRY(band_form_shifted_mode(one, h, (const double*)c->scal.p + 2 * f, dst, c->st));
+                cplx* dst = (cplx*)op->LU.p + ((size_t)f * n_own + h / R) * (tw ? 2 * bg.band_elems_h() : nel_g);
+                if (tw) CS_TRY(band_form_twisted(one, (const double*)c->scal.p + 2 * f, 1, dst, true, c->st, h));
+                else CS_TRY(band_form_shifted_mode(one, h, (const double*)c->scal.p + 2 * f, dst, c->st));
             }
         }
     }
     g_launches += 2 * H;
     CS_TRY(band_factor(bg, op->LU.p, true, nshift * n_own, c->st));
     g_launches += band_factor_launches(bg, true);
+    if (!tw) break;
+    // a broken-down two-front factorisation on ANY rank sends all ranks back to the one-front elimination (the band
+    // columns are exchanged collectively)
+    bool fin = true;
+    CS_TRY(band_factor_finite(bg, op->LU.p, true, nshift, &fin, c->st));
+    double* flag = (double*)c->scal.p + 511;         // (last double of the 4 KB the shifts live in)
+    const double bad = fin ? 0.0 : 1.0;
+    CS_CUDA(cudaMemcpyAsync(flag, &bad, sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CS_TRY(dist_allreduce_sum(d.g, d.comm, flag, 1, c->st));
+    double tot = 0.0;
+    CS_CUDA(cudaMemcpyAsync(&tot, flag, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    if (tot == 0.0) break;
+    if (getenv("CS_FACTOR_LOG")) fprintf(stderr, "[factor] slab mode: two-front factors not finite on some rank: one-front elimination instead\n");
+  }
     return CS_OK;
 }
 

@@ -1259,7 +1259,9 @@ __device__ __forceinline__ long long tw_orig(int half, long long i, long long n2
 template <typename TB, typename TL>
 __global__ void k_form_twisted(const long long* __restrict__ map3d, const int* __restrict__ jstr, const double* __restrict__ mdiag,
                                long long n2, int pw, int ldab, int nmodes, long long n2h, long long nt, long long w, long long padT, long long padB,
-                               const TB* __restrict__ K, const double* __restrict__ s_d, TL* __restrict__ LU) {
+                               const TB* __restrict__ K, const double* __restrict__ s_d, TL* __restrict__ LU, int mode_base) {
+    // mode_base: true theta-mode index of stored mode 0 (the mode-sharded slab solve forms one mode at a time; the shared
+    // axis unknown is a dummy in every mode but 0)
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long nelh = n2h * (long long)ldab;
     if (e >= nelh) return;
@@ -1277,7 +1279,7 @@ __global__ void k_form_twisted(const long long* __restrict__ map3d, const int* _
             const TB kv = K[(size_t)m * ((size_t)n2 * ldab) + (size_t)(pw + oi - oq) + (size_t)oq * ldab];
             v = Sc<TL>::from(Sc<TB>::re(kv), Sc<TB>::im(kv));
             if (oi == oq) {
-                const bool dummy = (map3d[oq] < 0) || (jstr[oq] == 0 && m > 0);
+                const bool dummy = (map3d[oq] < 0) || (jstr[oq] == 0 && mode_base + m > 0);
                 if (dummy) v = Sc<TL>::one();
                 else v = v + Sc<TL>::from(s_d[2 * f], s_d[2 * f + 1]) * Sc<TL>::from(mdiag[oq], 0.0);
             }
@@ -1285,11 +1287,11 @@ __global__ void k_form_twisted(const long long* __restrict__ map3d, const int* _
     }
     LU[(((size_t)f * nmodes + m) * 2 + half) * (size_t)nelh + e] = v;
 }
-int band_form_twisted(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st) {
+int band_form_twisted(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st, int mode_base) {
     const long long nelh = (long long)bp.band_elems_h();
     dim3 g((unsigned)cdiv(nelh, 256), 2 * bp.nmodes, nshift);
 #define CS_FORM_TW(TB, TL) k_form_twisted<TB, TL><<<g, 256, 0, st>>>(bp.map3d, bp.jstr, bp.mdiag, bp.n2, bp.pw, bp.ldab, bp.nmodes, bp.tw_n2h, bp.tw_nt, bp.tw_w, \
-                                                                    bp.tw_padT, bp.tw_padB, (const TB*)bp.Kband, s_d, (TL*)LU)
+                                                                    bp.tw_padT, bp.tw_padB, (const TB*)bp.Kband, s_d, (TL*)LU, mode_base)
     if (bp.cplx_band) { CS_CHECK(lu_cplx, "complex band needs complex LU"); CS_FORM_TW(cplx, cplx); }
     else if (lu_cplx) CS_FORM_TW(double, cplx);
     else CS_FORM_TW(double, double);
@@ -1945,7 +1947,7 @@ int band_factor_finite(const BandPlan& bp, const void* LU, bool lu_cplx, int nsh
 int band_form_and_factor(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st, bool allow_twist) {
     bp.tw_active = bp.twist && allow_twist;
     if (bp.tw_active) {
-        CS_TRY(band_form_twisted(bp, s_d, nshift, LU, lu_cplx, st));
+        CS_TRY(band_form_twisted(bp, s_d, nshift, LU, lu_cplx, st, 0));
         bp.diag_full = 0;
         if (lu_cplx) return band_factor_t<cplx, 16>(bp, (cplx*)LU, nshift * bp.nmodes, st);
         return band_factor_t<double, 16>(bp, (double*)LU, nshift * bp.nmodes, st);
@@ -2434,7 +2436,7 @@ void band_plan_twist(BandPlan& bp) {
     bp.twist = false;
     const char* tw_env = getenv("CS_TWIST");          // (read per plan: CS_TWIST=0 keeps the one-front elimination)
     const int on = tw_env ? atoi(tw_env) : 1;
-    if (!on || bp.Lrow <= 0 || bp.nb != 16 || bp.nbf != 16 || bp.fmap) return;
+    if (!on || bp.Lrow <= 0 || bp.nb != 16 || bp.nbf != 16) return;
     if (cluster_lu_plan<cplx, 16>(bp).ok || cluster_lu_plan<double, 16>(bp).ok) return;      // narrow bands: the cluster-resident LU
     const long long levels = bp.n2 / bp.Lrow;
     if (levels < 8 || bp.p > bp.Lrow + 16 || bp.Lrow < 16) return;                           // (the separator must decouple the two sides)

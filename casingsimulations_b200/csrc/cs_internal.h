@@ -149,6 +149,8 @@ int band_diag_weights(const BandPlan& bp, const double* s_d, int nshift, long lo
 // LU[f][mode] = Kband[mode] + s[f] * diag(mdiag)   (f = 0..nshift-1)
 int band_form_shifted(const BandPlan& bp, const double* s_d /*device, 2 per shift*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st);
 int band_form_shifted_mode(const BandPlan& bp, int mode, const double* s_d, void* LU, cudaStream_t st);
+// twisted halves (BandPlan::twist) of nshift x bp.nmodes systems; mode_base = true theta mode of stored mode 0
+int band_form_twisted(const BandPlan& bp, const double* s_d, int nshift, void* LU, bool lu_cplx, cudaStream_t st, int mode_base);
 // in-place blocked LU without pivoting of nsys_tot = nshift*nmodes band matrices
 int band_factor(const BandPlan& bp, void* LU, bool lu_cplx, int nsys_tot, cudaStream_t st);
 int band_form_and_factor(const BandPlan& bp, const double* s_d /*device*/, int nshift, void* LU, bool lu_cplx, cudaStream_t st, bool allow_twist = true);

@@ -859,11 +859,13 @@ def _run_dist_tool(nproc, args, env=None):
     return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
 
 
-def test_z_slab_solve_single_rank_matches_plain_solve():
+@pytest.mark.parametrize("twist", ["1", "0"])
+def test_z_slab_solve_single_rank_matches_plain_solve(twist):
     """cs_comm_init with ONE rank runs the whole slab code path (local plan, ownership masks, mode-sharded global factors,
-    slab <-> mode transposition) without NCCL: same answer as the plain solve on the same GPU."""
-    # (the slab path factors one-front; its single-GPU partner must too for the 1e-9 comparison of identical arithmetic)
-    res = _run_dist_tool(1, ["4", "25", "17", "compare"], env={"CS_TWIST": "0"})
+    slab <-> mode transposition) without NCCL: same answer as the plain solve on the same GPU -- with the two-front
+    elimination of the global mode systems (default) and with the one-front one; both sides of the comparison use the
+    same elimination, so the arithmetic is identical."""
+    res = _run_dist_tool(1, ["4", "25", "17", "compare"], env={"CS_TWIST": twist})
     print(res)
     assert res["info"]["relres"] <= 1e-10
     assert res["rel_diff_vs_single_gpu_j"] < 1e-9 and res["rel_diff_vs_single_gpu_h"] < 1e-6   # (h carries null-space noise)
@@ -875,7 +877,7 @@ def test_z_slab_solve_two_gpus_matches_single_gpu():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
-    res = _run_dist_tool(2, ["8", "10", "10", "compare"], env={"CS_TWIST": "0"})
+    res = _run_dist_tool(2, ["8", "10", "10", "compare"])
     print(res)
     assert res["n_gpus"] == 2 and res["info"]["relres"] <= 1e-10
     assert res["rel_diff_vs_single_gpu_j"] < 1e-9 and res["rel_diff_vs_single_gpu_h"] < 1e-6
