@@ -139,6 +139,16 @@ def test_top_casing_source():
     assert np.count_nonzero(d) == 2 and np.isclose(d.sum(), 0.0)
     lst = src.srcList
     assert len(lst) == 2 and lst[0].freq == 1.0 and lst[0].s_e.dtype == complex
+    # the sources of one survey carry their shared real parent vector (the solver groups them by it instead of comparing)
+    assert lst[0]._shared_s_e is lst[1]._shared_s_e and lst[0]._shared_s_e.dtype == float
+    assert np.array_equal(lst[0]._shared_s_e, np.real(lst[1].s_e))
+    # the wire checks are memoised per parameter set and dropped with the other derived quantities on assignment
+    assert ("surface wire", (1, 2)) in src._memo_assert_single
+    src.src_b = np.r_[900.0, 0.0, 0.0]
+    assert "_memo_assert_single" not in src.__dict__
+    src.validate()
+    assert ("surface wire", (1, 2)) in src._memo_assert_single
+    src.src_b = np.r_[1000.0, 0.0, 0.0]
     # 3-D: theta must be a cell-centre azimuth
     mp3, mg3 = _casing_setup(8, npadx=4, npadz=6, csz=20.0)
     th = mg3.mesh.vectorCCy[3]
